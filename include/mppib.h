@@ -1,0 +1,222 @@
+/*
+ * mppib.h -- C ABI of the B200-native MPPI rollout path ("mppib" = MPPI on Blackwell).
+ *
+ * This is the drop-in boundary below the Python planner host.  Every entry point
+ * replaces one piece of the reference's hot path (tud-airlab/mppi-isaac @ 2e6d5fb,
+ * paths relative to the reference tree):
+ *
+ *   mppib_sample    <- mppi_torch MPPIPlanner sampling + _bound_action (external dep
+ *                      pinned in poetry.lock:1273-1293; call site mppi_isaac.py:43-49,113)
+ *   mppib_rollout   <- IsaacGymWrapper.apply_robot_cmd + IsaacGymWrapper.step
+ *                      (mppiisaac/planner/isaacgym_wrapper.py:524-572, 639-655), i.e.
+ *                      gym.simulate/fetch_results/refresh_* for all K envs, T times
+ *   mppib_reduce    <- mppi_torch _compute_rollout_costs accumulation + _exp_util
+ *                      (softmax over K) + weighted control sum (call site mppi_isaac.py:113)
+ *   mppib_finalize  <- mppi_torch _update_distribution / U update / savgol filter_u /
+ *                      "return first action" (mppi_isaac.py:84,113)
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no torch types.
+ *   - Pointers without the _h suffix are DEVICE pointers into caller-owned buffers.
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - Every call returns 0 on success, <0 on error; mppib_last_error() gives the text.
+ *   - A handle is bound to one device and is not thread-safe (one handle per GPU).
+ *   - All floating point data is float32 (the reference path is float32 end to end:
+ *     isaacgym_wrapper.py:232,262,612).
+ *
+ * Device data layouts (sample index k is always the innermost, contiguous dimension):
+ *   U        [T][nu]            nominal control sequence (replicated on every GPU)
+ *   actions  [T][nu][K]         clamped perturbed controls actually rolled out
+ *   noise    [T][nu][K]         actions - U (after clamping / null / prior rows)
+ *   state    [NS][K]            per-rollout simulator state, NS = mppib_state_size():
+ *                               rows 0..ndof-1 = q, ndof..2ndof-1 = qdot, then free bodies
+ *   obs      [R][T][K]          observed rows per step, R = mppib_obs_size()
+ *   cost     [T][K]             per-step running cost from Objective.compute_cost
+ *   partial  [2 + T*nu]         (beta_g, eta_g, W_g[T][nu]) of one shard
+ */
+#ifndef MPPIB_H
+#define MPPIB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPPIB_ABI_VERSION 3
+
+#define MPPIB_MAX_BODIES 16   /* moving (1-DoF) bodies of the articulation            */
+#define MPPIB_MAX_LINKS  32   /* URDF links whose state can be observed               */
+#define MPPIB_MAX_NU     16   /* control dimension                                    */
+#define MPPIB_MAX_OBS    64   /* observation items                                    */
+#define MPPIB_MAX_FREE   4    /* free rigid bodies (box / sphere actors)              */
+#define MPPIB_MAX_SHAPES 24   /* collision primitives                                 */
+
+/* joint types (body frame is chosen so the joint axis is +z) */
+#define MPPIB_JOINT_REVOLUTE  0
+#define MPPIB_JOINT_PRISMATIC 1
+
+/* drive modes: isaacgym_wrapper.py:491-507 */
+#define MPPIB_DRIVE_VELOCITY 0   /* stiffness 0, damping 600 */
+#define MPPIB_DRIVE_EFFORT   1   /* stiffness 0, damping 10, armature 0 */
+
+/* observation item kinds (what Objective getters can read, isaacgym_wrapper.py:292-356) */
+#define MPPIB_OBS_LINK_STATE   0  /* 13 floats: pos3 quat_xyzw4 linvel3 angvel3 of link `index`      */
+#define MPPIB_OBS_DOF_STATE    1  /* 2*ndof floats interleaved q0,qd0,q1,qd1 (isaacgym_wrapper.py:190) */
+#define MPPIB_OBS_FREE_STATE   2  /* 13 floats root state of free body `index`                       */
+#define MPPIB_OBS_CONTACT      3  /* 3 floats net contact force on shape-owner `index`               */
+
+/* shape types */
+#define MPPIB_SHAPE_BOX    0
+#define MPPIB_SHAPE_SPHERE 1
+
+/* shape owner kinds */
+#define MPPIB_OWNER_STATIC 0   /* fixed in the world                                   */
+#define MPPIB_OWNER_LINK   1   /* attached to robot link owner_index                   */
+#define MPPIB_OWNER_FREE   2   /* attached to free body owner_index                    */
+
+/* MPPI update modes (mppi_torch `mppi_mode`, conf/mppi/panda.yaml:4 / omnipanda_effort.yaml:4) */
+#define MPPIB_MODE_SIMPLE 0   /* U += sum_k w_k noise_k, cost += lambda U^T Sigma^-1 noise, gamma = 1 */
+#define MPPIB_MODE_MEAN   1   /* "halton-spline" rule: mean <- (1-a) mean + a sum_k w_k action_k, discounted cost */
+
+typedef struct MppibModel {
+    int32_t abi_version;
+    int32_t nb;                 /* moving bodies == ndof                                     */
+    int32_t nlinks;             /* observable links (URDF order, depth first)                */
+    int32_t nu;                 /* command dimension                                         */
+    int32_t drive_mode;
+    int32_t gravity_on;         /* ActorWrapper.gravity (isaacgym_utils.py:24)               */
+    int32_t nfree;              /* free rigid bodies                                         */
+    int32_t nshapes;
+    float   gravity[3];         /* world gravity (0,0,-9.8): isaacgym_wrapper.py:29          */
+    float   base_pos[3];        /* robot base pose in the world (actor root state)           */
+    float   base_quat[4];       /* xyzw                                                      */
+
+    /* articulation, topologically sorted; parent -1 = fixed base */
+    int32_t parent[MPPIB_MAX_BODIES];
+    int32_t jtype[MPPIB_MAX_BODIES];
+    float   tree_R[MPPIB_MAX_BODIES][9];   /* rotation body(q=0) -> parent body coords, row major */
+    float   tree_p[MPPIB_MAX_BODIES][3];   /* body origin in parent body coords                   */
+    float   tree_quat[MPPIB_MAX_BODIES][4];/* tree_R as a unit quaternion, xyzw                   */
+    float   mass[MPPIB_MAX_BODIES];
+    float   mcom[MPPIB_MAX_BODIES][3];     /* mass * centre of mass, body coords                  */
+    float   inertia[MPPIB_MAX_BODIES][6];  /* about the body origin: xx yy zz xy xz yz            */
+    float   q_lo[MPPIB_MAX_BODIES];
+    float   q_hi[MPPIB_MAX_BODIES];
+    float   qd_max[MPPIB_MAX_BODIES];
+    float   effort[MPPIB_MAX_BODIES];
+    float   damping[MPPIB_MAX_BODIES];     /* URDF <dynamics damping>                             */
+    float   kd[MPPIB_MAX_BODIES];          /* drive damping gain                                  */
+    float   armature[MPPIB_MAX_BODIES];
+
+    /* command map, apply_robot_cmd/_ik (isaacgym_wrapper.py:510-572):
+       target[i] = cmd_c0[i]*u[cmd_i0[i]] + cmd_c1[i]*u[cmd_i1[i]] */
+    int32_t cmd_i0[MPPIB_MAX_BODIES];
+    int32_t cmd_i1[MPPIB_MAX_BODIES];
+    float   cmd_c0[MPPIB_MAX_BODIES];
+    float   cmd_c1[MPPIB_MAX_BODIES];
+
+    /* observable links: pose of the link frame in its owning body's frame */
+    int32_t link_body[MPPIB_MAX_LINKS];    /* -1 = rigidly attached to the base                   */
+    float   link_R[MPPIB_MAX_LINKS][9];
+    float   link_p[MPPIB_MAX_LINKS][3];
+    float   link_quat[MPPIB_MAX_LINKS][4]; /* link_R as a unit quaternion, xyzw                   */
+
+    /* free rigid bodies (box / sphere actors that are not fixed) */
+    float   free_mass[MPPIB_MAX_FREE];
+    float   free_inertia[MPPIB_MAX_FREE][3];   /* principal, body frame                           */
+    int32_t free_gravity[MPPIB_MAX_FREE];
+
+    /* collision primitives */
+    int32_t shape_type[MPPIB_MAX_SHAPES];
+    int32_t shape_owner_kind[MPPIB_MAX_SHAPES];
+    int32_t shape_owner[MPPIB_MAX_SHAPES];
+    int32_t shape_contact_slot[MPPIB_MAX_SHAPES]; /* row of the net-contact-force table, -1 none  */
+    float   shape_size[MPPIB_MAX_SHAPES][3];   /* box half extents / sphere radius in [0]         */
+    float   shape_pos[MPPIB_MAX_SHAPES][3];    /* pose in the owner frame (world for static)      */
+    float   shape_quat[MPPIB_MAX_SHAPES][4];
+    float   shape_friction[MPPIB_MAX_SHAPES];
+    int32_t ncontact_slots;
+    int32_t ground_plane;                  /* add_ground_plane (isaacgym_utils.py:61-68)          */
+    float   contact_kp;                    /* penalty stiffness  [N/m]                            */
+    float   contact_kd;                    /* penalty damping    [N s/m]                          */
+} MppibModel;
+
+typedef struct MppibObsItem {
+    int32_t kind;
+    int32_t index;
+} MppibObsItem;
+
+typedef struct MppibParams {
+    int32_t K;                 /* samples on THIS device                                   */
+    int32_t T;                 /* horizon                                                  */
+    int32_t substeps;          /* isaacgym_wrapper.py:24                                   */
+    float   dt;                /* model step; substep h = dt/substeps                      */
+    int32_t mode;              /* MPPIB_MODE_*                                             */
+    float   lambda_;           /* temperature                                              */
+    float   gamma;             /* rollout_var_discount (used by MODE_MEAN)                 */
+    float   step_size_mean;    /* 0.98 in mppi_torch                                       */
+    float   u_scale;
+    int32_t sample_null_action;/* global row K-1 := 0                                      */
+    int32_t filter_u;          /* Savitzky-Golay window 9 order 2 on U (needs T >= 9)      */
+    float   u_min[MPPIB_MAX_NU];
+    float   u_max[MPPIB_MAX_NU];
+    float   u_init[MPPIB_MAX_NU];
+    float   sigma_chol[MPPIB_MAX_NU * MPPIB_MAX_NU]; /* lower Cholesky factor of noise_sigma, row major nu x nu */
+    float   sigma_inv[MPPIB_MAX_NU * MPPIB_MAX_NU];  /* inverse of noise_sigma, row major nu x nu               */
+    int32_t nobs;
+    MppibObsItem obs[MPPIB_MAX_OBS];
+} MppibParams;
+
+typedef struct MppibContext* MppibHandle;
+
+/* lifetime ------------------------------------------------------------------------------- */
+int32_t mppib_abi_version(void);
+const char* mppib_last_error(void);
+int32_t mppib_create(const MppibModel* model_h, const MppibParams* params_h, int32_t device, MppibHandle* out);
+int32_t mppib_destroy(MppibHandle h);
+/* replaces the parameter block (update_mppi_params, mppi_isaac.py:129-138); K, T and obs may change */
+int32_t mppib_set_params(MppibHandle h, const MppibParams* params_h);
+/* replaces the model block (base pose / obstacle poses change between plans) */
+int32_t mppib_set_model(MppibHandle h, const MppibModel* model_h);
+int32_t mppib_state_size(MppibHandle h);   /* NS: rows of the state buffer             */
+int32_t mppib_obs_size(MppibHandle h);     /* R: rows of the obs buffer                */
+
+/* hot path ------------------------------------------------------------------------------- */
+/* K1: Philox-4x32-10 Gaussian draw (key = seed, plan_idx; counter = global sample index
+ * k_offset + k, t, block) -> noise = L z, action = clamp(u_scale-free U + noise, u_min, u_max),
+ * noise := action - U; global row k_global == K_total-1 is the null action when enabled;
+ * row K_total-2 is overwritten with prior_row[T][nu] when prior_row != NULL.  plan_ctr (device,
+ * nullable) is added to plan_idx on the device so that a captured CUDA graph draws fresh noise on
+ * every replay (mppib_shift increments it).                                                  */
+int32_t mppib_sample(MppibHandle h, uint64_t seed, uint64_t plan_idx, const uint32_t* plan_ctr,
+                     uint32_t k_offset, uint32_t k_total, const float* U, const float* prior_row,
+                     float* actions, float* noise, void* stream);
+
+/* K2: broadcast initial state state0[NS] (one row, shared by all K) or continue from
+ * state[NS][K] when state0 == NULL; apply actions[t0 .. t0+nsteps) ; write obs and the
+ * final state.  nsteps == T for a whole plan, 1 for the reference's step-wise protocol,
+ * 0 to only write the observation of the current state into slot t0.                        */
+int32_t mppib_rollout(MppibHandle h, const float* state0, float* state, const float* actions,
+                      int32_t t0, int32_t nsteps, float* obs, void* stream);
+
+/* K3: S_k = sum_t gamma^t cost[t][k] (+ lambda sum_t U_t^T Sigma^-1 noise_k,t in SIMPLE mode),
+ * beta_g = min_k S_k, w_k = exp(-(S_k - beta_g)/lambda), eta_g = sum w_k,
+ * W_g[t][j] = sum_k w_k x[t][j][k] with x = noise (SIMPLE) or actions (MEAN).
+ * Single pass over HBM; the last CTA to finish folds the per-CTA partials.                  */
+int32_t mppib_reduce(MppibHandle h, const float* cost, const float* x, const float* U,
+                     float* partial, void* stream);
+
+/* K4: combine G shard partials, update U in place, optional savgol, write action_out[nu]
+ * (= first row of U), and weights statistics stats[2] = (beta, eta).                        */
+int32_t mppib_finalize(MppibHandle h, const float* partials, int32_t G, float* U,
+                       float* action_out, float* stats, void* stream);
+
+/* shift U by one step: U[t] <- U[t+1], U[T-1] <- u_init (mppi_torch command() prologue);
+ * increments *plan_ctr (device, nullable) by one.                                            */
+int32_t mppib_shift(MppibHandle h, float* U, uint32_t* plan_ctr, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPPIB_H */

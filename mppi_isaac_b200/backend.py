@@ -1,0 +1,138 @@
+"""ctypes binding of ``libmppib.so`` (the C ABI in ``include/mppib.h``).
+
+This is the only compute backend the package ships.  There is NO CPU fallback: if the CUDA
+library is missing or no sm_100a device is visible, construction fails loudly.  Device
+memory, streams and ``torch.distributed`` come from PyTorch (plumbing); every kernel on the
+hot path is ours.  Tensors are passed as raw ``data_ptr()``s, the stream as
+``torch.cuda.current_stream().cuda_stream`` -- no torch types cross the ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from .model.blob import ABI_VERSION, MppibModel, MppibParams
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmppib.so")
+_lib = None
+
+SYMBOLS = [
+    "mppib_abi_version", "mppib_last_error", "mppib_create", "mppib_destroy", "mppib_set_params",
+    "mppib_set_model", "mppib_state_size", "mppib_obs_size", "mppib_sample", "mppib_rollout",
+    "mppib_reduce", "mppib_finalize", "mppib_shift",
+]
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load_library():
+    """dlopen libmppib.so; raises if it was not built (``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(
+            f"{_LIB_PATH} not found: the CUDA extension is not built. Run `python __graft_entry__.py` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(_LIB_PATH)
+    lib.mppib_last_error.restype = C.c_char_p
+    for name in SYMBOLS:
+        if name != "mppib_last_error":
+            getattr(lib, name).restype = C.c_int32
+    if lib.mppib_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libmppib.so ABI {lib.mppib_abi_version()} != python binding {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+class CudaBackend:
+    """One handle per GPU (``MppibHandle``).  All tensor arguments must live on ``self.device``."""
+
+    name = "cuda"
+
+    def __init__(self, device):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError(
+                f"mppi_isaac_b200 runs its hot path as sm_100a CUDA kernels only; device '{device}' is not a CUDA "
+                "device and there is no CPU fallback (the reference's CPU pipeline is reproduced by oracle/ for tests only)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device visible: mppi_isaac_b200 has no CPU fallback")
+        self.lib = load_library()
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        self.handle = C.c_void_p(0)
+        self.model = None
+        self.params = None
+        self.launches = 0   # kernels launched through this handle (bench.py's gpu_launches)
+
+    # -- lifetime -------------------------------------------------------------------------------
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.mppib_last_error().decode()}")
+
+    def create(self, model: MppibModel, params: MppibParams):
+        if self.handle:
+            self.destroy()
+        self.model, self.params = model, params
+        self._check(self.lib.mppib_create(C.byref(model), C.byref(params), C.c_int32(self.device.index), C.byref(self.handle)), "mppib_create")
+
+    def destroy(self):
+        if self.handle:
+            self.lib.mppib_destroy(self.handle)
+            self.handle = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    def set_params(self, params: MppibParams):
+        self.params = params
+        self._check(self.lib.mppib_set_params(self.handle, C.byref(params)), "mppib_set_params")
+
+    def set_model(self, model: MppibModel):
+        self.model = model
+        self._check(self.lib.mppib_set_model(self.handle, C.byref(model)), "mppib_set_model")
+
+    def state_size(self) -> int:
+        return int(self.lib.mppib_state_size(self.handle))
+
+    def obs_size(self) -> int:
+        return int(self.lib.mppib_obs_size(self.handle))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # -- hot path -------------------------------------------------------------------------------
+    def sample(self, seed, plan_idx, k_offset, k_total, U, prior_row, actions, noise, plan_ctr=None):
+        self.launches += 1
+        self._check(self.lib.mppib_sample(self.handle, C.c_uint64(seed), C.c_uint64(plan_idx), _ptr(plan_ctr), C.c_uint32(k_offset), C.c_uint32(k_total),
+                                          _ptr(U), _ptr(prior_row), _ptr(actions), _ptr(noise), self._stream()), "mppib_sample")
+
+    def rollout(self, state0, state, actions, t0, nsteps, obs, act_t0=0):
+        """``actions`` holds time slices [act_t0, ...) laid out [t][nu][K]; steps t0..t0+nsteps-1 are executed."""
+        self.launches += 1
+        base = actions.data_ptr() - act_t0 * self.model.nu * self.params.K * 4
+        self._check(self.lib.mppib_rollout(self.handle, _ptr(state0), _ptr(state), C.c_void_p(base), C.c_int32(t0), C.c_int32(nsteps),
+                                           _ptr(obs), self._stream()), "mppib_rollout")
+
+    def reduce(self, cost, x, U, partial):
+        self.launches += 1
+        self._check(self.lib.mppib_reduce(self.handle, _ptr(cost), _ptr(x), _ptr(U), _ptr(partial), self._stream()), "mppib_reduce")
+
+    def finalize(self, partials, G, U, action_out, stats):
+        self.launches += 1
+        self._check(self.lib.mppib_finalize(self.handle, _ptr(partials), C.c_int32(G), _ptr(U), _ptr(action_out), _ptr(stats), self._stream()), "mppib_finalize")
+
+    def shift(self, U, plan_ctr=None):
+        self.launches += 1
+        self._check(self.lib.mppib_shift(self.handle, _ptr(U), _ptr(plan_ctr), self._stream()), "mppib_shift")

@@ -1,0 +1,150 @@
+// api.cu -- the C ABI of include/mppib.h (handle lifetime + thin launch wrappers).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void mppib_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int reduce_grid_size(const MppibContext* c);
+
+static int validate(const MppibModel* m, const MppibParams* p) {
+    MPPIB_REQUIRE(m != nullptr && p != nullptr, "null model/params");
+    MPPIB_REQUIRE(m->abi_version == MPPIB_ABI_VERSION, "model abi_version %d != library %d", m->abi_version, MPPIB_ABI_VERSION);
+    MPPIB_REQUIRE(m->nb >= 1 && m->nb <= MPPIB_MAX_BODIES, "nb=%d out of range", m->nb);
+    MPPIB_REQUIRE(m->nlinks >= 0 && m->nlinks <= MPPIB_MAX_LINKS, "nlinks=%d out of range", m->nlinks);
+    MPPIB_REQUIRE(m->nu >= 1 && m->nu <= MPPIB_MAX_NU, "nu=%d out of range", m->nu);
+    MPPIB_REQUIRE(m->nfree == 0 && m->nshapes == 0, "free bodies / contact shapes are not supported by this build");
+    for (int i = 0; i < m->nb; ++i) {
+        MPPIB_REQUIRE(m->parent[i] >= -1 && m->parent[i] < i, "parent[%d]=%d is not topologically sorted", i, m->parent[i]);
+        MPPIB_REQUIRE(m->cmd_i0[i] >= 0 && m->cmd_i0[i] < m->nu && m->cmd_i1[i] >= 0 && m->cmd_i1[i] < m->nu, "cmd map of dof %d out of range", i);
+    }
+    MPPIB_REQUIRE(p->K >= 4 && p->K % 4 == 0, "K=%d must be a positive multiple of 4 (128-bit loads)", p->K);
+    MPPIB_REQUIRE(p->T >= 1 && p->substeps >= 1 && p->dt > 0.f, "bad T/substeps/dt");
+    MPPIB_REQUIRE(p->lambda_ > 0.f, "lambda must be positive");
+    MPPIB_REQUIRE(!(p->filter_u && p->T < 9), "filter_u needs T >= 9");
+    MPPIB_REQUIRE(p->nobs >= 0 && p->nobs <= MPPIB_MAX_OBS, "nobs out of range");
+    for (int i = 0; i < p->nobs; ++i) {
+        const int kd = p->obs[i].kind, ix = p->obs[i].index;
+        MPPIB_REQUIRE(kd >= 0 && kd <= MPPIB_OBS_CONTACT, "obs[%d].kind invalid", i);
+        if (kd == MPPIB_OBS_LINK_STATE) MPPIB_REQUIRE(ix >= 0 && ix < m->nlinks, "obs[%d] link index %d out of range", i, ix);
+    }
+    return 0;
+}
+
+static void derive(MppibContext* c) {
+    int r = 0;
+    for (int i = 0; i < c->params.nobs; ++i) r += obs_item_width(c->model, c->params.obs[i].kind);
+    c->obs_rows = r;
+    c->state_rows = 2 * c->model.nb + 13 * c->model.nfree;
+}
+
+static int alloc_scratch(MppibContext* c) {
+    if (c->reduce_scratch) { cudaFree(c->reduce_scratch); c->reduce_scratch = nullptr; }
+    c->reduce_max_ctas = c->num_sms * 4;
+    const size_t P = 2 + (size_t)c->params.T * c->model.nu;
+    MPPIB_CHECK_CUDA(cudaMalloc(&c->reduce_scratch, sizeof(float) * P * c->reduce_max_ctas));
+    if (!c->reduce_ticket) {
+        MPPIB_CHECK_CUDA(cudaMalloc(&c->reduce_ticket, sizeof(unsigned int)));
+        MPPIB_CHECK_CUDA(cudaMemset(c->reduce_ticket, 0, sizeof(unsigned int)));
+    }
+    return 0;
+}
+
+extern "C" {
+
+int32_t mppib_abi_version(void) { return MPPIB_ABI_VERSION; }
+const char* mppib_last_error(void) { return g_err; }
+
+int32_t mppib_create(const MppibModel* model_h, const MppibParams* params_h, int32_t device, MppibHandle* out) {
+    MPPIB_REQUIRE(out != nullptr, "null out handle");
+    if (int rc = validate(model_h, params_h)) return rc;
+    int ndev = 0;
+    MPPIB_CHECK_CUDA(cudaGetDeviceCount(&ndev));
+    MPPIB_REQUIRE(device >= 0 && device < ndev, "device %d not present (%d CUDA devices)", device, ndev);
+    MPPIB_CHECK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MPPIB_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    MPPIB_REQUIRE(prop.major == 10, "this library is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    MppibContext* c = new MppibContext();
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    c->model = *model_h;
+    c->params = *params_h;
+    c->num_sms = prop.multiProcessorCount;
+    derive(c);
+    if (int rc = alloc_scratch(c)) { delete c; return rc; }
+    *out = c;
+    return 0;
+}
+
+int32_t mppib_destroy(MppibHandle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->reduce_scratch) cudaFree(h->reduce_scratch);
+    if (h->reduce_ticket) cudaFree(h->reduce_ticket);
+    delete h;
+    return 0;
+}
+
+int32_t mppib_set_params(MppibHandle h, const MppibParams* params_h) {
+    MPPIB_REQUIRE(h != nullptr, "null handle");
+    if (int rc = validate(&h->model, params_h)) return rc;
+    const bool resize = params_h->T != h->params.T;
+    h->params = *params_h;
+    derive(h);
+    if (resize) { MPPIB_CHECK_CUDA(cudaSetDevice(h->device)); return alloc_scratch(h); }
+    return 0;
+}
+
+int32_t mppib_set_model(MppibHandle h, const MppibModel* model_h) {
+    MPPIB_REQUIRE(h != nullptr, "null handle");
+    if (int rc = validate(model_h, &h->params)) return rc;
+    const bool resize = model_h->nu != h->model.nu;
+    h->model = *model_h;
+    derive(h);
+    if (resize) { MPPIB_CHECK_CUDA(cudaSetDevice(h->device)); return alloc_scratch(h); }
+    return 0;
+}
+
+int32_t mppib_state_size(MppibHandle h) { return h ? h->state_rows : -1; }
+int32_t mppib_obs_size(MppibHandle h) { return h ? h->obs_rows : -1; }
+
+int32_t mppib_sample(MppibHandle h, uint64_t seed, uint64_t plan_idx, const uint32_t* plan_ctr, uint32_t k_offset, uint32_t k_total, const float* U,
+                     const float* prior_row, float* actions, float* noise, void* stream) {
+    MPPIB_REQUIRE(h && U && actions, "mppib_sample: null argument");
+    MPPIB_REQUIRE((uint64_t)k_offset + (uint64_t)h->params.K <= (uint64_t)k_total, "mppib_sample: shard [%u,+%d) exceeds k_total %u", k_offset, h->params.K, k_total);
+    return launch_sample(h, seed, plan_idx, plan_ctr, k_offset, k_total, U, prior_row, actions, noise, (cudaStream_t)stream);
+}
+
+int32_t mppib_rollout(MppibHandle h, const float* state0, float* state, const float* actions, int32_t t0, int32_t nsteps,
+                      float* obs, void* stream) {
+    MPPIB_REQUIRE(h && actions, "mppib_rollout: null argument");
+    MPPIB_REQUIRE(state0 || state, "mppib_rollout: need state0 (broadcast) or state (continue)");
+    MPPIB_REQUIRE(t0 >= 0 && nsteps >= 0 && t0 + (nsteps > 0 ? nsteps : 1) <= h->params.T, "mppib_rollout: steps [%d,%d) outside horizon %d", t0, t0 + nsteps, h->params.T);
+    return launch_rollout(h, state0, state, actions, t0, nsteps, obs, (cudaStream_t)stream);
+}
+
+int32_t mppib_reduce(MppibHandle h, const float* cost, const float* x, const float* U, float* partial, void* stream) {
+    MPPIB_REQUIRE(h && cost && x && U && partial, "mppib_reduce: null argument");
+    MPPIB_REQUIRE(((uintptr_t)cost & 15) == 0 && ((uintptr_t)x & 15) == 0, "mppib_reduce: cost/x must be 16-byte aligned");
+    return launch_reduce(h, cost, x, U, partial, (cudaStream_t)stream);
+}
+
+int32_t mppib_finalize(MppibHandle h, const float* partials, int32_t G, float* U, float* action_out, float* stats, void* stream) {
+    MPPIB_REQUIRE(h && partials && U && action_out && G >= 1, "mppib_finalize: bad argument");
+    return launch_finalize(h, partials, G, U, action_out, stats, (cudaStream_t)stream);
+}
+
+int32_t mppib_shift(MppibHandle h, float* U, uint32_t* plan_ctr, void* stream) {
+    MPPIB_REQUIRE(h && U, "mppib_shift: null argument");
+    return launch_shift(h, U, plan_ctr, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,56 @@
+// common.cuh -- shared declarations of the mppib CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/mppib.h"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing: no exceptions cross the C ABI; mppib_last_error() returns the last message
+// ------------------------------------------------------------------------------------------
+void mppib_set_error(const char* fmt, ...);
+
+#define MPPIB_CHECK_CUDA(expr)                                                              \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            mppib_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return -2;                                                                      \
+        }                                                                                   \
+    } while (0)
+
+#define MPPIB_REQUIRE(cond, ...)                                                            \
+    do {                                                                                    \
+        if (!(cond)) {                                                                      \
+            mppib_set_error(__VA_ARGS__);                                                   \
+            return -1;                                                                      \
+        }                                                                                   \
+    } while (0)
+
+struct MppibContext {
+    int device;
+    MppibModel model;
+    MppibParams params;
+    int obs_rows;            // R
+    int state_rows;          // NS
+    int num_sms;
+    // K3 scratch: per-CTA partials + ticket counter (device memory owned by the handle)
+    float* reduce_scratch;   // [max_ctas][2 + T*nu]
+    unsigned int* reduce_ticket;
+    int reduce_max_ctas;
+};
+
+// kernel launchers (defined in the .cu files)
+int launch_sample(MppibContext* c, uint64_t seed, uint64_t plan_idx, const uint32_t* plan_ctr, uint32_t k_offset, uint32_t k_total,
+                  const float* U, const float* prior_row, float* actions, float* noise, cudaStream_t s);
+int launch_rollout(MppibContext* c, const float* state0, float* state, const float* actions, int t0, int nsteps,
+                   float* obs, cudaStream_t s);
+int launch_reduce(MppibContext* c, const float* cost, const float* x, const float* U, float* partial, cudaStream_t s);
+int launch_finalize(MppibContext* c, const float* partials, int G, float* U, float* action_out, float* stats, cudaStream_t s);
+int launch_shift(MppibContext* c, float* U, uint32_t* plan_ctr, cudaStream_t s);
+
+static inline int obs_item_width(const MppibModel& m, int kind) {
+    return kind == MPPIB_OBS_DOF_STATE ? 2 * m.nb : (kind == MPPIB_OBS_CONTACT ? 3 : 13);
+}

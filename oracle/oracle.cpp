@@ -1,0 +1,511 @@
+// oracle.cpp -- CPU restatement of the MPPI rollout hot path.  TEST INFRASTRUCTURE ONLY.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+// load this library; the product package never imports it (it fails loudly without CUDA).
+//
+// PARITY UNPINNED: the arithmetic of this path lives in two third-party engines that are not
+// in /root/reference and cannot be installed here -- mppi_torch @75e17e87 (pyproject.toml:20,
+// poetry.lock:1273-1293) and IsaacGym 1.0rc4 / PhysX (pyproject.toml:16, thirdparty/README.md:3).
+// The reference ships no golden vectors for them.  This file therefore
+// restates the *pipeline* the reference source does pin, function by function:
+//
+//   oracle_sample    : mppi_torch "simple"/"random" Gaussian draw + _bound_action + null/prior rows
+//                      (spec: SURVEY.md 8(a) M4/M5; row K-1 null action, row K-2 prior,
+//                      mppiisaac/priors/fabrics_point.py:20 env_id=-2)
+//   oracle_rollout   : IsaacGymWrapper.apply_robot_cmd + step for K envs, T times
+//                      (mppiisaac/planner/isaacgym_wrapper.py:510-572 command map and diff-drive IK,
+//                       :639-655 step order command -> simulate -> observe, :21-39 dt/substeps/gravity,
+//                       :491-507 drive gains, :186-199 tensor layouts)
+//   oracle_reduce    : mppi_torch _compute_rollout_costs accumulation, _exp_util, weighted sum
+//                      
+//   oracle_finalize  : shard combine + _update_distribution + savgol (Appendix C)
+//
+// It is written for clarity, not speed: dense 6x6 spatial algebra (Featherstone's ABA), no
+// structure exploitation, optional float64 to quantify float32 round-off of the CUDA path.
+// What pins it: tests/test_oracle_*.py (FK golden values of SURVEY Appendix B, an independent
+// numpy CRBA/RNEA mass-matrix solve, scipy savgol, torch softmax, analytic drive response).
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+#include <algorithm>
+#include <limits>
+
+#include "../include/mppib.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// Philox-4x32-10 (Salmon et al. 2011).  key = (seed_lo, seed_hi ^ plan_lo), counter =
+// (global sample index, t, block, plan_hi).
+// ------------------------------------------------------------------------------------------
+struct U4 { uint32_t x, y, z, w; };
+
+inline U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)M0 * c.x, p1 = (uint64_t)M1 * c.z;
+        U4 n;
+        n.x = (uint32_t)(p1 >> 32) ^ c.y ^ k0;
+        n.y = (uint32_t)p1;
+        n.z = (uint32_t)(p0 >> 32) ^ c.w ^ k1;
+        n.w = (uint32_t)p0;
+        c = n;
+        k0 += W0; k1 += W1;
+    }
+    return c;
+}
+
+inline float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+// Box-Muller in double, rounded to float: the reference value the CUDA fast path is held to.
+inline void box_muller(uint32_t a, uint32_t b, float* z0, float* z1) {
+    double u0 = (double)u01(a), u1 = (double)u01(b);
+    double r = std::sqrt(-2.0 * std::log(u0));
+    double th = 2.0 * M_PI * u1;
+    *z0 = (float)(r * std::cos(th));
+    *z1 = (float)(r * std::sin(th));
+}
+
+template <class F>
+void parallel_for(int n, int nthreads, F f) {
+    if (nthreads <= 1 || n < 2 * nthreads) { f(0, n); return; }
+    std::vector<std::thread> th;
+    int chunk = (n + nthreads - 1) / nthreads;
+    for (int i = 0; i < nthreads; ++i) {
+        int a = i * chunk, b = std::min(n, a + chunk);
+        if (a >= b) break;
+        th.emplace_back([=]() { f(a, b); });
+    }
+    for (auto& t : th) t.join();
+}
+
+// ------------------------------------------------------------------------------------------
+// dense spatial algebra, motion vectors [w; v], force vectors [n; f]
+// ------------------------------------------------------------------------------------------
+template <class S> struct M3 { S a[3][3]; };
+template <class S> struct V6 { S a[6]; };
+template <class S> struct M6 { S a[6][6]; };
+
+template <class S> void cross3(const S* a, const S* b, S* o) {
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// Pluecker motion transform parent->child coords for a child frame at (R: child axes as columns
+// in parent coords, p: child origin in parent coords):  X = [E 0; -E p^x  E],  E = R^T.
+template <class S> M6<S> plucker(const M3<S>& R, const S* p) {
+    M6<S> X; std::memset(&X, 0, sizeof(X));
+    S E[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) E[i][j] = R.a[j][i];
+    S px[3][3] = {{0, -p[2], p[1]}, {p[2], 0, -p[0]}, {-p[1], p[0], 0}};
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        X.a[i][j] = E[i][j]; X.a[i + 3][j + 3] = E[i][j];
+        S s = 0; for (int k = 0; k < 3; ++k) s += E[i][k] * px[k][j];
+        X.a[i + 3][j] = -s;
+    }
+    return X;
+}
+template <class S> V6<S> mulXv(const M6<S>& X, const V6<S>& v) {
+    V6<S> o; for (int i = 0; i < 6; ++i) { S s = 0; for (int j = 0; j < 6; ++j) s += X.a[i][j] * v.a[j]; o.a[i] = s; } return o;
+}
+template <class S> V6<S> mulXTf(const M6<S>& X, const V6<S>& f) {
+    V6<S> o; for (int i = 0; i < 6; ++i) { S s = 0; for (int j = 0; j < 6; ++j) s += X.a[j][i] * f.a[j]; o.a[i] = s; } return o;
+}
+// crm(v) m  (motion cross motion)
+template <class S> V6<S> crm(const V6<S>& v, const V6<S>& m) {
+    V6<S> o; S t[3];
+    cross3(&v.a[0], &m.a[0], &o.a[0]);
+    cross3(&v.a[0], &m.a[3], &o.a[3]); cross3(&v.a[3], &m.a[0], t);
+    for (int i = 0; i < 3; ++i) o.a[3 + i] += t[i];
+    return o;
+}
+// crf(v) f  (motion cross force)
+template <class S> V6<S> crf(const V6<S>& v, const V6<S>& f) {
+    V6<S> o; S t[3];
+    cross3(&v.a[0], &f.a[0], &o.a[0]); cross3(&v.a[3], &f.a[3], t);
+    for (int i = 0; i < 3; ++i) o.a[i] += t[i];
+    cross3(&v.a[0], &f.a[3], &o.a[3]);
+    return o;
+}
+template <class S> M6<S> spatial_inertia(S m, const float* h, const float* I6) {
+    // [[I_o, h^x], [-(h^x), m 1]] with h = m*com, I_o about the body origin
+    M6<S> I; std::memset(&I, 0, sizeof(I));
+    S Io[3][3] = {{(S)I6[0], (S)I6[3], (S)I6[4]}, {(S)I6[3], (S)I6[1], (S)I6[5]}, {(S)I6[4], (S)I6[5], (S)I6[2]}};
+    S hx[3][3] = {{0, -(S)h[2], (S)h[1]}, {(S)h[2], 0, -(S)h[0]}, {-(S)h[1], (S)h[0], 0}};
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        I.a[i][j] = Io[i][j]; I.a[i][j + 3] = hx[i][j]; I.a[i + 3][j] = -hx[i][j];
+    }
+    for (int i = 0; i < 3; ++i) I.a[i + 3][i + 3] = m;
+    return I;
+}
+template <class S> void quat_mul(const S* a, const S* b, S* o) {  // xyzw
+    S x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    S y = a[3] * b[1] - a[0] * b[2] + a[1] * b[3] + a[2] * b[0];
+    S z = a[3] * b[2] + a[0] * b[1] - a[1] * b[0] + a[2] * b[3];
+    S w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+    o[0] = x; o[1] = y; o[2] = z; o[3] = w;
+}
+template <class S> M3<S> quat_to_R(const S* q) {
+    S x = q[0], y = q[1], z = q[2], w = q[3];
+    M3<S> R = {{{1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)},
+                {2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)},
+                {2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)}}};
+    return R;
+}
+
+// ------------------------------------------------------------------------------------------
+// articulated-body forward dynamics of one substep
+// ------------------------------------------------------------------------------------------
+template <class S>
+struct Articulation {
+    const MppibModel* m;
+    int nb;
+    M3<S> Rl[MPPIB_MAX_BODIES];   // body->parent rotation at the current q
+    S pl[MPPIB_MAX_BODIES][3];
+    M6<S> X[MPPIB_MAX_BODIES];
+    V6<S> v[MPPIB_MAX_BODIES], c[MPPIB_MAX_BODIES], pbias[MPPIB_MAX_BODIES];
+    V6<S> a0;                      // base acceleration (= -gravity in base coords)
+
+    void kinematics(const S* q, const S* qd) {
+        for (int i = 0; i < nb; ++i) {
+            M3<S> Rt; for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc) Rt.a[r][cc] = (S)m->tree_R[i][3 * r + cc];
+            if (m->jtype[i] == MPPIB_JOINT_REVOLUTE) {
+                S cq = std::cos(q[i]), sq = std::sin(q[i]);
+                for (int r = 0; r < 3; ++r) {   // Rt * Rz(q)
+                    Rl[i].a[r][0] = Rt.a[r][0] * cq + Rt.a[r][1] * sq;
+                    Rl[i].a[r][1] = -Rt.a[r][0] * sq + Rt.a[r][1] * cq;
+                    Rl[i].a[r][2] = Rt.a[r][2];
+                }
+                for (int r = 0; r < 3; ++r) pl[i][r] = (S)m->tree_p[i][r];
+            } else {
+                Rl[i] = Rt;
+                for (int r = 0; r < 3; ++r) pl[i][r] = (S)m->tree_p[i][r] + Rt.a[r][2] * q[i];
+            }
+            X[i] = plucker(Rl[i], pl[i]);
+            V6<S> vp; std::memset(&vp, 0, sizeof(vp));
+            if (m->parent[i] >= 0) vp = v[m->parent[i]];
+            V6<S> vj; std::memset(&vj, 0, sizeof(vj));
+            vj.a[m->jtype[i] == MPPIB_JOINT_REVOLUTE ? 2 : 5] = qd[i];
+            v[i] = mulXv(X[i], vp);
+            for (int k = 0; k < 6; ++k) v[i].a[k] += vj.a[k];
+            c[i] = crm(v[i], vj);
+        }
+    }
+
+    // one ABA solve; tau = explicit joint force, dimp = implicit diagonal added to D (h*(kd+damping)+armature)
+    void aba(const S* tau, const S* dimp, S* qdd) {
+        M6<S> IA[MPPIB_MAX_BODIES]; V6<S> pA[MPPIB_MAX_BODIES];
+        V6<S> U[MPPIB_MAX_BODIES]; S D[MPPIB_MAX_BODIES], u[MPPIB_MAX_BODIES];
+        for (int i = 0; i < nb; ++i) {
+            IA[i] = spatial_inertia<S>((S)m->mass[i], m->mcom[i], m->inertia[i]);
+            V6<S> Iv = mulXv(IA[i], v[i]);
+            pA[i] = crf(v[i], Iv);
+        }
+        for (int i = nb - 1; i >= 0; --i) {
+            int s = m->jtype[i] == MPPIB_JOINT_REVOLUTE ? 2 : 5;
+            for (int k = 0; k < 6; ++k) U[i].a[k] = IA[i].a[k][s];
+            D[i] = U[i].a[s] + dimp[i];
+            u[i] = tau[i] - pA[i].a[s];
+            int p = m->parent[i];
+            if (p >= 0) {
+                M6<S> Ia; V6<S> pa;
+                for (int r = 0; r < 6; ++r) for (int cc = 0; cc < 6; ++cc) Ia.a[r][cc] = IA[i].a[r][cc] - U[i].a[r] * U[i].a[cc] / D[i];
+                V6<S> Iac = mulXv(Ia, c[i]);
+                for (int k = 0; k < 6; ++k) pa.a[k] = pA[i].a[k] + Iac.a[k] + U[i].a[k] * (u[i] / D[i]);
+                // IA[p] += X^T Ia X ; pA[p] += X^T pa
+                M6<S> T;
+                for (int r = 0; r < 6; ++r) for (int cc = 0; cc < 6; ++cc) { S sum = 0; for (int k = 0; k < 6; ++k) sum += Ia.a[r][k] * X[i].a[k][cc]; T.a[r][cc] = sum; }
+                for (int r = 0; r < 6; ++r) for (int cc = 0; cc < 6; ++cc) { S sum = 0; for (int k = 0; k < 6; ++k) sum += X[i].a[k][r] * T.a[k][cc]; IA[p].a[r][cc] += sum; }
+                V6<S> pp = mulXTf(X[i], pa);
+                for (int k = 0; k < 6; ++k) pA[p].a[k] += pp.a[k];
+            }
+        }
+        V6<S> acc[MPPIB_MAX_BODIES];
+        for (int i = 0; i < nb; ++i) {
+            int s = m->jtype[i] == MPPIB_JOINT_REVOLUTE ? 2 : 5;
+            V6<S> ap = m->parent[i] >= 0 ? acc[m->parent[i]] : a0;
+            V6<S> a = mulXv(X[i], ap);
+            for (int k = 0; k < 6; ++k) a.a[k] += c[i].a[k];
+            S dot = 0; for (int k = 0; k < 6; ++k) dot += U[i].a[k] * a.a[k];
+            qdd[i] = (u[i] - dot) / D[i];
+            a.a[s] += qdd[i];
+            acc[i] = a;
+        }
+    }
+};
+
+template <class S>
+void rollout_one(const MppibModel* m, const MppibParams* p, int K, int k, S* q, S* qd,
+                 const float* actions, int t0, int nsteps, float* obs) {
+    const int nb = m->nb, nu = m->nu, T = p->T;
+    const S h = (S)p->dt / (S)p->substeps;
+    Articulation<S> art; art.m = m; art.nb = nb;
+    // base frame and gravity (Featherstone: a_base = -g expressed in base coordinates)
+    S bq[4] = {(S)m->base_quat[0], (S)m->base_quat[1], (S)m->base_quat[2], (S)m->base_quat[3]};
+    M3<S> Rb = quat_to_R(bq);
+    std::memset(&art.a0, 0, sizeof(art.a0));
+    if (m->gravity_on) for (int i = 0; i < 3; ++i) { S s = 0; for (int j = 0; j < 3; ++j) s += Rb.a[j][i] * (S)m->gravity[j]; art.a0.a[3 + i] = -s; }
+
+    const int nloop = nsteps > 0 ? nsteps : 1;   // nsteps == 0: observe only
+    for (int t = t0; t < t0 + nloop; ++t) {
+        // apply_robot_cmd (isaacgym_wrapper.py:524-572): command -> per-DOF targets
+        S target[MPPIB_MAX_BODIES];
+        for (int i = 0; i < nb && nsteps > 0; ++i) {
+            S u0 = (S)p->u_scale * (S)actions[((size_t)t * nu + m->cmd_i0[i]) * K + k];
+            S u1 = (S)p->u_scale * (S)actions[((size_t)t * nu + m->cmd_i1[i]) * K + k];
+            target[i] = (S)m->cmd_c0[i] * u0 + (S)m->cmd_c1[i] * u1;
+        }
+        // step (isaacgym_wrapper.py:639-641): `substeps` solver substeps of h = dt/substeps
+        for (int s = 0; s < (nsteps > 0 ? p->substeps : 0); ++s) {
+            art.kinematics(q, qd);
+            S tau[MPPIB_MAX_BODIES], dimp[MPPIB_MAX_BODIES], qdd[MPPIB_MAX_BODIES];
+            for (int i = 0; i < nb; ++i) {
+                S kd = (S)m->kd[i], b = (S)m->damping[i];
+                if (m->drive_mode == MPPIB_DRIVE_VELOCITY) {
+                    tau[i] = kd * (target[i] - qd[i]) - b * qd[i];     // implicit in qd_new via dimp
+                } else {
+                    S e = std::min(std::max(target[i], -(S)m->effort[i]), (S)m->effort[i]);
+                    tau[i] = e - (kd + b) * qd[i];
+                }
+                dimp[i] = (S)m->armature[i] + h * (kd + b);
+            }
+            art.aba(tau, dimp, qdd);
+            if (m->drive_mode == MPPIB_DRIVE_VELOCITY) {
+                // drive force limit (URDF <limit effort>): a joint whose implicit drive torque exceeds it is
+                // re-solved once with the constant saturated torque
+                bool any = false;
+                for (int i = 0; i < nb; ++i) {
+                    S td = (S)m->kd[i] * (target[i] - (qd[i] + h * qdd[i]));
+                    if (std::fabs(td) > (S)m->effort[i]) {
+                        any = true;
+                        tau[i] = (td > 0 ? (S)m->effort[i] : -(S)m->effort[i]) - (S)m->damping[i] * qd[i];
+                        dimp[i] = (S)m->armature[i] + h * (S)m->damping[i];
+                    }
+                }
+                if (any) art.aba(tau, dimp, qdd);
+            }
+            for (int i = 0; i < nb; ++i) {           // semi-implicit Euler + velocity / position limits
+                S v = qd[i] + h * qdd[i];
+                v = std::min(std::max(v, -(S)m->qd_max[i]), (S)m->qd_max[i]);
+                S x = q[i] + h * v;
+                if (x < (S)m->q_lo[i]) { x = (S)m->q_lo[i]; if (v < 0) v = 0; }
+                if (x > (S)m->q_hi[i]) { x = (S)m->q_hi[i]; if (v > 0) v = 0; }
+                q[i] = x; qd[i] = v;
+            }
+        }
+        if (!obs) continue;
+        // observe (refresh_* tensors, isaacgym_wrapper.py:642-645) -------------------------------------
+        art.kinematics(q, qd);
+        M3<S> Rw[MPPIB_MAX_BODIES]; S pw[MPPIB_MAX_BODIES][3], qw[MPPIB_MAX_BODIES][4];
+        for (int i = 0; i < nb; ++i) {
+            const M3<S>& Rp = m->parent[i] >= 0 ? Rw[m->parent[i]] : Rb;
+            const S* qp = m->parent[i] >= 0 ? qw[m->parent[i]] : bq;
+            S pp[3]; for (int r = 0; r < 3; ++r) pp[r] = m->parent[i] >= 0 ? pw[m->parent[i]][r] : (S)m->base_pos[r];
+            for (int r = 0; r < 3; ++r) {
+                S s = 0; for (int j = 0; j < 3; ++j) s += Rp.a[r][j] * art.pl[i][j];
+                pw[i][r] = pp[r] + s;
+                for (int cc = 0; cc < 3; ++cc) { S s2 = 0; for (int j = 0; j < 3; ++j) s2 += Rp.a[r][j] * art.Rl[i].a[j][cc]; Rw[i].a[r][cc] = s2; }
+            }
+            S qt[4] = {(S)m->tree_quat[i][0], (S)m->tree_quat[i][1], (S)m->tree_quat[i][2], (S)m->tree_quat[i][3]};
+            S tmp[4]; quat_mul(qp, qt, tmp);
+            if (m->jtype[i] == MPPIB_JOINT_REVOLUTE) {
+                S qz[4] = {0, 0, std::sin(q[i] / 2), std::cos(q[i] / 2)};
+                quat_mul(tmp, qz, qw[i]);
+            } else for (int r = 0; r < 4; ++r) qw[i][r] = tmp[r];
+        }
+        int row = 0;
+        const size_t TK = (size_t)T * K;
+        for (int o = 0; o < p->nobs; ++o) {
+            float vals[2 * MPPIB_MAX_BODIES > 13 ? 2 * MPPIB_MAX_BODIES : 13]; int w = 0;
+            if (p->obs[o].kind == MPPIB_OBS_LINK_STATE) {
+                int l = p->obs[o].index, b = m->link_body[l];
+                const M3<S>& R = b >= 0 ? Rw[b] : Rb;
+                S lp[3] = {(S)m->link_p[l][0], (S)m->link_p[l][1], (S)m->link_p[l][2]};
+                S off[3]; for (int r = 0; r < 3; ++r) { S s = 0; for (int j = 0; j < 3; ++j) s += R.a[r][j] * lp[j]; off[r] = s; }
+                S ql[4] = {(S)m->link_quat[l][0], (S)m->link_quat[l][1], (S)m->link_quat[l][2], (S)m->link_quat[l][3]};
+                S qo[4]; quat_mul(b >= 0 ? qw[b] : bq, ql, qo);
+                S ww[3] = {0, 0, 0}, vw[3] = {0, 0, 0};
+                if (b >= 0) for (int r = 0; r < 3; ++r) for (int j = 0; j < 3; ++j) { ww[r] += R.a[r][j] * art.v[b].a[j]; vw[r] += R.a[r][j] * art.v[b].a[3 + j]; }
+                S wxo[3]; cross3(ww, off, wxo);
+                for (int r = 0; r < 3; ++r) vals[r] = (float)((b >= 0 ? pw[b][r] : (S)m->base_pos[r]) + off[r]);
+                for (int r = 0; r < 4; ++r) vals[3 + r] = (float)qo[r];
+                for (int r = 0; r < 3; ++r) vals[7 + r] = (float)(vw[r] + wxo[r]);
+                for (int r = 0; r < 3; ++r) vals[10 + r] = (float)ww[r];
+                w = 13;
+            } else if (p->obs[o].kind == MPPIB_OBS_DOF_STATE) {
+                for (int i = 0; i < nb; ++i) { vals[2 * i] = (float)q[i]; vals[2 * i + 1] = (float)qd[i]; }
+                w = 2 * nb;
+            } else {
+                w = p->obs[o].kind == MPPIB_OBS_CONTACT ? 3 : 13;
+                for (int r = 0; r < w; ++r) vals[r] = 0.f;
+            }
+            for (int r = 0; r < w; ++r) obs[(size_t)(row + r) * TK + (size_t)t * K + k] = vals[r];
+            row += w;
+        }
+    }
+}
+
+template <class S>
+void rollout_impl(const MppibModel* m, const MppibParams* p, const float* state0, float* state,
+                  const float* actions, int t0, int nsteps, float* obs, int nthreads) {
+    const int K = p->K, nb = m->nb;
+    parallel_for(K, nthreads, [&](int a, int b) {
+        for (int k = a; k < b; ++k) {
+            S q[MPPIB_MAX_BODIES], qd[MPPIB_MAX_BODIES];
+            for (int i = 0; i < nb; ++i) {
+                q[i] = state0 ? (S)state0[i] : (S)state[(size_t)i * K + k];
+                qd[i] = state0 ? (S)state0[nb + i] : (S)state[(size_t)(nb + i) * K + k];
+            }
+            rollout_one<S>(m, p, K, k, q, qd, actions, t0, nsteps, obs);
+            if (state) for (int i = 0; i < nb; ++i) { state[(size_t)i * K + k] = (float)q[i]; state[(size_t)(nb + i) * K + k] = (float)qd[i]; }
+        }
+    });
+}
+
+int obs_rows(const MppibModel* m, const MppibParams* p) {
+    int r = 0;
+    for (int o = 0; o < p->nobs; ++o) r += p->obs[o].kind == MPPIB_OBS_DOF_STATE ? 2 * m->nb : (p->obs[o].kind == MPPIB_OBS_CONTACT ? 3 : 13);
+    return r;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t oracle_abi_version(void) { return MPPIB_ABI_VERSION; }
+int32_t oracle_obs_size(const MppibModel* m, const MppibParams* p) { return obs_rows(m, p); }
+int32_t oracle_state_size(const MppibModel* m) { return 2 * m->nb + 13 * m->nfree; }
+
+void oracle_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+    U4 r = philox4x32_10({c0, c1, c2, c3}, k0, k1);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+// K1 restatement.  All buffers are host pointers with the device layouts of include/mppib.h.
+void oracle_sample(const MppibModel* m, const MppibParams* p, uint64_t seed, uint64_t plan_idx, uint32_t k_offset,
+                   uint32_t k_total, const float* U, const float* prior_row, float* actions, float* noise, int nthreads) {
+    const int K = p->K, T = p->T, nu = m->nu;
+    const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32) ^ (uint32_t)plan_idx;
+    parallel_for(K, nthreads, [&](int a, int b) {
+        for (int k = a; k < b; ++k) {
+            uint32_t kg = k_offset + (uint32_t)k;
+            for (int t = 0; t < T; ++t) {
+                float z[MPPIB_MAX_NU + 4];
+                for (int blk = 0; blk * 4 < nu; ++blk) {
+                    U4 r = philox4x32_10({kg, (uint32_t)t, (uint32_t)blk, (uint32_t)(plan_idx >> 32)}, key0, key1);
+                    box_muller(r.x, r.y, &z[4 * blk], &z[4 * blk + 1]);
+                    box_muller(r.z, r.w, &z[4 * blk + 2], &z[4 * blk + 3]);
+                }
+                for (int j = 0; j < nu; ++j) {
+                    float n = 0.f;
+                    for (int i = 0; i <= j; ++i) n += p->sigma_chol[j * nu + i] * z[i];
+                    float u = U[t * nu + j];
+                    float act = u + n;
+                    if (p->sample_null_action && kg == k_total - 1) act = 0.f;
+                    act = std::min(std::max(act, p->u_min[j]), p->u_max[j]);
+                    if (prior_row && kg == k_total - 2) act = prior_row[t * nu + j];
+                    size_t idx = ((size_t)t * nu + j) * K + k;
+                    actions[idx] = act;
+                    if (noise) noise[idx] = act - u;
+                }
+            }
+        }
+    });
+}
+
+void oracle_rollout(const MppibModel* m, const MppibParams* p, const float* state0, float* state, const float* actions,
+                    int32_t t0, int32_t nsteps, float* obs, int32_t use_double, int32_t nthreads) {
+    if (use_double) rollout_impl<double>(m, p, state0, state, actions, t0, nsteps, obs, nthreads);
+    else rollout_impl<float>(m, p, state0, state, actions, t0, nsteps, obs, nthreads);
+}
+
+// K3 restatement (double accumulation).  partial = (beta, eta, W[T][nu]).
+void oracle_reduce(const MppibModel* m, const MppibParams* p, const float* cost, const float* x, const float* U,
+                   float* partial, float* S_out) {
+    const int K = p->K, T = p->T, nu = m->nu;
+    std::vector<double> S(K);
+    double beta = std::numeric_limits<double>::infinity();
+    for (int k = 0; k < K; ++k) {
+        double s = 0, g = 1;
+        for (int t = 0; t < T; ++t) { s += g * (double)cost[(size_t)t * K + k]; g *= (double)p->gamma; }
+        if (p->mode == MPPIB_MODE_SIMPLE) {
+            // perturbation cost  lambda * sum_t U_t^T Sigma^-1 noise_t   (noise @ Sigma^-1, then dot with U)
+            double pc = 0;
+            for (int t = 0; t < T; ++t) for (int j = 0; j < nu; ++j) {
+                double ac = 0;
+                for (int i = 0; i < nu; ++i) ac += (double)x[((size_t)t * nu + i) * K + k] * (double)p->sigma_inv[i * nu + j];
+                pc += (double)U[t * nu + j] * ac;
+            }
+            s += (double)p->lambda_ * pc;
+        }
+        S[k] = s;
+        if (std::isfinite(s) && s < beta) beta = s;
+    }
+    double eta = 0; std::vector<double> W((size_t)T * nu, 0.0);
+    for (int k = 0; k < K; ++k) {
+        double w = std::isfinite(S[k]) ? std::exp(-(S[k] - beta) / (double)p->lambda_) : 0.0;
+        eta += w;
+        for (int i = 0; i < T * nu; ++i) W[i] += w * (double)x[(size_t)i * K + k];
+        if (S_out) S_out[k] = (float)S[k];
+    }
+    partial[0] = (float)beta; partial[1] = (float)eta;
+    for (int i = 0; i < T * nu; ++i) partial[2 + i] = (float)W[i];
+}
+
+// Savitzky-Golay window 9, polyorder 2, mode='interp' (SURVEY Appendix C), along T for one column.
+static void savgol9(const double* y, int T, double* out) {
+    static const double mid[9] = {-21, 14, 39, 54, 59, 54, 39, 14, -21};
+    static const double edge[4][9] = {{763, 441, 189, 7, -105, -147, -119, -21, 147},
+                                      {441, 322, 220.5, 136.5, 70, 21, -10.5, -24.5, -21},
+                                      {189, 220.5, 232, 223.5, 195, 146.5, 78, -10.5, -119},
+                                      {7, 136.5, 223.5, 268, 270, 229.5, 146.5, 21, -147}};
+    for (int t = 0; t < T; ++t) {
+        double s = 0;
+        if (t < 4) { for (int i = 0; i < 9; ++i) s += edge[t][i] * y[i]; s /= 1155.0; }
+        else if (t >= T - 4) { int e = T - 1 - t; for (int i = 0; i < 9; ++i) s += edge[e][i] * y[T - 1 - i]; s /= 1155.0; }
+        else { for (int i = 0; i < 9; ++i) s += mid[i] * y[t - 4 + i]; s /= 231.0; }
+        out[t] = s;
+    }
+}
+
+// K4 restatement: combine G partials, update U, optional filter, first action.
+void oracle_finalize(const MppibModel* m, const MppibParams* p, const float* partials, int32_t G, float* U,
+                     float* action_out, float* stats) {
+    const int T = p->T, nu = m->nu, P = 2 + T * nu;
+    double beta = std::numeric_limits<double>::infinity();
+    for (int g = 0; g < G; ++g) if (partials[(size_t)g * P + 1] > 0) beta = std::min(beta, (double)partials[(size_t)g * P]);
+    double eta = 0; std::vector<double> W((size_t)T * nu, 0.0);
+    for (int g = 0; g < G; ++g) {
+        if (!(partials[(size_t)g * P + 1] > 0)) continue;
+        double s = std::exp(-((double)partials[(size_t)g * P] - beta) / (double)p->lambda_);
+        eta += s * (double)partials[(size_t)g * P + 1];
+        for (int i = 0; i < T * nu; ++i) W[i] += s * (double)partials[(size_t)g * P + 2 + i];
+    }
+    std::vector<double> Un((size_t)T * nu);
+    for (int i = 0; i < T * nu; ++i) {
+        double wm = eta > 0 ? W[i] / eta : (p->mode == MPPIB_MODE_SIMPLE ? 0.0 : (double)U[i]);   // no valid sample: keep U
+        Un[i] = p->mode == MPPIB_MODE_SIMPLE ? (double)U[i] + wm
+                                             : (1.0 - (double)p->step_size_mean) * (double)U[i] + (double)p->step_size_mean * wm;
+    }
+    if (p->filter_u) {
+        std::vector<double> col(T), out(T);
+        for (int j = 0; j < nu; ++j) {
+            for (int t = 0; t < T; ++t) col[t] = Un[t * nu + j];
+            savgol9(col.data(), T, out.data());
+            // smoothing may overshoot the control bounds at the horizon edges: clamp back (spec decision)
+            for (int t = 0; t < T; ++t) Un[t * nu + j] = std::min(std::max(out[t], (double)p->u_min[j]), (double)p->u_max[j]);
+        }
+    }
+    for (int i = 0; i < T * nu; ++i) U[i] = (float)Un[i];
+    for (int j = 0; j < nu; ++j) action_out[j] = U[j];
+    if (stats) { stats[0] = (float)beta; stats[1] = (float)eta; }
+}
+
+void oracle_shift(const MppibModel* m, const MppibParams* p, float* U) {
+    const int T = p->T, nu = m->nu;
+    for (int t = 0; t + 1 < T; ++t) for (int j = 0; j < nu; ++j) U[t * nu + j] = U[(t + 1) * nu + j];
+    for (int j = 0; j < nu; ++j) U[(T - 1) * nu + j] = p->u_init[j];
+}
+
+}  // extern "C"

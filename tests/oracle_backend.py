@@ -1,0 +1,80 @@
+"""Checker backend: the CPU oracle behind the same interface as ``mppi_isaac_b200.backend.CudaBackend``.
+
+TEST INFRASTRUCTURE.  It lets the `-m "not gpu"` suite drive the host logic (planner sequencing, facade views,
+sharding, transport) end to end on CPU tensors, and gives the GPU parity tests a planner-level reference.  The
+product package never imports this file or ``oracle/``.
+"""
+import numpy as np
+import torch
+
+from oracle import oracle as orc
+
+
+def _np(t):
+    return None if t is None else t.detach().numpy()
+
+
+class OracleBackend:
+    name = "oracle"
+
+    def __init__(self, device="cpu", use_double=False, nthreads=1):
+        self.device = torch.device("cpu")
+        self.model = self.params = None
+        self.use_double, self.nthreads = use_double, nthreads
+        self.launches = 0
+
+    def create(self, model, params):
+        self.model, self.params = model, params
+
+    def destroy(self):
+        pass
+
+    def set_params(self, params):
+        self.params = params
+
+    def set_model(self, model):
+        self.model = model
+
+    def state_size(self):
+        return 2 * self.model.nb + 13 * self.model.nfree
+
+    def obs_size(self):
+        return orc.obs_size(self.model, self.params)
+
+    def sample(self, seed, plan_idx, k_offset, k_total, U, prior_row, actions, noise, plan_ctr=None):
+        plan = plan_idx + (int(plan_ctr[0]) if plan_ctr is not None else 0)
+        a, n = orc.sample(self.model, self.params, seed, plan, _np(U), k_offset, k_total, _np(prior_row), self.nthreads)
+        actions.copy_(torch.from_numpy(a))
+        if noise is not None:
+            noise.copy_(torch.from_numpy(n))
+
+    def rollout(self, state0, state, actions, t0, nsteps, obs, act_t0=0):
+        T, K, nu = self.params.T, self.params.K, self.model.nu
+        a = np.zeros((T, nu, K), np.float32)
+        src = _np(actions).reshape(-1, nu, K)
+        a[act_t0:act_t0 + src.shape[0]] = src
+        st = _np(state) if state is not None else None
+        s0 = _np(state0)
+        import ctypes as C
+        f = lambda x: None if x is None else x.ctypes.data_as(C.POINTER(C.c_float))
+        o = _np(obs)
+        assert o is None or o.flags["C_CONTIGUOUS"]
+        assert st is None or st.flags["C_CONTIGUOUS"]
+        orc.lib().oracle_rollout(C.byref(self.model), C.byref(self.params), f(None if s0 is None else np.ascontiguousarray(s0, np.float32)),
+                                 f(st), f(a), C.c_int32(t0), C.c_int32(nsteps), f(o), C.c_int32(int(self.use_double)), C.c_int32(self.nthreads))
+
+    def reduce(self, cost, x, U, partial):
+        p, _ = orc.reduce(self.model, self.params, _np(cost.contiguous()), _np(x), _np(U))
+        partial.copy_(torch.from_numpy(p))
+
+    def finalize(self, partials, G, U, action_out, stats):
+        Un, act, st = orc.finalize(self.model, self.params, _np(partials.contiguous())[:G], _np(U))
+        U.copy_(torch.from_numpy(Un))
+        action_out.copy_(torch.from_numpy(act))
+        if stats is not None:
+            stats.copy_(torch.from_numpy(st))
+
+    def shift(self, U, plan_ctr=None):
+        U.copy_(torch.from_numpy(orc.shift(self.model, self.params, _np(U))))
+        if plan_ctr is not None:
+            plan_ctr += 1

@@ -1,0 +1,65 @@
+"""Shared builders for the test scenes (BASELINE configs C1 / C2 on the built-in conf + compiled models)."""
+import copy
+
+import numpy as np
+
+from mppi_isaac_b200.model.blob import (OBS_DOF_STATE, OBS_LINK_STATE, build_scene, make_params)
+from mppi_isaac_b200.utils.config_store import IsaacGymConfig, MPPIConfig, load_actor_cfgs, load_isaacgym_config
+
+
+def panda_scene():
+    return build_scene(load_actor_cfgs(["panda_stick", "goal"]))
+
+
+def point_scene():
+    return build_scene(load_actor_cfgs(["point_robot", "goal"]))
+
+
+def panda_mppi(K=64, T=30, mode="simple", **kw):
+    d = dict(num_samples=K, horizon=T, mppi_mode=mode, sampling_method="random", noise_sigma=(0.1 * np.eye(7)).tolist(),
+             u_min=[-0.2], u_max=[0.2], lambda_=0.05, sample_null_action=True, rollout_var_discount=0.95)
+    d.update(kw)
+    return MPPIConfig(**d)
+
+
+def point_mppi(K=128, T=12, mode="simple", **kw):
+    d = dict(num_samples=K, horizon=T, mppi_mode=mode, sampling_method="random", noise_sigma=np.eye(3).tolist(),
+             u_min=[-1.5], u_max=[1.5], lambda_=0.1, sample_null_action=True, rollout_var_discount=0.95)
+    d.update(kw)
+    return MPPIConfig(**d)
+
+
+def panda_setup(K=64, T=30, mode="simple", obs_links=("panda_ee_tip",), dof=True, sim=None, **kw):
+    sc = panda_scene()
+    obs = [(OBS_LINK_STATE, sc.robot.link_names.index(n)) for n in obs_links]
+    if dof:
+        obs.append((OBS_DOF_STATE, 0))
+    p = make_params(panda_mppi(K, T, mode, **kw), sim or IsaacGymConfig(), sc.nu, K, obs)
+    dof0 = sc.dof_state0
+    state0 = np.concatenate([dof0[0::2], dof0[1::2]]).astype(np.float32)
+    return sc, p, state0
+
+
+def point_setup(K=128, T=12, mode="simple", **kw):
+    sc = point_scene()
+    obs = [(OBS_LINK_STATE, sc.robot.link_names.index("base_link")), (OBS_DOF_STATE, 0)]
+    p = make_params(point_mppi(K, T, mode, **kw), IsaacGymConfig(), sc.nu, K, obs)
+    state0 = np.array([0.1, 0, 0, 0, 0, 0], np.float32)
+    return sc, p, state0
+
+
+def panda_cfg(K=64, T=30, device="cpu", **mppi_kw):
+    cfg = load_isaacgym_config("config_panda_b200")
+    cfg = copy.deepcopy(cfg)
+    cfg.mppi.num_samples, cfg.mppi.horizon, cfg.mppi.device = K, T, device
+    for k, v in mppi_kw.items():
+        setattr(cfg.mppi, k, v)
+    return cfg
+
+
+def point_cfg(K=128, T=12, device="cpu", **mppi_kw):
+    cfg = copy.deepcopy(load_isaacgym_config("config_point_robot_b200"))
+    cfg.mppi.num_samples, cfg.mppi.horizon, cfg.mppi.device = K, T, device
+    for k, v in mppi_kw.items():
+        setattr(cfg.mppi, k, v)
+    return cfg

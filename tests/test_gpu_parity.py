@@ -1,0 +1,232 @@
+"""-m gpu: parity of the CUDA path against the oracle, through the C ABI (CudaBackend = ctypes on libmppib.so).
+
+Tolerances (float32 path):
+  K1  Philox integers exact -> Gaussians |d| <= 2e-6 * max(1,|z|) (double Box-Muller vs logf/sincospif)
+  K2  one model step |dq| <= 1e-5 ; free-running T=30 |dq| <= 1e-3 rad, link position <= 1e-4 m... (measured ~1e-6)
+  K3/K4  |U_gpu - U_oracle|_inf <= 1e-5 * max(1, |U|_inf)
+Full-size properties at BASELINE sizes (K = 10 000 / 65 536): shard-combine invariance, replica determinism,
+uniform-cost and dominant-sample limits."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from mppi_isaac_b200.model.blob import MODE_SIMPLE, OBS_DOF_STATE, OBS_LINK_STATE
+from scenes import panda_cfg, panda_setup, point_cfg, point_setup
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def gpu_backend(sc, p):
+    from mppi_isaac_b200.backend import CudaBackend
+    be = CudaBackend(DEV)
+    be.create(sc.model, p)
+    return be
+
+
+def dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(DEV)
+
+
+def test_native_library_is_loaded():
+    from mppi_isaac_b200 import backend
+    backend.load_library()
+    with open("/proc/self/maps") as f:
+        assert "libmppib.so" in f.read()
+
+
+@pytest.mark.parametrize("setup,K,T", [(panda_setup, 1000, 30), (point_setup, 128, 12)])
+def test_k1_sample_parity(oracle, setup, K, T):
+    sc, p, _ = setup(K=K, T=T)
+    nu = sc.nu
+    be = gpu_backend(sc, p)
+    rng = np.random.default_rng(0)
+    U = rng.uniform(-0.1, 0.1, (T, nu)).astype(np.float32)
+    prior = rng.uniform(-0.3, 0.3, (T, nu)).astype(np.float32)
+    actions, noise = torch.zeros((T, nu, K), device=DEV), torch.zeros((T, nu, K), device=DEV)
+    ctr = torch.tensor([5], dtype=torch.int32, device=DEV)
+    be.sample(1234, 2, 0, K, dev(U), dev(prior), actions, noise, ctr)       # effective plan index 7
+    a_ref, n_ref = oracle.sample(sc.model, p, 1234, 7, U, prior_row=prior)
+    a, n = actions.cpu().numpy(), noise.cpu().numpy()
+    scale = float(np.sqrt(max(p.sigma_chol[0] ** 2, 1e-12)))
+    assert np.abs(a - a_ref).max() <= 2e-6 * max(1.0, 6 * scale)
+    assert np.abs(n - n_ref).max() <= 2e-6 * max(1.0, 6 * scale)
+    np.testing.assert_array_equal(a[:, :, -1], 0)
+    np.testing.assert_array_equal(a[:, :, -2], prior)
+    # shard invariance on the device: two shards with k_offset reproduce the single launch
+    p2 = copy.copy(p); p2.K = K // 2
+    be2 = gpu_backend(sc, p2)
+    parts = []
+    for g in range(2):
+        aa = torch.zeros((T, nu, K // 2), device=DEV)
+        be2.sample(1234, 7, g * (K // 2), K, dev(U), dev(prior), aa, None)
+        parts.append(aa.cpu().numpy())
+    np.testing.assert_array_equal(np.concatenate(parts, axis=2), a)
+
+
+@pytest.mark.parametrize("setup,K,T", [(panda_setup, 1000, 30), (point_setup, 128, 12)])
+def test_k2_rollout_parity_free_running(oracle, setup, K, T):
+    sc, p, state0 = setup(K=K, T=T)
+    be = gpu_backend(sc, p)
+    rng = np.random.default_rng(1)
+    lim = float(p.u_max[0])
+    actions = rng.uniform(-lim, lim, (T, sc.nu, K)).astype(np.float32)
+    R = be.obs_size()
+    obs, state = torch.zeros((R, T, K), device=DEV), torch.zeros((be.state_size(), K), device=DEV)
+    be.rollout(dev(state0), state, dev(actions), 0, T, obs)
+    st_ref, obs_ref = oracle.rollout(sc.model, p, state0, actions, use_double=True, nthreads=8)
+    o, s = obs.cpu().numpy(), state.cpu().numpy()
+    nb = sc.ndof
+    assert np.abs(s[:nb] - st_ref[:nb]).max() <= 1e-3                      # stated gate
+    assert np.abs(s[:nb] - st_ref[:nb]).max() <= 2e-5                      # what float32 actually delivers
+    assert np.abs(o[0:3] - obs_ref[0:3]).max() <= 1e-4                     # link position [m]
+    qa, qb = o[3:7], obs_ref[3:7]
+    assert np.minimum(np.abs(qa - qb), np.abs(qa + qb)).max() <= 2e-5      # quaternion up to sign
+    assert np.abs(o[7:13] - obs_ref[7:13]).max() <= 2e-3                   # link velocities (x kd amplification)
+    assert np.abs(o[13:] - obs_ref[13:]).max() <= 2e-3
+
+
+def test_k2_one_step_lockstep(oracle):
+    """Oracle state re-injected before every step: one-step error of the kernel alone."""
+    sc, p, state0 = panda_setup(K=256, T=30)
+    be = gpu_backend(sc, p)
+    rng = np.random.default_rng(2)
+    actions = rng.uniform(-0.2, 0.2, (30, 7, 256)).astype(np.float32)
+    a_d = dev(actions)
+    state_ref = np.repeat(state0[:, None], 256, 1).astype(np.float32)
+    R = be.obs_size()
+    obs = torch.zeros((R, 30, 256), device=DEV)
+    worst = 0.0
+    for t in range(30):
+        st = dev(state_ref)
+        be.rollout(None, st, a_d, t, 1, obs)
+        state_ref, _ = oracle.rollout(sc.model, p, None, actions, t, 1, state=state_ref.copy(), want_obs=False)
+        worst = max(worst, float(np.abs(st.cpu().numpy()[:7] - state_ref[:7]).max()))
+    assert worst <= 1e-5
+
+
+def test_k2_stepwise_equals_batched_and_observe_only(oracle):
+    sc, p, state0 = panda_setup(K=64, T=6)
+    be = gpu_backend(sc, p)
+    actions = dev(np.random.default_rng(3).uniform(-0.2, 0.2, (6, 7, 64)).astype(np.float32))
+    R = be.obs_size()
+    obs_a, obs_b = torch.zeros((R, 6, 64), device=DEV), torch.zeros((R, 6, 64), device=DEV)
+    st_a, st_b = torch.zeros((14, 64), device=DEV), dev(np.repeat(state0[:, None], 64, 1))
+    be.rollout(dev(state0), st_a, actions, 0, 6, obs_a)
+    for t in range(6):
+        be.rollout(None, st_b, actions[t:t + 1], t, 1, obs_b, act_t0=t)
+    assert torch.equal(obs_a, obs_b) and torch.equal(st_a, st_b)
+    obs_c = torch.zeros_like(obs_a)
+    be.rollout(None, st_b, actions, 5, 0, obs_c)                           # observe-only into slot 5
+    assert torch.equal(obs_c[:, 5], obs_a[:, 5])
+
+
+def test_k2_replica_determinism_full_size():
+    """K = 10 000 identical inputs -> bit-identical trajectories (reference test invariant, full BASELINE size)."""
+    sc, p, state0 = panda_setup(K=10000, T=30)
+    be = gpu_backend(sc, p)
+    a = np.random.default_rng(4).uniform(-0.2, 0.2, (30, 7, 1)).astype(np.float32)
+    actions = dev(np.repeat(a, 10000, axis=2))
+    obs = torch.zeros((be.obs_size(), 30, 10000), device=DEV)
+    be.rollout(dev(state0), None, actions, 0, 30, obs)
+    assert bool((obs == obs[:, :, :1]).all())
+
+
+@pytest.mark.parametrize("mode", ["simple", "halton-spline"])
+@pytest.mark.parametrize("K", [64, 1000, 4100])
+def test_k3_k4_parity(oracle, mode, K):
+    sc, p, _ = panda_setup(K=K, T=30, mode=mode, filter_u=True)
+    be = gpu_backend(sc, p)
+    rng = np.random.default_rng(5)
+    U = rng.uniform(-0.1, 0.1, (30, 7)).astype(np.float32)
+    a, n = oracle.sample(sc.model, p, 3, 0, U)
+    cost = rng.uniform(0, 10, (30, K)).astype(np.float32)
+    cost[:, K // 3] = np.nan                                                # a diverged rollout gets weight 0
+    x = n if p.mode == MODE_SIMPLE else a
+    partial = torch.zeros(2 + 210, device=DEV)
+    be.reduce(dev(cost), dev(x), dev(U), partial)
+    p_ref, _ = oracle.reduce(sc.model, p, cost, x, U)
+    pg = partial.cpu().numpy()
+    assert abs(pg[0] - p_ref[0]) <= 1e-5 * max(1, abs(p_ref[0]))
+    np.testing.assert_allclose(pg[1], p_ref[1], rtol=2e-5)
+    np.testing.assert_allclose(pg[2:], p_ref[2:], rtol=0, atol=2e-5 * max(1.0, np.abs(p_ref[2:]).max()))
+    Ud, act, stats = dev(U), torch.zeros(7, device=DEV), torch.zeros(2, device=DEV)
+    be.finalize(partial.view(1, -1), 1, Ud, act, stats)
+    U_ref, act_ref, st_ref = oracle.finalize(sc.model, p, p_ref[None], U)
+    assert np.abs(Ud.cpu().numpy() - U_ref).max() <= 1e-5 * max(1.0, np.abs(U_ref).max())
+    np.testing.assert_array_equal(act.cpu().numpy(), Ud.cpu().numpy()[0])
+    Us = dev(U); be.shift(Us)
+    np.testing.assert_array_equal(Us.cpu().numpy(), oracle.shift(sc.model, p, U))
+
+
+def test_k3_properties_at_baseline_sizes():
+    """Size-independent properties at K = 65 536 (C5 size on one GPU) and K = 10 000 (headline)."""
+    for K in (10000, 65536):
+        sc, p, _ = panda_setup(K=K, T=30, filter_u=False)
+        be = gpu_backend(sc, p)
+        g = torch.Generator(device=DEV).manual_seed(0)
+        x = torch.randn((30, 7, K), device=DEV, generator=g) * 0.3
+        U = torch.zeros((30, 7), device=DEV)
+        partial = torch.zeros(212, device=DEV)
+        # uniform cost -> W/eta is the plain mean
+        be.reduce(torch.ones((30, K), device=DEV), x, U, partial)
+        assert abs(float(partial[1]) - K) <= 1e-3 * K
+        torch.testing.assert_close(partial[2:] / partial[1], x.mean(dim=2).reshape(-1), atol=2e-5, rtol=0)
+        # one dominant sample -> W/eta is that sample
+        cost = torch.rand((30, K), device=DEV, generator=g)
+        cost[:, 777] = -1e3
+        be.reduce(cost, x, U, partial)
+        torch.testing.assert_close(partial[2:] / partial[1], x[:, :, 777].reshape(-1), atol=1e-6, rtol=0)
+        # shard-combine invariance: 8 shards through K4 == 1 shard through K4
+        cost = torch.rand((30, K), device=DEV, generator=g) * 5
+        be.reduce(cost, x, U, partial)
+        U1, act = torch.zeros((30, 7), device=DEV), torch.zeros(7, device=DEV)
+        be.finalize(partial.view(1, -1), 1, U1, act, None)
+        p8 = copy.copy(p); p8.K = K // 8
+        be8 = gpu_backend(sc, p8)
+        parts = torch.zeros((8, 212), device=DEV)
+        for s in range(8):
+            sl = slice(s * p8.K, (s + 1) * p8.K)
+            be8.reduce(cost[:, sl].contiguous(), x[:, :, sl].contiguous(), U, parts[s])
+        U8 = torch.zeros((30, 7), device=DEV)
+        be8.finalize(parts, 8, U8, act, None)
+        torch.testing.assert_close(U8, U1, atol=2e-6, rtol=0)
+
+
+@pytest.mark.parametrize("robot", ["panda", "point"])
+def test_full_plan_parity_through_planner_api(robot):
+    """MPPIisaacPlanner on the GPU (CUDA graph on) vs the same planner on the checker backend, closed loop."""
+    from mppi_isaac_b200 import MPPIisaacPlanner
+    from mppi_isaac_b200.objectives import PandaReachObjective, PointReachObjective
+    from oracle_backend import OracleBackend
+    if robot == "panda":
+        mk, obj, q = (lambda d: panda_cfg(K=1000, T=30, device=d)), PandaReachObjective, np.array([0.0, -0.94, 0.0, -2.8, 0.0, 1.8675, 0.0])
+    else:
+        mk, obj, q = (lambda d: point_cfg(K=128, T=12, device=d)), PointReachObjective, np.array([0.1, 0.0, 0.0])
+    gpu = MPPIisaacPlanner(mk(DEV), obj(), use_cuda_graph=True)
+    cpu = MPPIisaacPlanner(mk("cpu"), obj(), backend=OracleBackend(nthreads=8))
+    qd = np.zeros_like(q)
+    for it in range(5):
+        ag, ac = gpu.compute_action(q, qd), cpu.compute_action(q, qd)
+        lim = float(gpu.mppi.backend.params.u_max[0])
+        assert float((ag - ac).abs().max()) <= 2e-4 * max(1.0, lim), f"plan {it}"
+        q = q + 0.05 * ac.numpy(); qd = ac.numpy()
+    assert gpu.mppi._graph is not None, "CUDA-graph capture of the plan failed"
+    np.testing.assert_allclose(gpu.mppi.U.cpu().numpy(), cpu.mppi.U.numpy(), atol=2e-4)
+    rg, rc = torch.load(__import__("io").BytesIO(gpu.get_rollouts())), torch.load(__import__("io").BytesIO(cpu.get_rollouts()))
+    assert rg.shape == rc.shape
+    assert float((rg.cpu() - rc).abs().max()) <= 1e-3
+
+
+def test_stepwise_protocol_on_gpu_matches_batched():
+    from mppi_isaac_b200 import MPPIisaacPlanner
+    from mppi_isaac_b200.objectives import PandaReachObjective
+    q = [0.0, -0.94, 0.0, -2.8, 0.0, 1.8675, 0.0]
+    a = MPPIisaacPlanner(panda_cfg(K=256, T=12, device=DEV), PandaReachObjective(), rollout_mode="batched", use_cuda_graph=False)
+    b = MPPIisaacPlanner(panda_cfg(K=256, T=12, device=DEV), PandaReachObjective(), rollout_mode="stepwise")
+    for it in range(3):
+        ua, ub = a.compute_action(q, [0] * 7), b.compute_action(q, [0] * 7)
+        assert float((ua - ub).abs().max()) <= 1e-6
+    assert torch.equal(a.mppi.actions, b.mppi.actions)

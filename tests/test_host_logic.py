@@ -1,0 +1,173 @@
+"""Host logic of the drop-in boundary (planner sequencing, facade views, transport, sharding), driven on CPU
+through the checker backend.  No CUDA here; the same code paths run on the GPU with CudaBackend."""
+import numpy as np
+import pytest
+import torch
+
+from mppi_isaac_b200 import MPPIisaacPlanner
+from mppi_isaac_b200.objectives import PandaReachObjective, PointReachObjective
+from mppi_isaac_b200.planner.mppi import shard_samples
+from mppi_isaac_b200.planner.rollout_sim import ObservationError, RolloutSim
+from mppi_isaac_b200.utils.config_store import IsaacGymConfig
+from mppi_isaac_b200.utils.conversions import matrix_to_euler_angles, quaternion_to_matrix, quaternion_to_yaw
+from mppi_isaac_b200.utils.transport import bytes_to_torch, torch_to_bytes
+from oracle_backend import OracleBackend
+from scenes import panda_cfg, point_cfg
+
+Q0 = [0.0, -0.94, 0.0, -2.8, 0.0, 1.8675, 0.0]
+
+
+def make(cfg, obj, **kw):
+    return MPPIisaacPlanner(cfg, obj, backend=OracleBackend(), **kw)
+
+
+def test_public_surface_matches_reference_names():
+    p = make(panda_cfg(K=16, T=10), PandaReachObjective())
+    for name in ("update_objective", "dynamics", "running_cost", "compute_action", "reset_rollout_sim", "compute_action_tensor",
+                 "command", "add_to_env", "get_rollouts", "update_weights", "update_mppi_params"):
+        assert callable(getattr(p, name))
+    for attr in ("cfg", "objective", "sim", "mppi", "prior", "state_place_holder"):
+        assert hasattr(p, attr)
+    assert p.state_place_holder.shape == (16, 14)
+    s = p.sim
+    for name in ("get_actor_position_by_name", "get_actor_velocity_by_name", "get_actor_orientation_by_name", "get_actor_link_by_name",
+                 "get_rigid_body_by_rigid_body_index", "get_actor_contact_forces_by_name", "get_dof_state", "apply_robot_cmd", "step",
+                 "reset_robot_state", "save_root_state", "reset_root_state", "reset_to_initial_poses",
+                 "update_root_state_tensor_by_obstacles", "set_actor_position_by_name"):
+        assert callable(getattr(s, name))
+    assert s.num_envs == 16 and s._visualize_link_present and isinstance(s.env_cfg, list)
+
+
+def test_point_robot_plan_c1_converges():
+    """BASELINE config C1 (point_robot reach, K=128, T=12): closed loop drives the base towards the goal."""
+    cfg = point_cfg()
+    p = make(cfg, PointReachObjective())
+    q, qd = np.array([0.1, 0.0, 0.0]), np.zeros(3)
+    d0 = np.hypot(1 - q[0], 1 - q[1])
+    for it in range(25):
+        a = p.compute_action(q, qd).numpy()
+        assert a.shape == (3,) and np.all(np.abs(a) <= 1.5 + 1e-6)
+        q = q + cfg.isaacgym.dt * a          # kinematic world: the velocity drive tracks the command
+        qd = a
+    assert np.hypot(1 - q[0], 1 - q[1]) < 0.35 * d0
+
+
+def test_batched_equals_stepwise_protocol():
+    """One T-step launch + one batched cost call == the reference's T x (dynamics, running_cost) protocol."""
+    a = make(panda_cfg(K=32, T=12), PandaReachObjective(), rollout_mode="batched")
+    b = make(panda_cfg(K=32, T=12), PandaReachObjective(), rollout_mode="stepwise")
+    for it in range(3):
+        ua = a.compute_action(Q0, [0] * 7)
+        ub = b.compute_action(Q0, [0] * 7)
+        np.testing.assert_allclose(ua.numpy(), ub.numpy(), atol=1e-6)
+    np.testing.assert_allclose(a.mppi.U.numpy(), b.mppi.U.numpy(), atol=1e-6)
+    np.testing.assert_array_equal(a.mppi.actions.numpy(), b.mppi.actions.numpy())
+    ra, rb = bytes_to_torch(a.get_rollouts()), bytes_to_torch(b.get_rollouts())
+    assert ra.shape == (12, 32, 3)
+    np.testing.assert_allclose(ra.numpy(), rb.numpy(), atol=1e-6)
+
+
+def test_getter_views_shapes_and_values():
+    p = make(panda_cfg(K=8, T=5, filter_u=False), PandaReachObjective())
+    p.compute_action(Q0, [0] * 7)
+    s = p.sim                                             # batched mode after a plan
+    ee = s.get_actor_link_by_name("panda", "panda_ee_tip")
+    assert ee.shape == (40, 13) and s.get_actor_position_by_name("goal").shape == (40, 3)
+    assert s.get_actor_position_by_name("goal").stride(0) == 0       # static actor: one row, expanded
+    np.testing.assert_allclose(s.get_actor_position_by_name("goal")[7].numpy(), [1.0, 1.0, 0.5])
+    assert s._root_state.shape == (40, 2, 13)
+    assert s.get_actor_contact_forces_by_name("goal", "sphere").shape == (40, 3)
+    # row t*K + k of the batched view is sample k at step t
+    np.testing.assert_array_equal(ee[2 * 8 + 3].numpy(), s._obs[0:13, 2, 3].numpy())
+    with pytest.raises(ObservationError):
+        s.get_actor_link_by_name("panda", "panda_link3")              # not in the traced plan
+    # step mode: (K, .) views
+    s.begin_step_mode()
+    assert s.get_actor_link_by_name("panda", "panda_ee_tip").shape == (8, 13)
+    u = torch.zeros(8, 7)
+    p.dynamics(None, u)
+    assert s.get_actor_link_by_name("panda", "panda_ee_tip").shape == (8, 13)
+    assert p.running_cost(None).shape == (8,)
+
+
+def test_observe_all_exposes_dense_tensors():
+    p = make(panda_cfg(K=8, T=4, filter_u=False), PandaReachObjective(), observe="all")
+    p.compute_action(Q0, [0] * 7)
+    s = p.sim
+    assert s._rigid_body_state.shape == (32, 11, 13) and s._dof_state.shape == (32, 14) and s._net_contact_force.shape == (32, 11, 3)
+    dof = s.get_dof_state()
+    np.testing.assert_allclose(dof[:, 0::2][0].numpy(), np.array(Q0) + 0.05 * p.mppi.actions[0, :, 0].numpy(), atol=2e-3)
+    np.testing.assert_array_equal(s.get_actor_link_by_name("panda", "panda_link3").numpy(), s._rigid_body_state[:, 3].numpy())
+
+
+def test_compute_action_tensor_roundtrip_and_warm_start():
+    p = make(panda_cfg(K=32, T=12), PandaReachObjective())
+    dof = torch.tensor([[v for q in Q0 for v in (q, 0.0)]], dtype=torch.float32)
+    root = p.sim._root_state[:1].clone()
+    root[0, 1, :3] = torch.tensor([0.5, 0.2, 0.4])                     # move the goal
+    out = p.compute_action_tensor(torch_to_bytes(dof), torch_to_bytes(root))
+    act = bytes_to_torch(out)
+    assert act.shape == (7,) and act.dtype == torch.float32
+    np.testing.assert_allclose(p.sim.get_actor_position_by_name("goal")[0].numpy(), [0.5, 0.2, 0.4])
+    U1 = p.mppi.U.clone()
+    bytes_to_torch(p.command())
+    # warm start: the new plan started from U shifted by one step (last row u_init = 0)
+    assert not torch.equal(U1, p.mppi.U)
+    assert int(p.mppi.plan_ctr[0]) == 2
+
+
+def test_update_weights_and_mppi_params():
+    p = make(panda_cfg(K=32, T=12), PandaReachObjective())
+    p.compute_action(Q0, [0] * 7)
+    p.update_weights({"robot_to_goal": 2.0, "robot_ori": 0.0})
+    assert p.objective.weights["robot_to_goal"] == 2.0
+    p.update_mppi_params({"noise_sigma": (0.05 * np.eye(7)).tolist()})
+    assert abs(p.mppi.backend.params.sigma_chol[0] - np.sqrt(0.05)) < 1e-6
+    assert float(p.mppi.U.abs().max()) == 0.0                          # reference rebuilds MPPIPlanner -> U reset
+
+
+def test_prior_goes_to_row_k_minus_2_stepwise():
+    class Prior:
+        def compute_command(self, sim):
+            assert sim.get_actor_link_by_name("panda", "panda_ee_tip").shape[0] == sim.num_envs
+            return torch.full((7,), 0.123)
+    cfg = panda_cfg(K=16, T=9, use_priors=True)
+    p = make(cfg, PandaReachObjective(), prior=Prior())
+    assert p.mppi.rollout_mode == "stepwise"
+    p.compute_action(Q0, [0] * 7)
+    np.testing.assert_allclose(p.mppi.actions[:, :, 14].numpy(), 0.123)
+    assert np.all(p.mppi.actions[:, :, 15].numpy() == 0)               # null action row
+
+
+def test_shard_samples_and_errors():
+    assert shard_samples(10000, 0, 1) == (10000, 0)
+    parts = [shard_samples(10000, r, 8) for r in range(8)]
+    assert sum(k for k, _ in parts) == 10000 and all(k % 4 == 0 for k, _ in parts)
+    assert [o for _, o in parts] == list(np.cumsum([0] + [k for k, _ in parts[:-1]]))
+    with pytest.raises(ValueError):
+        shard_samples(10, 0, 2)
+    with pytest.raises(ValueError, match="horizon"):
+        make(panda_cfg(K=16, T=6, filter_u=True), PandaReachObjective())
+    with pytest.raises(NotImplementedError):
+        RolloutSim(IsaacGymConfig(), ["panda_stick", "goal"], viewer=True, device="cpu", backend=OracleBackend())
+
+
+def test_transport_and_conversions():
+    t = torch.arange(12, dtype=torch.float32).reshape(3, 4)
+    assert torch.equal(bytes_to_torch(torch_to_bytes(t)), t)
+    psi = torch.tensor([0.3, -1.2, 2.9])
+    quat = torch.stack([torch.zeros(3), torch.zeros(3), torch.sin(psi / 2), torch.cos(psi / 2)], 1)
+    np.testing.assert_allclose(quaternion_to_yaw(quat).numpy(), psi.numpy(), atol=1e-6)       # conversions.py:4-11
+    # real-first quaternion API: identity and a 90 deg yaw
+    R = quaternion_to_matrix(torch.tensor([[1.0, 0, 0, 0], [np.cos(np.pi / 4), 0, 0, np.sin(np.pi / 4)]]))
+    np.testing.assert_allclose(R[0].numpy(), np.eye(3), atol=1e-7)
+    np.testing.assert_allclose(R[1].numpy(), [[0, -1, 0], [1, 0, 0], [0, 0, 1]], atol=1e-6)
+    e = matrix_to_euler_angles(R, "ZYX")
+    np.testing.assert_allclose(e[1].numpy(), [np.pi / 2, 0, 0], atol=1e-6)
+    # scipy cross-check of the ZYX convention on random rotations
+    from scipy.spatial.transform import Rotation
+    rot = Rotation.random(20, random_state=0)
+    ours = matrix_to_euler_angles(torch.tensor(rot.as_matrix(), dtype=torch.float64), "ZYX").numpy()
+    np.testing.assert_allclose(ours, rot.as_euler("ZYX"), atol=1e-9)
+    wxyz = np.roll(rot.as_quat(), 1, axis=1)
+    np.testing.assert_allclose(quaternion_to_matrix(torch.tensor(wxyz)).numpy(), rot.as_matrix(), atol=1e-12)
