@@ -12,7 +12,6 @@ void mppib_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-int reduce_grid_size(const MppibContext* c);
 
 static int validate(const MppibModel* m, const MppibParams* p) {
     MPPIB_REQUIRE(m != nullptr && p != nullptr, "null model/params");
@@ -48,7 +47,7 @@ static void derive(MppibContext* c) {
 static int alloc_scratch(MppibContext* c) {
     if (c->reduce_scratch) { cudaFree(c->reduce_scratch); c->reduce_scratch = nullptr; }
     c->reduce_max_ctas = c->num_sms * 4;
-    const size_t P = 2 + (size_t)c->params.T * c->model.nu;
+    const size_t P = (2 + (size_t)c->params.T * c->model.nu + 3) & ~(size_t)3;   // rows padded to 16 bytes
     MPPIB_CHECK_CUDA(cudaMalloc(&c->reduce_scratch, sizeof(float) * P * c->reduce_max_ctas));
     if (!c->reduce_ticket) {
         MPPIB_CHECK_CUDA(cudaMalloc(&c->reduce_ticket, sizeof(unsigned int)));

@@ -5,20 +5,23 @@
 // spec SURVEY.md 8(a) M5/M6 and 8(e)).
 //
 // K3 data flow (HBM-bound; every input byte is read from HBM exactly once):
-//   cost[T][K], x[T*nu][K]  --128-bit coalesced loads-->  shared-memory tile of CK=64 samples
-//   S_k   = sum_t gamma^t cost[t][k]  (+ lambda * sum_r g[r] x[r][k],  g = Sigma^-1 U,  SIMPLE mode)
-//   beta_c = min_k S_k ; w_k = exp(-(S_k - beta_c)/lambda) ; eta_c = sum_k w_k
-//   W_c[r] = sum_k w_k x[r][k]            (thread r, rotated float4 reads: bank-conflict free)
-//   CTA running (beta, eta, W) merged online (log-sum-exp style rescale); CTAs grid-stride over chunks;
-//   per-CTA partials -> global scratch; the LAST CTA (atomic ticket) folds them into `partial`.
+//   * persistent CTAs (one per SM), each walks tiles of W samples: tile = x[T*nu][W] + cost[T][W]
+//   * tiles arrive by TMA (cp.async.bulk.tensor.2d, one elected thread, mbarrier complete_tx) into an NS-deep
+//     shared-memory ring, so NS-1 tiles (~90 KB / SM) are always in flight while the CTA computes
+//   * per tile:  S_k = sum_t gamma^t cost[t][k]  (+ sum_r g[r] x[r][k],  g = lambda Sigma^-1 U,  SIMPLE mode)
+//                b = min_k S_k ; w_k = exp(-(S_k - b)/lambda) ; eta = sum_k w_k ; W[r] = sum_k w_k x[r][k]
+//     and an online log-sum-exp merge into the CTA's running (beta, eta, W) -- no second pass for the minimum
+//   * per-CTA partials -> global scratch; the LAST CTA (atomic ticket) folds them in parallel into `partial`
 // Algorithmic bytes per launch: 4*K*T*(nu+1) + 4*(T*nu+2)   (BASELINE.md section 3).
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int CK = 64;          // samples per tile
 constexpr int NT = 256;         // threads per CTA
 constexpr int RPT = 2;          // rows of W per thread (T*nu <= 512)
+constexpr int MAX_GRID = 256;   // persistent CTAs (<= scratch rows)
 
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
@@ -30,32 +33,72 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// merge (b2, e2, w2) into running (b, e, w...) -- caller applies s_old / s_new to its W registers
-__device__ __forceinline__ void merge_scales(float b_run, float b_new, float inv_lambda, float& b_out, float& s_old, float& s_new) {
-    b_out = fminf(b_run, b_new);
-    s_old = (b_run == INFINITY) ? 0.f : expf(-(b_run - b_out) * inv_lambda);
-    s_new = (b_new == INFINITY) ? 0.f : expf(-(b_new - b_out) * inv_lambda);
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// 2-D tiled TMA load: box (W columns x rows) of a row-major [rows][K] float tensor -> dense smem tile
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int col, int row, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(col), "r"(row), "r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(NT)
-reduce_kernel(const __grid_constant__ MppibParams p, int nu, const float* __restrict__ cost, const float* __restrict__ x,
-              const float* __restrict__ U, float* __restrict__ scratch, unsigned int* __restrict__ ticket,
+template <int W, int NS>
+__global__ void __launch_bounds__(NT, 1)
+mppib_reduce_kernel(const __grid_constant__ MppibParams p, const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_c,
+              int nu, int xbox_rows, const float* __restrict__ U, float* __restrict__ scratch, unsigned int* __restrict__ ticket,
               float* __restrict__ partial) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int KPL = W / 32;   // samples per lane
     const int K = p.K, T = p.T, NR = T * nu;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float inv_lambda = 1.0f / p.lambda_;
     const bool simple = p.mode == MPPIB_MODE_SIMPLE;
 
-    float* xs = smem;                    // [NR][CK]
-    float* cs = xs + (size_t)NR * CK;    // [T][CK]
-    float* g = cs + (size_t)T * CK;      // [NR]   lambda * Sigma^-1 U (SIMPLE)
-    float* gp = g + NR;                  // [T]    gamma^t
-    float* red = gp + T;                 // [4][CK]
-    float* wk = red + 4 * CK;            // [CK]
-    float* misc = wk + CK;               // [4]
+    const int tile_floats = (NR + T) * W;
+    float* tiles = reinterpret_cast<float*>(smem_raw);                       // [NS][(NR+T)*W], each stage 128-B aligned
+    const int stage_floats = (tile_floats + 31) & ~31;
+    float* g = tiles + (size_t)NS * stage_floats;                            // [NR]  lambda * Sigma^-1 U (SIMPLE)
+    float* gp = g + NR;                                                      // [T]   gamma^t
+    float* red = gp + ((T + 1) & ~1);                                        // [8][W]
+    float* wk = red + 8 * W;                                                 // [W]
+    float* misc = wk + W;                                                    // [8]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (((size_t)((misc + 8) - tiles) * 4 + 15) & ~(size_t)15));  // [NS] mbarriers
 
+    const int ntiles = (K + W - 1) / W;
+    const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const uint32_t tile_bytes = (uint32_t)tile_floats * 4u;
+
+    auto issue = [&](int i) {   // elected thread: TMA the i-th tile of this CTA into ring slot i % NS
+        const int s = i % NS, k0 = ((int)blockIdx.x + i * (int)gridDim.x) * W;
+        float* dst = tiles + (size_t)s * stage_floats;
+        mbar_expect_tx(&full[s], tile_bytes);
+        for (int r0 = 0; r0 < NR; r0 += xbox_rows) tma_load_2d(dst + (size_t)r0 * W, &tm_x, k0, r0, &full[s]);
+        tma_load_2d(dst + (size_t)NR * W, &tm_c, k0, 0, &full[s]);
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int i = 0; i < NS && i < my_tiles; ++i) issue(i);
+    }
     for (int r = tid; r < NR; r += NT) {
         float acc = 0.f;
         if (simple) {
@@ -66,85 +109,100 @@ reduce_kernel(const __grid_constant__ MppibParams p, int nu, const float* __rest
         g[r] = acc;
     }
     for (int t = tid; t < T; t += NT) gp[t] = powf(p.gamma, (float)t);
+    __syncthreads();
 
     float b_run = INFINITY, e_run = 0.f, w_run[RPT];
 #pragma unroll
     for (int i = 0; i < RPT; ++i) w_run[i] = 0.f;
 
-    const int nchunks = (K + CK - 1) / CK;
-    for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-        const int k0 = chunk * CK;
-        __syncthreads();   // previous tile fully consumed (also orders g/gp init on the first trip)
-        // ---- stage the tile: 128-bit loads, k innermost => each row segment is 256 contiguous bytes
-        const int nvec = (NR + T) * (CK / 4);
-        for (int idx = tid; idx < nvec; idx += NT) {
-            const int row = idx / (CK / 4), c4 = idx % (CK / 4);
-            const int k = k0 + 4 * c4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float* src = row < NR ? x + (size_t)row * K : cost + (size_t)(row - NR) * K;
-            if (k + 3 < K) v = __ldg(reinterpret_cast<const float4*>(src + k));
-            else if (k < K) { v.x = src[k]; if (k + 1 < K) v.y = src[k + 1]; if (k + 2 < K) v.z = src[k + 2]; }
-            float* dst = row < NR ? xs + (size_t)row * CK : cs + (size_t)(row - NR) * CK;
-            *reinterpret_cast<float4*>(dst + 4 * c4) = v;
-        }
-        __syncthreads();
-        // ---- trajectory cost S_k: 4 partial sums per sample
+    for (int i = 0; i < my_tiles; ++i) {
+        const int s = i % NS;
+        const int k0 = ((int)blockIdx.x + i * (int)gridDim.x) * W;
+        const float* xs = tiles + (size_t)s * stage_floats;       // [NR][W]
+        const float* cs = xs + (size_t)NR * W;                    // [T][W]
+        mbar_wait(&full[s], (uint32_t)((i / NS) & 1));
+        // ---- S_k partial sums: warp w takes rows r = w, w+8, ...; lane = sample(s)
         {
-            const int kk = tid & (CK - 1), part = tid >> 6;
-            float acc = 0.f;
-            for (int t = part; t < T; t += 4) acc += gp[t] * cs[t * CK + kk];
-            if (simple) for (int r = part; r < NR; r += 4) acc += g[r] * xs[r * CK + kk];
-            red[part * CK + kk] = acc;
-        }
-        __syncthreads();
-        if (tid < CK) {
-            float S = red[tid] + red[CK + tid] + red[2 * CK + tid] + red[3 * CK + tid];
-            const bool valid = (k0 + tid < K) && isfinite(S);
-            S = valid ? S : INFINITY;
-            float bmin = warp_min(S);
-            if ((tid & 31) == 0) misc[tid >> 5] = bmin;
-            red[tid] = S;
-        }
-        __syncthreads();
-        const float b_c = fminf(misc[0], misc[1]);
-        if (tid < CK) {
-            const float S = red[tid];
-            const float w = (S == INFINITY) ? 0.f : expf(-(S - b_c) * inv_lambda);
-            wk[tid] = w;
-            float es = warp_sum(w);
-            if ((tid & 31) == 0) misc[2 + (tid >> 5)] = es;
-        }
-        __syncthreads();
-        if (b_c != INFINITY) {
-            const float e_c = misc[2] + misc[3];
-            float b_out, s_old, s_new;
-            merge_scales(b_run, b_c, inv_lambda, b_out, s_old, s_new);
+            float acc[KPL];
 #pragma unroll
-            for (int i = 0; i < RPT; ++i) {
-                const int r = tid + i * NT;
+            for (int q = 0; q < KPL; ++q) acc[q] = 0.f;
+            for (int t = warp; t < T; t += 8) {
+                const float gt = gp[t];
+#pragma unroll
+                for (int q = 0; q < KPL; ++q) acc[q] += gt * cs[t * W + lane + 32 * q];
+            }
+            if (simple) {
+                for (int r = warp; r < NR; r += 8) {
+                    const float gr = g[r];
+#pragma unroll
+                    for (int q = 0; q < KPL; ++q) acc[q] += gr * xs[r * W + lane + 32 * q];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < KPL; ++q) red[warp * W + lane + 32 * q] = acc[q];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            float S[KPL], bmin = INFINITY;
+#pragma unroll
+            for (int q = 0; q < KPL; ++q) {
+                const int kk = lane + 32 * q;
+                float sum = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) sum += red[w8 * W + kk];
+                const bool valid = (k0 + kk < K) && isfinite(sum);
+                S[q] = valid ? sum : INFINITY;
+                bmin = fminf(bmin, S[q]);
+            }
+            bmin = warp_min(bmin);
+            float es = 0.f;
+#pragma unroll
+            for (int q = 0; q < KPL; ++q) {
+                const float w = (S[q] == INFINITY) ? 0.f : expf(-(S[q] - bmin) * inv_lambda);
+                wk[lane + 32 * q] = w;
+                es += w;
+            }
+            es = warp_sum(es);
+            if (lane == 0) { misc[0] = bmin; misc[1] = es; }
+        }
+        __syncthreads();
+        const float b_c = misc[0];
+        if (b_c != INFINITY) {
+            const float e_c = misc[1];
+            const float b_out = fminf(b_run, b_c);
+            const float s_old = (b_run == INFINITY) ? 0.f : expf(-(b_run - b_out) * inv_lambda);
+            const float s_new = expf(-(b_c - b_out) * inv_lambda);
+#pragma unroll
+            for (int rr = 0; rr < RPT; ++rr) {
+                const int r = tid + rr * NT;
                 if (r < NR) {
                     float acc = 0.f;
-                    const float4* xr = reinterpret_cast<const float4*>(xs + (size_t)r * CK);
+                    const float4* xr = reinterpret_cast<const float4*>(xs + (size_t)r * W);
                     const float4* w4 = reinterpret_cast<const float4*>(wk);
 #pragma unroll
-                    for (int j = 0; j < CK / 4; ++j) {
-                        const int jj = (j + r) & (CK / 4 - 1);   // rotation => conflict-free LDS.128
+                    for (int j = 0; j < W / 4; ++j) {
+                        const int jj = (j + r) & (W / 4 - 1);   // rotation => conflict-free LDS.128
                         const float4 a = xr[jj], b = w4[jj];
                         acc += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
                     }
-                    w_run[i] = w_run[i] * s_old + acc * s_new;
+                    w_run[rr] = w_run[rr] * s_old + acc * s_new;
                 }
             }
             e_run = e_run * s_old + e_c * s_new;
             b_run = b_out;
         }
+        __syncthreads();   // every thread is done with ring slot s and with red/wk/misc
+        if (tid == 0 && i + NS < my_tiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before async-proxy writes
+            issue(i + NS);
+        }
     }
-    // ---- per-CTA partial -> scratch ; last CTA folds
+    // ---- per-CTA partial -> scratch ; last CTA folds all of them in parallel
     const int P = 2 + NR;
-    float* mine = scratch + (size_t)blockIdx.x * P;
+    float* mine = scratch + (size_t)blockIdx.x * (((P + 3) >> 2) << 2);   // rows padded to 16 bytes
     if (tid == 0) { mine[0] = b_run; mine[1] = e_run; }
 #pragma unroll
-    for (int i = 0; i < RPT; ++i) { const int r = tid + i * NT; if (r < NR) mine[2 + r] = w_run[i]; }
+    for (int rr = 0; rr < RPT; ++rr) { const int r = tid + rr * NT; if (r < NR) mine[2 + r] = w_run[rr]; }
     __threadfence();
     __syncthreads();
     __shared__ unsigned int s_last;
@@ -152,45 +210,76 @@ reduce_kernel(const __grid_constant__ MppibParams p, int nu, const float* __rest
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    float b = INFINITY;
-    for (int c = 0; c < (int)gridDim.x; ++c) b = fminf(b, __ldcg(scratch + (size_t)c * P));
-    float e = 0.f, w[RPT];
+    const int G = (int)gridDim.x;
+    float* sc = tiles;                   // [MAX_GRID] scale of every CTA partial (the ring is idle now)
+    float* fold = tiles + MAX_GRID;      // [4][PP]
+    {
+        float b = (tid < G) ? __ldcg(scratch + (size_t)tid * ((((P + 3) >> 2) << 2))) : INFINITY;
+        float bm = warp_min(b);
+        if (lane == 0) misc[warp] = bm;
+        __syncthreads();
+        float bb = INFINITY;
 #pragma unroll
-    for (int i = 0; i < RPT; ++i) w[i] = 0.f;
-    for (int c = 0; c < (int)gridDim.x; ++c) {
-        const float* src = scratch + (size_t)c * P;
-        const float bc = __ldcg(src);
-        if (bc == INFINITY) continue;
-        const float s = expf(-(bc - b) * inv_lambda);
-        e += s * __ldcg(src + 1);
+        for (int w8 = 0; w8 < 8; ++w8) bb = fminf(bb, misc[w8]);
+        if (tid < G) sc[tid] = (b == INFINITY) ? 0.f : expf(-(b - bb) * inv_lambda);
+        __syncthreads();
+        // parallel fold with deep memory-level parallelism: P4 = ceil(P/4) float4 columns x 4 CTA groups of 64 threads;
+        // thread (cg, e4) sums CTAs c = cg, cg+4, ... with 8 independent 128-bit L2 loads in flight
+        // (scratch rows are padded to a multiple of 4 floats, so every row is 16-byte aligned)
+        const int P4 = (P + 3) >> 2, PP = P4 << 2;
+        const int cg = tid >> 6, e4 = tid & 63;
+        for (int e = e4; e < P4; e += 64) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int c = cg;
+            for (; c + 28 < G; c += 32) {
+                float4 v[8];
 #pragma unroll
-        for (int i = 0; i < RPT; ++i) { const int r = tid + i * NT; if (r < NR) w[i] += s * __ldcg(src + 2 + r); }
+                for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(scratch + (size_t)(c + 4 * u) * PP) + e);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const float sc_ = sc[c + 4 * u]; acc.x += sc_ * v[u].x; acc.y += sc_ * v[u].y; acc.z += sc_ * v[u].z; acc.w += sc_ * v[u].w; }
+            }
+            for (; c < G; c += 4) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(scratch + (size_t)c * PP) + e);
+                const float sc_ = sc[c];
+                acc.x += sc_ * v.x; acc.y += sc_ * v.y; acc.z += sc_ * v.z; acc.w += sc_ * v.w;
+            }
+            reinterpret_cast<float4*>(fold + (size_t)cg * PP)[e] = acc;
+        }
+        __syncthreads();
+        for (int e = tid; e < P; e += NT) {
+            const float v = fold[e] + fold[PP + e] + fold[2 * PP + e] + fold[3 * PP + e];
+            partial[e] = e == 0 ? bb : v;
+        }
+        if (tid == 0) *ticket = 0u;
     }
-    if (tid == 0) { partial[0] = b; partial[1] = e; *ticket = 0u; }
-#pragma unroll
-    for (int i = 0; i < RPT; ++i) { const int r = tid + i * NT; if (r < NR) partial[2 + r] = w[i]; }
 }
 
+__constant__ float c_sg_mid[9] = {-21.f, 14.f, 39.f, 54.f, 59.f, 54.f, 39.f, 14.f, -21.f};
+__constant__ float c_sg_edge[4][9] = {{763.f, 441.f, 189.f, 7.f, -105.f, -147.f, -119.f, -21.f, 147.f},
+                                      {441.f, 322.f, 220.5f, 136.5f, 70.f, 21.f, -10.5f, -24.5f, -21.f},
+                                      {189.f, 220.5f, 232.f, 223.5f, 195.f, 146.5f, 78.f, -10.5f, -119.f},
+                                      {7.f, 136.5f, 223.5f, 268.f, 270.f, 229.5f, 146.5f, 21.f, -147.f}};
+
 // K4: combine G shard partials, U update, optional Savitzky-Golay (window 9, order 2, 'interp' edges), action out.
-__global__ void __launch_bounds__(512)
-finalize_kernel(const __grid_constant__ MppibParams p, int nu, const float* __restrict__ partials, int G,
+__global__ void __launch_bounds__(256)
+mppib_finalize_kernel(const __grid_constant__ MppibParams p, int nu, const float* __restrict__ partials, int G,
                 float* __restrict__ U, float* __restrict__ action_out, float* __restrict__ stats) {
-    extern __shared__ float un[];   // [T*nu]
+    extern __shared__ float un[];   // [T*nu] then [G] scales
     const int T = p.T, NR = T * nu, P = 2 + NR;
+    float* sg = un + NR;
     const float inv_lambda = 1.0f / p.lambda_;
     float b = INFINITY;
     for (int gidx = 0; gidx < G; ++gidx) if (partials[(size_t)gidx * P + 1] > 0.f) b = fminf(b, partials[(size_t)gidx * P]);
-    float e = 0.f;
-    for (int gidx = 0; gidx < G; ++gidx) {
+    for (int gidx = threadIdx.x; gidx < G; gidx += blockDim.x) {
         const float eg = partials[(size_t)gidx * P + 1];
-        if (eg > 0.f) e += expf(-(partials[(size_t)gidx * P] - b) * inv_lambda) * eg;
+        sg[gidx] = eg > 0.f ? expf(-(partials[(size_t)gidx * P] - b) * inv_lambda) : 0.f;
     }
+    __syncthreads();
+    float e = 0.f;
+    for (int gidx = 0; gidx < G; ++gidx) e += sg[gidx] * partials[(size_t)gidx * P + 1];
     for (int r = threadIdx.x; r < NR; r += blockDim.x) {
         float w = 0.f;
-        for (int gidx = 0; gidx < G; ++gidx) {
-            const float eg = partials[(size_t)gidx * P + 1];
-            if (eg > 0.f) w += expf(-(partials[(size_t)gidx * P] - b) * inv_lambda) * partials[(size_t)gidx * P + 2 + r];
-        }
+        for (int gidx = 0; gidx < G; ++gidx) w += sg[gidx] * partials[(size_t)gidx * P + 2 + r];
         const float wm = e > 0.f ? w / e : (p.mode == MPPIB_MODE_SIMPLE ? 0.f : U[r]);   // no valid sample: keep U
         un[r] = p.mode == MPPIB_MODE_SIMPLE ? U[r] + wm : (1.0f - p.step_size_mean) * U[r] + p.step_size_mean * wm;
     }
@@ -199,15 +288,21 @@ finalize_kernel(const __grid_constant__ MppibParams p, int nu, const float* __re
         float out = un[r];
         if (p.filter_u) {
             const int t = r / nu, j = r % nu;
-            const float mid[9] = {-21.f, 14.f, 39.f, 54.f, 59.f, 54.f, 39.f, 14.f, -21.f};
-            const float edge[4][9] = {{763.f, 441.f, 189.f, 7.f, -105.f, -147.f, -119.f, -21.f, 147.f},
-                                      {441.f, 322.f, 220.5f, 136.5f, 70.f, 21.f, -10.5f, -24.5f, -21.f},
-                                      {189.f, 220.5f, 232.f, 223.5f, 195.f, 146.5f, 78.f, -10.5f, -119.f},
-                                      {7.f, 136.5f, 223.5f, 268.f, 270.f, 229.5f, 146.5f, 21.f, -147.f}};
             float s = 0.f;
-            if (t < 4) { for (int i = 0; i < 9; ++i) s += edge[t][i] * un[i * nu + j]; s *= (1.0f / 1155.0f); }
-            else if (t >= T - 4) { const int ee = T - 1 - t; for (int i = 0; i < 9; ++i) s += edge[ee][i] * un[(T - 1 - i) * nu + j]; s *= (1.0f / 1155.0f); }
-            else { for (int i = 0; i < 9; ++i) s += mid[i] * un[(t - 4 + i) * nu + j]; s *= (1.0f / 231.0f); }
+            if (t < 4) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) s += c_sg_edge[t][i] * un[i * nu + j];
+                s *= (1.0f / 1155.0f);
+            } else if (t >= T - 4) {
+                const int ee = T - 1 - t;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) s += c_sg_edge[ee][i] * un[(T - 1 - i) * nu + j];
+                s *= (1.0f / 1155.0f);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) s += c_sg_mid[i] * un[(t - 4 + i) * nu + j];
+                s *= (1.0f / 231.0f);
+            }
             out = fminf(fmaxf(s, p.u_min[j]), p.u_max[j]);   // smoothing may overshoot the bounds at the edges
         }
         U[r] = out;
@@ -216,7 +311,7 @@ finalize_kernel(const __grid_constant__ MppibParams p, int nu, const float* __re
     if (threadIdx.x == 0 && stats) { stats[0] = b; stats[1] = e; }
 }
 
-__global__ void shift_kernel(const __grid_constant__ MppibParams p, int nu, float* __restrict__ U, uint32_t* __restrict__ plan_ctr) {
+__global__ void mppib_shift_kernel(const __grid_constant__ MppibParams p, int nu, float* __restrict__ U, uint32_t* __restrict__ plan_ctr) {
     extern __shared__ float tmp[];
     const int NR = p.T * nu;
     for (int r = threadIdx.x; r < NR; r += blockDim.x) tmp[r] = r + nu < NR ? U[r + nu] : p.u_init[r % nu];
@@ -225,49 +320,95 @@ __global__ void shift_kernel(const __grid_constant__ MppibParams p, int nu, floa
     if (threadIdx.x == 0 && plan_ctr) *plan_ctr += 1u;
 }
 
+template <int W, int NS>
 size_t reduce_smem_bytes(int T, int nu) {
     const int NR = T * nu;
-    return sizeof(float) * ((size_t)NR * CK + (size_t)T * CK + NR + T + 4 * CK + CK + 4);
+    const size_t stage = ((size_t)(NR + T) * W + 31) & ~(size_t)31;
+    size_t ring = (size_t)NS * stage;
+    const size_t fold = MAX_GRID + 4 * (size_t)(2 + NR + 3);  // the last CTA reuses the ring for the fold
+    if (ring < fold) ring = (fold + 31) & ~(size_t)31;
+    return sizeof(float) * (ring + NR + T + 1 + 8 * W + W + 8) + 16 + sizeof(uint64_t) * NS + 128;
 }
 
-}  // namespace
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int reduce_grid_size(const MppibContext* c) {
-    const int nchunks = (c->params.K + CK - 1) / CK;
-    int per_sm = (int)(220 * 1024 / reduce_smem_bytes(c->params.T, c->model.nu));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
-    const int cap = c->num_sms * per_sm;
-    return nchunks < cap ? nchunks : cap;
-}
-
-int launch_reduce(MppibContext* c, const float* cost, const float* x, const float* U, float* partial, cudaStream_t s) {
-    const int T = c->params.T, nu = c->model.nu;
-    MPPIB_REQUIRE(T * nu <= RPT * NT, "mppib_reduce: T*nu = %d exceeds %d", T * nu, RPT * NT);
-    const size_t smem = reduce_smem_bytes(T, nu);
-    MPPIB_REQUIRE(smem <= 227 * 1024, "mppib_reduce: tile of %zu bytes exceeds shared memory", smem);
-    static bool attr_set = false;
-    if (!attr_set) {
-        MPPIB_CHECK_CUDA(cudaFuncSetAttribute(reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
     }
-    const int grid = reduce_grid_size(c);
+    return fn;
+}
+
+// row-major [rows][K] float32 tensor, box = box_rows x W columns, zero fill out of bounds, no swizzle
+int make_map(CUtensorMap* tm, const float* base, int rows, int K, int box_rows, int W) {
+    EncodeTiledFn enc = get_encode();
+    MPPIB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)W, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MPPIB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for rows=%d K=%d box=%dx%d", (int)r, rows, K, box_rows, W);
+    return 0;
+}
+
+template <int W, int NS>
+int launch_reduce_t(MppibContext* c, const float* cost, const float* x, const float* U, float* partial, cudaStream_t s) {
+    const int T = c->params.T, nu = c->model.nu, NR = T * nu, K = c->params.K;
+    const size_t smem = reduce_smem_bytes<W, NS>(T, nu);
+    MPPIB_REQUIRE(smem <= 226 * 1024, "mppib_reduce: ring of %zu bytes exceeds shared memory", smem);
+    static size_t smem_attr = 0;
+    if (smem > smem_attr) {
+        MPPIB_CHECK_CUDA(cudaFuncSetAttribute(mppib_reduce_kernel<W, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_attr = smem;
+    }
+    // box rows <= 256 per TMA instruction: split T*nu rows evenly
+    const int nbox = (NR + 255) / 256;
+    const int xbox_rows = (NR + nbox - 1) / nbox;
+    MPPIB_REQUIRE(NR % xbox_rows == 0, "mppib_reduce: T*nu = %d cannot be split into equal TMA boxes", NR);
+    CUtensorMap tm_x, tm_c;
+    if (int rc = make_map(&tm_x, x, NR, K, xbox_rows, W)) return rc;
+    if (int rc = make_map(&tm_c, cost, T, K, T, W)) return rc;
+    const int ntiles = (K + W - 1) / W;
+    int grid = ntiles < c->num_sms ? ntiles : c->num_sms;
+    if (grid > MAX_GRID) grid = MAX_GRID;
     MPPIB_REQUIRE(grid <= c->reduce_max_ctas, "mppib_reduce: scratch too small");
-    reduce_kernel<<<grid, NT, smem, s>>>(c->params, nu, cost, x, U, c->reduce_scratch, c->reduce_ticket, partial);
+    mppib_reduce_kernel<W, NS><<<grid, NT, smem, s>>>(c->params, tm_x, tm_c, nu, xbox_rows, U, c->reduce_scratch, c->reduce_ticket, partial);
     MPPIB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
+}  // namespace
+
+int launch_reduce(MppibContext* c, const float* cost, const float* x, const float* U, float* partial, cudaStream_t s) {
+    const int T = c->params.T, nu = c->model.nu;
+    MPPIB_REQUIRE(T * nu <= RPT * NT, "mppib_reduce: T*nu = %d exceeds %d", T * nu, RPT * NT);
+    MPPIB_REQUIRE(T <= 256, "mppib_reduce: T = %d exceeds the 256-row TMA box", T);
+    // wide tiles once every SM has several of them; narrow tiles keep all SMs busy at small K
+    const bool wide = c->params.K >= 64 * c->num_sms * 3 && reduce_smem_bytes<64, 3>(T, nu) <= 226 * 1024;
+    if (wide) return launch_reduce_t<64, 3>(c, cost, x, U, partial, s);
+    if (reduce_smem_bytes<32, 4>(T, nu) <= 226 * 1024) return launch_reduce_t<32, 4>(c, cost, x, U, partial, s);
+    return launch_reduce_t<32, 2>(c, cost, x, U, partial, s);
+}
+
 int launch_finalize(MppibContext* c, const float* partials, int G, float* U, float* action_out, float* stats, cudaStream_t s) {
     const int NR = c->params.T * c->model.nu;
-    finalize_kernel<<<1, 512, NR * sizeof(float), s>>>(c->params, c->model.nu, partials, G, U, action_out, stats);
+    mppib_finalize_kernel<<<1, 256, (NR + G) * sizeof(float), s>>>(c->params, c->model.nu, partials, G, U, action_out, stats);
     MPPIB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 int launch_shift(MppibContext* c, float* U, uint32_t* plan_ctr, cudaStream_t s) {
     const int NR = c->params.T * c->model.nu;
-    shift_kernel<<<1, 256, NR * sizeof(float), s>>>(c->params, c->model.nu, U, plan_ctr);
+    mppib_shift_kernel<<<1, 256, NR * sizeof(float), s>>>(c->params, c->model.nu, U, plan_ctr);
     MPPIB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

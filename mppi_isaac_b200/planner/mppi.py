@@ -207,6 +207,7 @@ class MPPIPlanner:
                 self._try_capture()
             if self._graph is not None:
                 self._graph.replay()
+                self.sim.mark_batched()
             else:
                 self._plan_batched()
         else:

@@ -106,8 +106,7 @@ class MPPIisaacPlanner(object):
 
     def reset_rollout_sim(self, dof_state_tensor, root_state_tensor, rigid_body_state_tensor=None):
         self.sim.visualize_link_buffer = []
-        self.sim.set_world_state(bytes_to_torch(dof_state_tensor), bytes_to_torch(root_state_tensor))
-        if self.sim.sync_base_pose():
+        if self.sim.set_world_state(bytes_to_torch(dof_state_tensor), bytes_to_torch(root_state_tensor)):
             self.mppi.invalidate_graph()       # the robot base pose is a kernel constant
 
     def compute_action_tensor(self, dof_state_tensor, root_state_tensor):

@@ -81,9 +81,17 @@ class RolloutSim:
         self.robot_indices = torch.tensor([i for i, a in enumerate(self.env_cfg) if a.type == "robot"], device=dev)
         self.obstacle_indices = torch.tensor(
             [i for i, a in enumerate(self.env_cfg) if a.type in ("sphere", "box") and a.name != "dummy"], device=dev)
-        self._root0 = torch.from_numpy(sc.root_state0.copy()).to(dev)            # (A,13) one world state
+        # ONE world state for all K rollouts, kept in a single device buffer [state0 (NS) | root0 (A*13)] so that a
+        # world update is one host->device copy from a pinned staging buffer
         dof0 = sc.dof_state0
-        self._state0 = torch.from_numpy(np.concatenate([dof0[0::2], dof0[1::2]]).astype(np.float32)).to(dev)  # (NS,) [q | qd]
+        ns, na = 2 * sc.ndof, len(self.env_cfg)
+        host = np.concatenate([dof0[0::2], dof0[1::2], sc.root_state0.reshape(-1)]).astype(np.float32)
+        self._world = torch.from_numpy(host.copy()).to(dev)
+        self._state0 = self._world[:ns]                                           # (NS,) [q | qd]
+        self._root0 = self._world[ns:].view(na, 13)                               # (A,13)
+        self._stage = torch.from_numpy(host.copy())
+        if torch.device(dev).type == "cuda":
+            self._stage = self._stage.pin_memory()
         if self._visualize_link_present:
             rcfg = self.env_cfg[sc.robot_actor]
             self._viz_link = sc.robot.link_names.index(rcfg.visualize_link)
@@ -125,11 +133,17 @@ class RolloutSim:
         self._backend.create(sc.model, self.params)
         assert self._backend.obs_size() == self._R
         NS = self._backend.state_size()
-        self._state = self._state0[:, None].repeat(1, K).contiguous() if K else None   # (NS,K)
+        self._state = self._state0[:, None].repeat(1, K).contiguous()                  # (NS,K)
         assert self._state.shape[0] == NS
         self._obs = torch.zeros((max(self._R, 1), T, K), dtype=torch.float32, device=dev)
         self._cmd = torch.zeros((sc.nu, K), dtype=torch.float32, device=dev)
         self._state_is_broadcast = True
+        self._state_stale = False
+
+    def _sync_step_state(self):
+        if self._state_stale:
+            self._state.copy_(self._state0[:, None].expand(-1, self.num_envs))
+            self._state_stale = False
 
     @property
     def backend(self):
@@ -195,6 +209,7 @@ class RolloutSim:
 
     def _refresh_initial(self):
         """Observe the current state into slot 0 (reference: refresh_* right after a reset)."""
+        self._sync_step_state()
         self._backend.rollout(None, self._state, self._cmd, 0, 0, self._obs, act_t0=0)
         self._have_obs = True
         self._slot = 0
@@ -353,7 +368,10 @@ class RolloutSim:
             self.sync_base_pose()
 
     def sync_base_pose(self):
-        row = self._root0[self.scene.robot_actor].detach().cpu().numpy()
+        return self._sync_base_pose_from(self._root0[self.scene.robot_actor].detach().cpu())
+
+    def _sync_base_pose_from(self, row):
+        row = row.numpy() if hasattr(row, "numpy") else row
         m = self.scene.model
         changed = False
         for i in range(3):
@@ -373,8 +391,8 @@ class RolloutSim:
         if state.dim() == 1 or state.shape[0] == 1:
             row = state.reshape(-1)
             self._state0.copy_(torch.cat([row[0:2 * nd:2], row[1:2 * nd:2]]))   # in place: the pointer is baked into CUDA graphs
-            self._state.copy_(self._state0[:, None].expand(-1, self.num_envs))
             self._state_is_broadcast = True
+            self._state_stale = True          # the (NS,K) step-protocol buffer is refreshed lazily
         else:
             self._state[:nd] = state[:, 0:2 * nd:2].t()
             self._state[nd:2 * nd] = state[:, 1:2 * nd:2].t()
@@ -403,6 +421,7 @@ class RolloutSim:
     def step(self):
         """One model step of length dt for all K rollouts (mppib_rollout with nsteps = 1)."""
         self._mode = "step"
+        self._sync_step_state()
         t = self._t % self._T
         self._backend.rollout(None, self._state, self._cmd, t, 1, self._obs, act_t0=t)
         self._state_is_broadcast = False
@@ -415,6 +434,10 @@ class RolloutSim:
     def rollout_all(self, actions: torch.Tensor):
         """Whole horizon in ONE launch from the broadcast world state; switches getters to batched views."""
         self._backend.rollout(self._state0, None, actions, 0, self._T, self._obs, act_t0=0)
+        self.mark_batched()
+
+    def mark_batched(self):
+        """Host-side bookkeeping after a whole-horizon rollout (also called after a CUDA-graph replay)."""
         self._mode = "batched"
         self._have_obs = True
         self._t = 0
@@ -425,7 +448,8 @@ class RolloutSim:
     def begin_step_mode(self):
         """Re-arm the step protocol from the broadcast world state."""
         self._mode = "step"
-        self._state.copy_(self._state0[:, None].expand(-1, self.num_envs))
+        self._state_stale = True
+        self._sync_step_state()
         self._state_is_broadcast = True
         self._have_obs = False
         self._t = 0
@@ -457,11 +481,27 @@ class RolloutSim:
         self.set_actor_dof_state(torch.tensor(dof_state, dtype=torch.float32))
 
     def set_world_state(self, dof_state_row: torch.Tensor, root_state: torch.Tensor):
-        """(1,2*ndof) + (1,A,13) world snapshot -> all rollouts (mppi_isaac.py:87-99)."""
-        root = torch.as_tensor(root_state, dtype=torch.float32).reshape(-1, 13)
-        self._root0.copy_(root.to(self.device, non_blocking=True))
-        self.set_actor_dof_state(torch.as_tensor(dof_state_row, dtype=torch.float32).reshape(-1).to(self.device, non_blocking=True))
+        """(1,2*ndof) + (1,A,13) world snapshot -> all rollouts (mppi_isaac.py:87-99).
+        Host tensors go through the pinned staging buffer: one H2D copy, no device->host traffic.
+        Returns True when the robot base pose (a kernel constant) changed."""
+        root = torch.as_tensor(root_state).reshape(-1, 13)
+        dof = torch.as_tensor(dof_state_row).reshape(-1)
+        nd = self.scene.ndof
         self.visualize_link_buffer = []
+        if root.device.type != "cpu" or dof.device.type != "cpu":
+            self._root0.copy_(root.to(self.device, dtype=torch.float32))
+            self.set_actor_dof_state(dof.to(self.device, dtype=torch.float32))
+            return self.sync_base_pose()
+        st = self._stage
+        st[:nd] = dof[0:2 * nd:2]
+        st[nd:2 * nd] = dof[1:2 * nd:2]
+        st[2 * nd:] = root.reshape(-1)
+        self._world.copy_(st, non_blocking=True)
+        self._state_is_broadcast = True
+        self._state_stale = True
+        self._have_obs = False
+        self._t = 0
+        return self._sync_base_pose_from(st[2 * nd:].view(-1, 13)[self.scene.robot_actor])
 
     def save_root_state(self):
         self.saved_root_state = self._root0.clone()

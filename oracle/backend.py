@@ -1,13 +1,13 @@
 """Checker backend: the CPU oracle behind the same interface as ``mppi_isaac_b200.backend.CudaBackend``.
 
-TEST INFRASTRUCTURE.  It lets the `-m "not gpu"` suite drive the host logic (planner sequencing, facade views,
+TEST INFRASTRUCTURE (also the CPU-baseline arm of bench.py).  It lets the `-m "not gpu"` suite drive the host logic (planner sequencing, facade views,
 sharding, transport) end to end on CPU tensors, and gives the GPU parity tests a planner-level reference.  The
 product package never imports this file or ``oracle/``.
 """
 import numpy as np
 import torch
 
-from oracle import oracle as orc
+from . import oracle as orc
 
 
 def _np(t):

@@ -48,6 +48,19 @@ def point_setup(K=128, T=12, mode="simple", **kw):
     return sc, p, state0
 
 
+def gripper_setup(K=64, T=30, mode="simple", **kw):
+    """panda + two-finger gripper: a TREE (both fingers hang off link 7) -> exercises the general-topology kernel path."""
+    sc = build_scene(load_actor_cfgs(["panda_gripper", "goal"]))
+    names = sc.robot.link_names
+    obs = [(OBS_LINK_STATE, names.index("panda_ee")), (OBS_DOF_STATE, 0), (OBS_LINK_STATE, names.index("panda_leftfinger")),
+           (OBS_LINK_STATE, names.index("panda_rightfinger"))]
+    mc = panda_mppi(K, T, mode, noise_sigma=(0.1 * np.eye(9)).tolist(), **kw)
+    p = make_params(mc, IsaacGymConfig(), sc.nu, K, obs)
+    dof0 = sc.dof_state0
+    state0 = np.concatenate([dof0[0::2], dof0[1::2]]).astype(np.float32)
+    return sc, p, state0
+
+
 def panda_cfg(K=64, T=30, device="cpu", **mppi_kw):
     cfg = load_isaacgym_config("config_panda_b200")
     cfg = copy.deepcopy(cfg)

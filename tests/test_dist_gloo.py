@@ -28,7 +28,7 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from mppi_isaac_b200 import MPPIisaacPlanner
     from mppi_isaac_b200.objectives import PandaReachObjective
-    from oracle_backend import OracleBackend
+    from oracle.backend import OracleBackend
     from scenes import panda_cfg
     p = MPPIisaacPlanner(panda_cfg(K=64, T=12), PandaReachObjective(), backend=OracleBackend())
     assert p.sim.num_envs == 64 // world and p.k_offset == rank * (64 // world)
@@ -46,7 +46,7 @@ def test_two_rank_sharded_plan_matches_single_process(tmp_path):
     sys.path.insert(0, HERE)
     from mppi_isaac_b200 import MPPIisaacPlanner
     from mppi_isaac_b200.objectives import PandaReachObjective
-    from oracle_backend import OracleBackend
+    from oracle.backend import OracleBackend
     from scenes import panda_cfg
     single = MPPIisaacPlanner(panda_cfg(K=64, T=12), PandaReachObjective(), backend=OracleBackend())
     ref = np.stack([single.compute_action(Q0, [0] * 7).numpy() for _ in range(3)])

@@ -13,7 +13,7 @@ import pytest
 import torch
 
 from mppi_isaac_b200.model.blob import MODE_SIMPLE, OBS_DOF_STATE, OBS_LINK_STATE
-from scenes import panda_cfg, panda_setup, point_cfg, point_setup
+from scenes import gripper_setup, panda_cfg, panda_setup, point_cfg, point_setup
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -66,7 +66,7 @@ def test_k1_sample_parity(oracle, setup, K, T):
     np.testing.assert_array_equal(np.concatenate(parts, axis=2), a)
 
 
-@pytest.mark.parametrize("setup,K,T", [(panda_setup, 1000, 30), (point_setup, 128, 12)])
+@pytest.mark.parametrize("setup,K,T", [(panda_setup, 1000, 30), (point_setup, 128, 12), (gripper_setup, 512, 30)])
 def test_k2_rollout_parity_free_running(oracle, setup, K, T):
     sc, p, state0 = setup(K=K, T=T)
     be = gpu_backend(sc, p)
@@ -85,7 +85,11 @@ def test_k2_rollout_parity_free_running(oracle, setup, K, T):
     qa, qb = o[3:7], obs_ref[3:7]
     assert np.minimum(np.abs(qa - qb), np.abs(qa + qb)).max() <= 2e-5      # quaternion up to sign
     assert np.abs(o[7:13] - obs_ref[7:13]).max() <= 2e-3                   # link velocities (x kd amplification)
-    assert np.abs(o[13:] - obs_ref[13:]).max() <= 2e-3
+    dof_rows = slice(13, 13 + 2 * nb)
+    assert np.abs(o[dof_rows] - obs_ref[dof_rows]).max() <= 2e-3
+    for r0 in range(13 + 2 * nb, o.shape[0], 13):                          # further observed links (gripper fingers)
+        assert np.abs(o[r0:r0 + 3] - obs_ref[r0:r0 + 3]).max() <= 1e-4
+        assert np.minimum(np.abs(o[r0 + 3:r0 + 7] - obs_ref[r0 + 3:r0 + 7]), np.abs(o[r0 + 3:r0 + 7] + obs_ref[r0 + 3:r0 + 7])).max() <= 2e-5
 
 
 def test_k2_one_step_lockstep(oracle):
@@ -179,19 +183,20 @@ def test_k3_properties_at_baseline_sizes():
         cost[:, 777] = -1e3
         be.reduce(cost, x, U, partial)
         torch.testing.assert_close(partial[2:] / partial[1], x[:, :, 777].reshape(-1), atol=1e-6, rtol=0)
-        # shard-combine invariance: 8 shards through K4 == 1 shard through K4
+        # shard-combine invariance: G shards through K4 == 1 shard through K4
         cost = torch.rand((30, K), device=DEV, generator=g) * 5
         be.reduce(cost, x, U, partial)
         U1, act = torch.zeros((30, 7), device=DEV), torch.zeros(7, device=DEV)
         be.finalize(partial.view(1, -1), 1, U1, act, None)
-        p8 = copy.copy(p); p8.K = K // 8
+        G = 8 if K % 32 == 0 else 4                                        # shards must stay multiples of 4
+        p8 = copy.copy(p); p8.K = K // G
         be8 = gpu_backend(sc, p8)
-        parts = torch.zeros((8, 212), device=DEV)
-        for s in range(8):
+        parts = torch.zeros((G, 212), device=DEV)
+        for s in range(G):
             sl = slice(s * p8.K, (s + 1) * p8.K)
             be8.reduce(cost[:, sl].contiguous(), x[:, :, sl].contiguous(), U, parts[s])
         U8 = torch.zeros((30, 7), device=DEV)
-        be8.finalize(parts, 8, U8, act, None)
+        be8.finalize(parts, G, U8, act, None)
         torch.testing.assert_close(U8, U1, atol=2e-6, rtol=0)
 
 
@@ -200,7 +205,7 @@ def test_full_plan_parity_through_planner_api(robot):
     """MPPIisaacPlanner on the GPU (CUDA graph on) vs the same planner on the checker backend, closed loop."""
     from mppi_isaac_b200 import MPPIisaacPlanner
     from mppi_isaac_b200.objectives import PandaReachObjective, PointReachObjective
-    from oracle_backend import OracleBackend
+    from oracle.backend import OracleBackend
     if robot == "panda":
         mk, obj, q = (lambda d: panda_cfg(K=1000, T=30, device=d)), PandaReachObjective, np.array([0.0, -0.94, 0.0, -2.8, 0.0, 1.8675, 0.0])
     else:

@@ -11,7 +11,7 @@ from mppi_isaac_b200.planner.rollout_sim import ObservationError, RolloutSim
 from mppi_isaac_b200.utils.config_store import IsaacGymConfig
 from mppi_isaac_b200.utils.conversions import matrix_to_euler_angles, quaternion_to_matrix, quaternion_to_yaw
 from mppi_isaac_b200.utils.transport import bytes_to_torch, torch_to_bytes
-from oracle_backend import OracleBackend
+from oracle.backend import OracleBackend
 from scenes import panda_cfg, point_cfg
 
 Q0 = [0.0, -0.94, 0.0, -2.8, 0.0, 1.8675, 0.0]
