@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MPPIB_ABI_VERSION 3
+#define MPPIB_ABI_VERSION 4
 
 #define MPPIB_MAX_BODIES 16   /* moving (1-DoF) bodies of the articulation            */
 #define MPPIB_MAX_LINKS  32   /* URDF links whose state can be observed               */
@@ -51,6 +51,8 @@ extern "C" {
 #define MPPIB_MAX_OBS    64   /* observation items                                    */
 #define MPPIB_MAX_FREE   4    /* free rigid bodies (box / sphere actors)              */
 #define MPPIB_MAX_SHAPES 24   /* collision primitives                                 */
+#define MPPIB_MAX_CONTACTS 24 /* contact points kept per rollout and substep             */
+#define MPPIB_MAX_SLOTS  8    /* bodies whose net contact force is tracked            */
 
 /* joint types (body frame is chosen so the joint axis is +z) */
 #define MPPIB_JOINT_REVOLUTE  0
@@ -122,24 +124,38 @@ typedef struct MppibModel {
     float   link_p[MPPIB_MAX_LINKS][3];
     float   link_quat[MPPIB_MAX_LINKS][4]; /* link_R as a unit quaternion, xyzw                   */
 
-    /* free rigid bodies (box / sphere actors that are not fixed) */
+    /* free rigid bodies: box actors that are not fixed (isaacgym_utils.py:29-40, isaacgym_wrapper.py:450-456).
+       Their initial state is row free_actor[f] of the root-state buffer handed to mppib_rollout.           */
+    int32_t free_actor[MPPIB_MAX_FREE];
     float   free_mass[MPPIB_MAX_FREE];
-    float   free_inertia[MPPIB_MAX_FREE][3];   /* principal, body frame                           */
+    float   free_mass_pct[MPPIB_MAX_FREE];     /* noise_percentage_mass: mass *= 1 + pct * U(-1,1) per rollout */
+    float   free_half[MPPIB_MAX_FREE][3];      /* box half extents (solid-box inertia for the configured mass) */
     int32_t free_gravity[MPPIB_MAX_FREE];
+    int32_t free_slot[MPPIB_MAX_FREE];         /* row of the net-contact-force table, -1 none                  */
 
-    /* collision primitives */
+    /* collision boxes.  owner kind STATIC: pose = root state of actor shape_actor; LINK: rigidly attached to
+       articulation body shape_owner (-1 = base) with the local pose below; FREE: free body shape_owner.     */
     int32_t shape_type[MPPIB_MAX_SHAPES];
     int32_t shape_owner_kind[MPPIB_MAX_SHAPES];
     int32_t shape_owner[MPPIB_MAX_SHAPES];
-    int32_t shape_contact_slot[MPPIB_MAX_SHAPES]; /* row of the net-contact-force table, -1 none  */
-    float   shape_size[MPPIB_MAX_SHAPES][3];   /* box half extents / sphere radius in [0]         */
-    float   shape_pos[MPPIB_MAX_SHAPES][3];    /* pose in the owner frame (world for static)      */
+    int32_t shape_actor[MPPIB_MAX_SHAPES];     /* actor index (root-state row) for STATIC / FREE, -1 for LINK  */
+    int32_t shape_slot[MPPIB_MAX_SHAPES];      /* row of the net-contact-force table, -1 none                  */
+    float   shape_half[MPPIB_MAX_SHAPES][3];   /* box half extents                                             */
+    float   shape_pos[MPPIB_MAX_SHAPES][3];    /* pose in the owner frame                                      */
     float   shape_quat[MPPIB_MAX_SHAPES][4];
     float   shape_friction[MPPIB_MAX_SHAPES];
+    float   shape_fric_pct[MPPIB_MAX_SHAPES];  /* noise_percentage_friction (isaacgym_wrapper.py:468-475)      */
+    float   shape_size_sigma[MPPIB_MAX_SHAPES][3]; /* noise_sigma_size on the FULL box size (isaacgym_utils.py:29-40) */
     int32_t ncontact_slots;
-    int32_t ground_plane;                  /* add_ground_plane (isaacgym_utils.py:61-68)          */
-    float   contact_kp;                    /* penalty stiffness  [N/m]                            */
-    float   contact_kd;                    /* penalty damping    [N s/m]                          */
+    int32_t ground_plane;                  /* add_ground_plane: z = 0, friction 1 (isaacgym_utils.py:61-68)    */
+    float   ground_friction;
+    float   contact_kp;                    /* penalty stiffness  [N/m]   (integrated implicitly)               */
+    float   contact_kd;                    /* penalty damping    [N s/m]                                       */
+    float   max_depen;                     /* cap of the penetration-recovery velocity [m/s]                   */
+    float   ground_margin;                 /* speculative-contact distance to the ground plane [m]             */
+    float   contact_margin;                /* speculative-contact distance between boxes [m] (PhysX contact_offset 0.01) */
+    int32_t contact_iters;                 /* Gauss-Seidel sweeps over the contact set per substep             */
+    int32_t nactors;                       /* rows of the root-state buffer                                    */
 } MppibModel;
 
 typedef struct MppibObsItem {
@@ -164,6 +180,8 @@ typedef struct MppibParams {
     float   u_init[MPPIB_MAX_NU];
     float   sigma_chol[MPPIB_MAX_NU * MPPIB_MAX_NU]; /* lower Cholesky factor of noise_sigma, row major nu x nu */
     float   sigma_inv[MPPIB_MAX_NU * MPPIB_MAX_NU];  /* inverse of noise_sigma, row major nu x nu               */
+    uint32_t k_offset;         /* global index of local sample 0 (keys the per-rollout randomisation) */
+    uint32_t rand_seed;        /* seed of the per-rollout size / mass / friction draws              */
     int32_t nobs;
     MppibObsItem obs[MPPIB_MAX_OBS];
 } MppibParams;
@@ -193,12 +211,13 @@ int32_t mppib_sample(MppibHandle h, uint64_t seed, uint64_t plan_idx, const uint
                      uint32_t k_offset, uint32_t k_total, const float* U, const float* prior_row,
                      float* actions, float* noise, void* stream);
 
-/* K2: broadcast initial state state0[NS] (one row, shared by all K) or continue from
- * state[NS][K] when state0 == NULL; apply actions[t0 .. t0+nsteps) ; write obs and the
+/* K2: broadcast initial state state0[2*ndof] (+ free bodies from root0) to all K rollouts, or continue
+ * from state[NS][K] when state0 == NULL; root0[nactors][13] holds the world's actor root states (poses of
+ * static boxes, initial states of free bodies) and may be NULL for contact-free scenes; apply actions[t0 .. t0+nsteps) ; write obs and the
  * final state.  nsteps == T for a whole plan, 1 for the reference's step-wise protocol,
  * 0 to only write the observation of the current state into slot t0.                        */
-int32_t mppib_rollout(MppibHandle h, const float* state0, float* state, const float* actions,
-                      int32_t t0, int32_t nsteps, float* obs, void* stream);
+int32_t mppib_rollout(MppibHandle h, const float* state0, const float* root0, float* state,
+                      const float* actions, int32_t t0, int32_t nsteps, float* obs, void* stream);
 
 /* K3: S_k = sum_t gamma^t cost[t][k] (+ lambda sum_t U_t^T Sigma^-1 noise_k,t in SIMPLE mode),
  * beta_g = min_k S_k, w_k = exp(-(S_k - beta_g)/lambda), eta_g = sum w_k,

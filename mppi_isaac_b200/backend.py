@@ -118,11 +118,11 @@ class CudaBackend:
         self._check(self.lib.mppib_sample(self.handle, C.c_uint64(seed), C.c_uint64(plan_idx), _ptr(plan_ctr), C.c_uint32(k_offset), C.c_uint32(k_total),
                                           _ptr(U), _ptr(prior_row), _ptr(actions), _ptr(noise), self._stream()), "mppib_sample")
 
-    def rollout(self, state0, state, actions, t0, nsteps, obs, act_t0=0):
+    def rollout(self, state0, state, actions, t0, nsteps, obs, act_t0=0, root0=None):
         """``actions`` holds time slices [act_t0, ...) laid out [t][nu][K]; steps t0..t0+nsteps-1 are executed."""
         self.launches += 1
         base = actions.data_ptr() - act_t0 * self.model.nu * self.params.K * 4
-        self._check(self.lib.mppib_rollout(self.handle, _ptr(state0), _ptr(state), C.c_void_p(base), C.c_int32(t0), C.c_int32(nsteps),
+        self._check(self.lib.mppib_rollout(self.handle, _ptr(state0), _ptr(root0), _ptr(state), C.c_void_p(base), C.c_int32(t0), C.c_int32(nsteps),
                                            _ptr(obs), self._stream()), "mppib_rollout")
 
     def reduce(self, cost, x, U, partial):

@@ -19,7 +19,14 @@ static int validate(const MppibModel* m, const MppibParams* p) {
     MPPIB_REQUIRE(m->nb >= 1 && m->nb <= MPPIB_MAX_BODIES, "nb=%d out of range", m->nb);
     MPPIB_REQUIRE(m->nlinks >= 0 && m->nlinks <= MPPIB_MAX_LINKS, "nlinks=%d out of range", m->nlinks);
     MPPIB_REQUIRE(m->nu >= 1 && m->nu <= MPPIB_MAX_NU, "nu=%d out of range", m->nu);
-    MPPIB_REQUIRE(m->nfree == 0 && m->nshapes == 0, "free bodies / contact shapes are not supported by this build");
+    MPPIB_REQUIRE(m->nfree >= 0 && m->nfree <= MPPIB_MAX_FREE && m->nshapes >= 0 && m->nshapes <= MPPIB_MAX_SHAPES, "nfree / nshapes out of range");
+    for (int s = 0; s < m->nshapes; ++s) {
+        MPPIB_REQUIRE(m->shape_slot[s] >= -1 && m->shape_slot[s] < MPPIB_MAX_SLOTS, "shape %d: contact slot out of range", s);
+        if (m->shape_owner_kind[s] != MPPIB_OWNER_LINK) MPPIB_REQUIRE(m->shape_actor[s] >= 0 && m->shape_actor[s] < m->nactors, "shape %d: actor index out of range", s);
+        if (m->shape_owner_kind[s] == MPPIB_OWNER_LINK) MPPIB_REQUIRE(m->shape_owner[s] >= -1 && m->shape_owner[s] < m->nb, "shape %d: body index out of range", s);
+        if (m->shape_owner_kind[s] == MPPIB_OWNER_FREE) MPPIB_REQUIRE(m->shape_owner[s] >= 0 && m->shape_owner[s] < m->nfree, "shape %d: free body index out of range", s);
+    }
+    for (int f = 0; f < m->nfree; ++f) MPPIB_REQUIRE(m->free_actor[f] >= 0 && m->free_actor[f] < m->nactors && m->free_mass[f] > 0.f, "free body %d invalid", f);
     for (int i = 0; i < m->nb; ++i) {
         MPPIB_REQUIRE(m->parent[i] >= -1 && m->parent[i] < i, "parent[%d]=%d is not topologically sorted", i, m->parent[i]);
         MPPIB_REQUIRE(m->cmd_i0[i] >= 0 && m->cmd_i0[i] < m->nu && m->cmd_i1[i] >= 0 && m->cmd_i1[i] < m->nu, "cmd map of dof %d out of range", i);
@@ -33,6 +40,8 @@ static int validate(const MppibModel* m, const MppibParams* p) {
         const int kd = p->obs[i].kind, ix = p->obs[i].index;
         MPPIB_REQUIRE(kd >= 0 && kd <= MPPIB_OBS_CONTACT, "obs[%d].kind invalid", i);
         if (kd == MPPIB_OBS_LINK_STATE) MPPIB_REQUIRE(ix >= 0 && ix < m->nlinks, "obs[%d] link index %d out of range", i, ix);
+        if (kd == MPPIB_OBS_FREE_STATE) MPPIB_REQUIRE(ix >= 0 && ix < MPPIB_MAX_FREE, "obs[%d] free body index %d out of range", i, ix);
+        if (kd == MPPIB_OBS_CONTACT) MPPIB_REQUIRE(ix >= 0 && ix < MPPIB_MAX_SLOTS, "obs[%d] contact slot %d out of range", i, ix);
     }
     return 0;
 }
@@ -122,12 +131,12 @@ int32_t mppib_sample(MppibHandle h, uint64_t seed, uint64_t plan_idx, const uint
     return launch_sample(h, seed, plan_idx, plan_ctr, k_offset, k_total, U, prior_row, actions, noise, (cudaStream_t)stream);
 }
 
-int32_t mppib_rollout(MppibHandle h, const float* state0, float* state, const float* actions, int32_t t0, int32_t nsteps,
+int32_t mppib_rollout(MppibHandle h, const float* state0, const float* root0, float* state, const float* actions, int32_t t0, int32_t nsteps,
                       float* obs, void* stream) {
     MPPIB_REQUIRE(h && actions, "mppib_rollout: null argument");
     MPPIB_REQUIRE(state0 || state, "mppib_rollout: need state0 (broadcast) or state (continue)");
     MPPIB_REQUIRE(t0 >= 0 && nsteps >= 0 && t0 + (nsteps > 0 ? nsteps : 1) <= h->params.T, "mppib_rollout: steps [%d,%d) outside horizon %d", t0, t0 + nsteps, h->params.T);
-    return launch_rollout(h, state0, state, actions, t0, nsteps, obs, (cudaStream_t)stream);
+    return launch_rollout(h, state0, root0, state, actions, t0, nsteps, obs, (cudaStream_t)stream);
 }
 
 int32_t mppib_reduce(MppibHandle h, const float* cost, const float* x, const float* U, float* partial, void* stream) {

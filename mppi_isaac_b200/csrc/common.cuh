@@ -45,7 +45,7 @@ struct MppibContext {
 // kernel launchers (defined in the .cu files)
 int launch_sample(MppibContext* c, uint64_t seed, uint64_t plan_idx, const uint32_t* plan_ctr, uint32_t k_offset, uint32_t k_total,
                   const float* U, const float* prior_row, float* actions, float* noise, cudaStream_t s);
-int launch_rollout(MppibContext* c, const float* state0, float* state, const float* actions, int t0, int nsteps,
+int launch_rollout(MppibContext* c, const float* state0, const float* root0, float* state, const float* actions, int t0, int nsteps,
                    float* obs, cudaStream_t s);
 int launch_reduce(MppibContext* c, const float* cost, const float* x, const float* U, float* partial, cudaStream_t s);
 int launch_finalize(MppibContext* c, const float* partials, int G, float* U, float* action_out, float* stats, cudaStream_t s);

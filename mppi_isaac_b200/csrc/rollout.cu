@@ -183,13 +183,16 @@ __device__ __forceinline__ void body_kinematics(const MppibModel& m, int i, floa
     out.V.f = par.V.f + qd * S.f;
 }
 
-template <bool CHAIN>
+#include "contact.cuh"
+
+template <bool CHAIN, bool CONTACT>
 __global__ void __launch_bounds__(32)
 mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant__ MppibParams p,
-                     const float* __restrict__ state0, float* __restrict__ state, const float* __restrict__ actions,
-                     int t0, int nsteps, float* __restrict__ obs) {
+                     const float* __restrict__ state0, const float* __restrict__ root0, float* __restrict__ state,
+                     const float* __restrict__ actions, int t0, int nsteps, float* __restrict__ obs) {
     extern __shared__ float sm[];
-    constexpr int NSLOT = CHAIN ? NSLOT_CHAIN : NSLOT_TREE;
+    constexpr int NSLOT = (CHAIN && !CONTACT) ? NSLOT_CHAIN : NSLOT_TREE;
+    constexpr bool STORE_FRAMES = !CHAIN || CONTACT;     // world frame of every body kept in shared memory
     const int K = p.K, T = p.T, nu = m.nu, nb = m.nb;
     const int lane = threadIdx.x;
     const int k = blockIdx.x * 32 + lane;
@@ -201,6 +204,9 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
         SM(i, F_Q) = state0 ? state0[i] : state[(size_t)i * K + k];
         SM(i, F_QD) = state0 ? state0[nb + i] : state[(size_t)(nb + i) * K + k];
     }
+    float* xs = sm + (size_t)nb * NSLOT * 32;             // free bodies / shapes / contacts (CONTACT kernels only)
+    const contact::Layout L(nb, m.nfree, m.nshapes);
+    if (CONTACT) contact::init(m, p, L, xs, lane, p.k_offset + (uint32_t)k, root0, state, state0 != nullptr, K, k);
     Frame base;
     const Quat bq = {m.base_quat[0], m.base_quat[1], m.base_quat[2], m.base_quat[3]};
     base.R = quat_to_R(bq);
@@ -271,7 +277,7 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
                     st6(sm, i * NSLOT + F_PB, lane, pb);
                     SM(i, F_SAT) = 0.f;
                     if (CHAIN) par = f;
-                    else { stM3(sm, i * NSLOT + F_R, lane, f.R); st3(sm, i * NSLOT + F_O, lane, f.o); st6(sm, i * NSLOT + F_V, lane, f.V); }
+                    if (STORE_FRAMES) { stM3(sm, i * NSLOT + F_R, lane, f.R); st3(sm, i * NSLOT + F_O, lane, f.o); st6(sm, i * NSLOT + F_V, lane, f.V); }
                 }
             }
 #pragma unroll 1
@@ -306,7 +312,9 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
                     else if (vel_mode) { tau = kd * (tgt - qdi) - b * qdi; dimp = m.armature[i] + h * (kd + b); }
                     else { tau = fminf(fmaxf(tgt, -m.effort[i]), m.effort[i]) - (kd + b) * qdi; dimp = m.armature[i] + h * (kd + b); }
                     const V6 U = mul(IA, S);
-                    const float invD = __frcp_rn(dot6(S, U) + dimp);
+                    const float Dj = dot6(S, U) + dimp;
+                    const float invD = __frcp_rn(Dj);
+                    if (CONTACT) xs[(L.jv0 + nb + i) * 32 + lane] = fmaxf(Dj, 1e-6f);   // joint compliance of the contact solve
                     const float uu = tau - dot6(S, pA);
                     st6(sm, i * NSLOT + F_U, lane, U);
                     SM(i, F_INVD) = invD; SM(i, F_UU) = uu;
@@ -346,15 +354,28 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
                 }
                 if (!any) break;
             }
+            if (CONTACT) {
+                // ------------------------------------------------------------------ contacts on the predicted velocities
+                for (int i = 0; i < nb; ++i) { xs[(L.jv0 + 2 * nb + i) * 32 + lane] = SM(i, F_QD) + h * SM(i, F_QDD); xs[(L.jv0 + i) * 32 + lane] = 0.f; }
+                contact::shapes_world<NSLOT>(m, L, sm, xs, lane, base.R, base.o, root0);
+                const int nc = contact::detect(m, L, xs, lane);
+                for (int f = 0; f < m.nfree; ++f) if (m.free_gravity[f]) {
+                    const int fb = L.fb0 + f * contact::FBN;
+                    xs[(fb + contact::FB_V) * 32 + lane] += h * m.gravity[0]; xs[(fb + contact::FB_V + 1) * 32 + lane] += h * m.gravity[1];
+                    xs[(fb + contact::FB_V + 2) * 32 + lane] += h * m.gravity[2];
+                }
+                contact::solve<NSLOT>(m, L, sm, xs, lane, nc, h);
+            }
             // ------------------------------------------------------------------ integrate
             for (int i = 0; i < nb; ++i) {
-                float v = SM(i, F_QD) + h * SM(i, F_QDD);
+                float v = CONTACT ? xs[(L.jv0 + 2 * nb + i) * 32 + lane] + xs[(L.jv0 + i) * 32 + lane] : SM(i, F_QD) + h * SM(i, F_QDD);
                 v = fminf(fmaxf(v, -m.qd_max[i]), m.qd_max[i]);
                 float x = SM(i, F_Q) + h * v;
                 if (x < m.q_lo[i]) { x = m.q_lo[i]; if (v < 0.f) v = 0.f; }
                 if (x > m.q_hi[i]) { x = m.q_hi[i]; if (v > 0.f) v = 0.f; }
                 SM(i, F_Q) = x; SM(i, F_QD) = v;
             }
+            if (CONTACT) contact::integrate_free(m, L, xs, lane, h);
         }
         if (obs == nullptr) continue;
         // ---------------------------------------------------------------------------------- observe
@@ -413,10 +434,13 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
                     dst[(size_t)(row + 2 * i + 1) * TK] = SM(i, F_QD);
                 }
                 row += 2 * nb;
+            } else if (kind == MPPIB_OBS_FREE_STATE) {
+                const int fb = L.fb0 + idx * contact::FBN;
+                for (int r = 0; r < 13; ++r) dst[(size_t)(row + r) * TK] = (CONTACT && idx < m.nfree) ? xs[(fb + r) * 32 + lane] : 0.f;
+                row += 13;
             } else {
-                const int w = kind == MPPIB_OBS_CONTACT ? 3 : 13;
-                for (int r = 0; r < w; ++r) dst[(size_t)(row + r) * TK] = 0.f;
-                row += w;
+                for (int r = 0; r < 3; ++r) dst[(size_t)(row + r) * TK] = (CONTACT && idx < MPPIB_MAX_SLOTS) ? xs[(L.net0 + 3 * idx + r) * 32 + lane] : 0.f;
+                row += 3;
             }
         }
     }
@@ -425,31 +449,42 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
             state[(size_t)i * K + k] = SM(i, F_Q);
             state[(size_t)(nb + i) * K + k] = SM(i, F_QD);
         }
+        if (CONTACT) for (int f = 0; f < m.nfree; ++f)
+            for (int r = 0; r < 13; ++r) state[(size_t)(2 * nb + 13 * f + r) * K + k] = xs[(L.fb0 + f * contact::FBN + r) * 32 + lane];
     }
 }
 
-template <bool CHAIN>
-int launch_t(MppibContext* c, const float* state0, float* state, const float* actions, int t0, int nsteps, float* obs, cudaStream_t s) {
+template <bool CHAIN, bool CONTACT>
+int launch_t(MppibContext* c, const float* state0, const float* root0, float* state, const float* actions, int t0, int nsteps, float* obs, cudaStream_t s) {
     const int K = c->params.K;
-    const size_t smem = sizeof(float) * 32 * (size_t)c->model.nb * (CHAIN ? NSLOT_CHAIN : NSLOT_TREE);
+    const int nslot = (CHAIN && !CONTACT) ? NSLOT_CHAIN : NSLOT_TREE;
+    const contact::Layout L(c->model.nb, c->model.nfree, c->model.nshapes);
+    const size_t smem = sizeof(float) * 32 * ((size_t)c->model.nb * nslot + (CONTACT ? (size_t)L.total : 0));
+    MPPIB_REQUIRE(smem <= 226 * 1024, "mppib_rollout: %zu bytes of shared memory per CTA exceed the SM (too many bodies / shapes)", smem);
     static size_t smem_attr = 48 * 1024;
     if (smem > smem_attr) {
-        MPPIB_CHECK_CUDA(cudaFuncSetAttribute(mppib_rollout_kernel<CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MPPIB_CHECK_CUDA(cudaFuncSetAttribute(mppib_rollout_kernel<CHAIN, CONTACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_attr = smem;
     }
     dim3 grid((K + 31) / 32), block(32);
-    mppib_rollout_kernel<CHAIN><<<grid, block, smem, s>>>(c->model, c->params, state0, state, actions, t0, nsteps, obs);
+    mppib_rollout_kernel<CHAIN, CONTACT><<<grid, block, smem, s>>>(c->model, c->params, state0, root0, state, actions, t0, nsteps, obs);
     MPPIB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 }  // namespace
 
-int launch_rollout(MppibContext* c, const float* state0, float* state, const float* actions, int t0, int nsteps,
+int launch_rollout(MppibContext* c, const float* state0, const float* root0, float* state, const float* actions, int t0, int nsteps,
                    float* obs, cudaStream_t s) {
     const MppibModel& m = c->model;
     bool chain = true;
     for (int i = 0; i < m.nb; ++i) if (m.parent[i] != i - 1) chain = false;
-    if (chain) return launch_t<true>(c, state0, state, actions, t0, nsteps, obs, s);
-    return launch_t<false>(c, state0, state, actions, t0, nsteps, obs, s);
+    const bool contact = m.nfree > 0 || m.nshapes > 0;
+    if (contact) {
+        MPPIB_REQUIRE(root0 != nullptr, "mppib_rollout: root0 is required for scenes with free bodies / collision boxes");
+        if (chain) return launch_t<true, true>(c, state0, root0, state, actions, t0, nsteps, obs, s);
+        return launch_t<false, true>(c, state0, root0, state, actions, t0, nsteps, obs, s);
+    }
+    if (chain) return launch_t<true, false>(c, state0, root0, state, actions, t0, nsteps, obs, s);
+    return launch_t<false, false>(c, state0, root0, state, actions, t0, nsteps, obs, s);
 }

@@ -18,8 +18,9 @@ import numpy as np
 
 from .urdf import RobotModel, compile_urdf, load_compiled, quat_xyzw_to_R, R_to_quat_xyzw
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_BODIES, MAX_LINKS, MAX_NU, MAX_OBS, MAX_FREE, MAX_SHAPES = 16, 32, 16, 64, 4, 24
+MAX_CONTACTS, MAX_SLOTS = 24, 8
 
 JOINT_REVOLUTE, JOINT_PRISMATIC = 0, 1
 DRIVE_VELOCITY, DRIVE_EFFORT = 0, 1
@@ -45,12 +46,15 @@ class MppibModel(C.Structure):
         ("cmd_i0", i32 * MAX_BODIES), ("cmd_i1", i32 * MAX_BODIES),
         ("cmd_c0", f32 * MAX_BODIES), ("cmd_c1", f32 * MAX_BODIES),
         ("link_body", i32 * MAX_LINKS), ("link_R", (f32 * 9) * MAX_LINKS), ("link_p", (f32 * 3) * MAX_LINKS), ("link_quat", (f32 * 4) * MAX_LINKS),
-        ("free_mass", f32 * MAX_FREE), ("free_inertia", (f32 * 3) * MAX_FREE), ("free_gravity", i32 * MAX_FREE),
+        ("free_actor", i32 * MAX_FREE), ("free_mass", f32 * MAX_FREE), ("free_mass_pct", f32 * MAX_FREE),
+        ("free_half", (f32 * 3) * MAX_FREE), ("free_gravity", i32 * MAX_FREE), ("free_slot", i32 * MAX_FREE),
         ("shape_type", i32 * MAX_SHAPES), ("shape_owner_kind", i32 * MAX_SHAPES), ("shape_owner", i32 * MAX_SHAPES),
-        ("shape_contact_slot", i32 * MAX_SHAPES),
-        ("shape_size", (f32 * 3) * MAX_SHAPES), ("shape_pos", (f32 * 3) * MAX_SHAPES),
-        ("shape_quat", (f32 * 4) * MAX_SHAPES), ("shape_friction", f32 * MAX_SHAPES),
-        ("ncontact_slots", i32), ("ground_plane", i32), ("contact_kp", f32), ("contact_kd", f32),
+        ("shape_actor", i32 * MAX_SHAPES), ("shape_slot", i32 * MAX_SHAPES),
+        ("shape_half", (f32 * 3) * MAX_SHAPES), ("shape_pos", (f32 * 3) * MAX_SHAPES),
+        ("shape_quat", (f32 * 4) * MAX_SHAPES), ("shape_friction", f32 * MAX_SHAPES), ("shape_fric_pct", f32 * MAX_SHAPES),
+        ("shape_size_sigma", (f32 * 3) * MAX_SHAPES),
+        ("ncontact_slots", i32), ("ground_plane", i32), ("ground_friction", f32), ("contact_kp", f32), ("contact_kd", f32),
+        ("max_depen", f32), ("ground_margin", f32), ("contact_margin", f32), ("contact_iters", i32), ("nactors", i32),
     ]
 
 
@@ -65,6 +69,7 @@ class MppibParams(C.Structure):
         ("filter_u", i32),
         ("u_min", f32 * MAX_NU), ("u_max", f32 * MAX_NU), ("u_init", f32 * MAX_NU),
         ("sigma_chol", f32 * (MAX_NU * MAX_NU)), ("sigma_inv", f32 * (MAX_NU * MAX_NU)),
+        ("k_offset", C.c_uint32), ("rand_seed", C.c_uint32),
         ("nobs", i32), ("obs", MppibObsItem * MAX_OBS),
     ]
 
@@ -135,8 +140,23 @@ def _set(arr, values):
         arr[i] = v
 
 
-def build_scene(actor_cfgs: list, gravity=(0.0, 0.0, -9.8), assets_dirs=None,
-                contact_kp: float = 2.0e4, contact_kd: float = 2.0e2) -> Scene:
+def _box_of_collision(col: dict):
+    """Collision geometry -> (half extents, centre offset in the geometry frame).  Everything is a box on this path."""
+    kind = col["kind"]
+    if kind == "box":
+        return 0.5 * np.asarray(col["size"], float), np.zeros(3)
+    if kind == "sphere":
+        return np.full(3, float(col["size"][0])), np.zeros(3)
+    if kind == "cylinder":
+        r, l = float(col["size"][0]), float(col["size"][1])
+        return np.array([r, r, 0.5 * l]), np.zeros(3)
+    if kind == "mesh" and "aabb_half" in col:
+        return np.asarray(col["aabb_half"], float), np.asarray(col["aabb_center"], float)
+    return None, None
+
+
+def build_scene(actor_cfgs: list, gravity=(0.0, 0.0, -9.8), assets_dirs=None, substep: float = 0.025,
+                contact_kp: float = 1.0e5, contact_kd: float = 1.0e3, contact_iters: int = 8) -> Scene:
     robots = [i for i, a in enumerate(actor_cfgs) if a.type == "robot"]
     if len(robots) != 1:
         raise NotImplementedError("exactly one robot actor per environment is supported on this path "
@@ -196,7 +216,6 @@ def build_scene(actor_cfgs: list, gravity=(0.0, 0.0, -9.8), assets_dirs=None,
 
     # rigid-body bookkeeping in the env domain (actor order, links in URDF depth-first order)
     body_names, body_offset, off = [], [], 0
-    free_actor: Dict[int, int] = {}
     root0 = np.zeros((len(actor_cfgs), 13), np.float32)
     for ai, a in enumerate(actor_cfgs):
         root0[ai, 0:3] = a.init_pos
@@ -205,11 +224,69 @@ def build_scene(actor_cfgs: list, gravity=(0.0, 0.0, -9.8), assets_dirs=None,
         body_names.append(names)
         body_offset.append(off)
         off += len(names)
-        if a.type in ("box", "sphere") and not a.fixed:
-            raise NotImplementedError(f"free rigid-body actor '{a.name}' needs the contact path, which is not built yet")
-    m.nfree, m.nshapes, m.ncontact_slots = 0, 0, 0
-    m.ground_plane = 1
-    m.contact_kp, m.contact_kd = contact_kp, contact_kd
+
+    # ---- free bodies, collision boxes, contact slots (replaces _create_actor's shape setup, isaacgym_wrapper.py:429-482)
+    free_actor: Dict[int, int] = {}
+    contact_slot: Dict[int, int] = {}
+    shapes = []          # dicts: kind, owner, actor, half, pos, quat, friction, fric_pct, sigma, body (env rigid body index)
+    nfree = 0
+    for ai, a in enumerate(actor_cfgs):
+        if ai == ra or not a.collision:
+            continue
+        if a.type == "sphere":
+            raise NotImplementedError(f"colliding sphere actor '{a.name}' is not supported on this path (boxes only)")
+        if a.type != "box":
+            raise NotImplementedError(f"actor asset of type {a.type} is not yet implemented!")      # isaacgym_utils.py:54-56
+        half = 0.5 * np.asarray(a.size, float)[:3]
+        sigma = np.asarray(a.noise_sigma_size if a.noise_sigma_size is not None else [0, 0, 0], float)[:3]
+        sh = dict(kind=OWNER_STATIC, owner=-1, actor=ai, half=half, pos=np.zeros(3), quat=np.array([0, 0, 0, 1.0]),
+                  friction=float(a.friction), fric_pct=float(a.noise_percentage_friction), sigma=sigma, body=body_offset[ai])
+        if not a.fixed:
+            if nfree >= MAX_FREE:
+                raise ValueError("too many free rigid bodies (MPPIB_MAX_FREE)")
+            f = nfree
+            nfree += 1
+            free_actor[ai] = f
+            m.free_actor[f], m.free_mass[f], m.free_mass_pct[f] = ai, float(a.mass), float(a.noise_percentage_mass)
+            _set(m.free_half[f], half)
+            m.free_gravity[f] = 1 if a.gravity else 0
+            sh.update(kind=OWNER_FREE, owner=f)
+        shapes.append(sh)
+    have_world = len(shapes) > 0
+    if have_world and rcfg.collision:
+        for l, cols in enumerate(robot.link_collisions):
+            for col in cols:
+                half, cen = _box_of_collision(col)
+                if half is None:
+                    continue
+                Rg, pg = np.asarray(col["R"], float), np.asarray(col["p"], float)
+                R_bl, p_bl = robot.link_R[l], robot.link_p[l]            # link frame in its owning body's frame
+                pos = p_bl + R_bl @ (pg + Rg @ cen)
+                shapes.append(dict(kind=OWNER_LINK, owner=int(robot.link_body[l]), actor=-1, half=half, pos=pos,
+                                   quat=R_to_quat_xyzw(R_bl @ Rg), friction=float(rcfg.friction), fric_pct=0.0, sigma=np.zeros(3),
+                                   body=body_offset[ra] + l))
+    if len(shapes) > MAX_SHAPES:
+        raise ValueError(f"{len(shapes)} collision boxes exceed MPPIB_MAX_SHAPES")
+    # contact-force slots: non-robot bodies first, then robot links while slots remain
+    for sh in sorted(shapes, key=lambda d: (d["kind"] == OWNER_LINK, d["body"])):
+        if sh["body"] not in contact_slot and len(contact_slot) < MAX_SLOTS:
+            contact_slot[sh["body"]] = len(contact_slot)
+    for si, sh in enumerate(shapes):
+        m.shape_type[si], m.shape_owner_kind[si], m.shape_owner[si], m.shape_actor[si] = SHAPE_BOX, sh["kind"], sh["owner"], sh["actor"]
+        m.shape_slot[si] = contact_slot.get(sh["body"], -1)
+        _set(m.shape_half[si], sh["half"]); _set(m.shape_pos[si], sh["pos"]); _set(m.shape_quat[si], sh["quat"])
+        m.shape_friction[si], m.shape_fric_pct[si] = sh["friction"], sh["fric_pct"]
+        _set(m.shape_size_sigma[si], sh["sigma"])
+        if sh["kind"] == OWNER_FREE:
+            m.free_slot[sh["owner"]] = m.shape_slot[si]
+    m.nfree, m.nshapes, m.ncontact_slots = nfree, len(shapes), len(contact_slot)
+    m.nactors = len(actor_cfgs)
+    m.ground_plane, m.ground_friction = 1, 1.0                        # isaacgym_utils.py:61-68
+    m.contact_kp, m.contact_kd, m.contact_iters = contact_kp, contact_kd, contact_iters
+    # speculative contacts: a body may not close a gap faster than gap / h (keeps resting contacts alive at large h)
+    m.ground_margin = max(0.01, 1.5 * abs(gravity[2]) * substep * substep)
+    m.max_depen = 0.25
+    m.contact_margin = 0.01                                           # isaacgym_wrapper.py:33 contact_offset
 
     ndof = robot.nb
     dof0 = np.zeros(2 * ndof, np.float32)
@@ -217,7 +294,7 @@ def build_scene(actor_cfgs: list, gravity=(0.0, 0.0, -9.8), assets_dirs=None,
         dof0[:] = np.asarray(rcfg.init_joint_pose, np.float32)[: 2 * ndof]
     return Scene(model=m, robot=robot, actor_cfgs=actor_cfgs, actor_names=[a.name for a in actor_cfgs],
                  robot_actor=ra, body_names=body_names, body_offset=body_offset, free_actor=free_actor,
-                 root_state0=root0, dof_state0=dof0, ndof=ndof, nu=int(m.nu))
+                 root_state0=root0, dof_state0=dof0, contact_slot=contact_slot, ndof=ndof, nu=int(m.nu))
 
 
 def make_params(mppi_cfg, sim_cfg, nu: int, K_local: int, obs_items: Sequence[tuple]) -> MppibParams:
@@ -259,6 +336,8 @@ def make_params(mppi_cfg, sim_cfg, nu: int, K_local: int, obs_items: Sequence[tu
             p.sigma_inv[j * nu + i] = sinv[j, i]
     if len(obs_items) > MAX_OBS:
         raise ValueError("too many observation items")
+    p.k_offset = int(getattr(mppi_cfg, "_k_offset", 0))
+    p.rand_seed = int(getattr(mppi_cfg, "seed_val", 0)) & 0xFFFFFFFF
     p.nobs = len(obs_items)
     for i, (kind, index) in enumerate(obs_items):
         p.obs[i].kind, p.obs[i].index = int(kind), int(index)

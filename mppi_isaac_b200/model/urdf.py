@@ -438,9 +438,16 @@ def compile_urdf(urdf_path: str, fixed_base: bool = True, density: float = DEFAU
         link_body.append(owner)
         link_T.append((R_bl, p_bl))
         lk = links[name]
-        link_cols.append([
-            dict(kind=g.kind, size=list(g.size), R=g.R.tolist(), p=g.p.tolist(), mesh=g.mesh) for g in lk.collisions
-        ])
+        cols = []
+        for g in lk.collisions:
+            d = dict(kind=g.kind, size=list(g.size), R=g.R.tolist(), p=g.p.tolist(), mesh=g.mesh)
+            if g.kind == "mesh":      # axis-aligned bounding box in the geometry frame (collision proxy of the rollout path)
+                v, _ = load_mesh(resolve_mesh(g.mesh, urdf_path))
+                v = v * np.asarray(g.scale, float)
+                d["aabb_center"] = (0.5 * (v.min(0) + v.max(0))).tolist()
+                d["aabb_half"] = (0.5 * (v.max(0) - v.min(0))).tolist()
+            cols.append(d)
+        link_cols.append(cols)
         m, c, Ic = link_mass_properties(lk, urdf_path, density)
         if name == root and root_mass_override is not None and m > 0:
             # isaacgym_wrapper.py:450-456 overwrites body-0 mass (inertia left untouched)

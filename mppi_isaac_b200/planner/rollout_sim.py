@@ -73,7 +73,7 @@ class RolloutSim:
     # construction (start_sim, isaacgym_wrapper.py:124-236)
     # ------------------------------------------------------------------------------------------
     def start_sim(self):
-        self.scene: Scene = build_scene(self.env_cfg, assets_dirs=self._assets_dirs)
+        self.scene: Scene = build_scene(self.env_cfg, assets_dirs=self._assets_dirs, substep=float(self.cfg.dt) / int(self.cfg.substeps))
         sc = self.scene
         self._visualize_link_present = any(a.visualize_link for a in self.env_cfg)
         self.visualize_link_buffer = []
@@ -117,7 +117,8 @@ class RolloutSim:
         """(Re)create the kernel handle and the K-indexed buffers for the current obs plan."""
         sc, K, T, dev = self.scene, self.num_envs, self._T, self.device
         if self._observe == "all":
-            self._obs_items = [(OBS_LINK_STATE, l) for l in range(sc.robot.nlinks)] + [(OBS_DOF_STATE, 0)]
+            self._obs_items = ([(OBS_LINK_STATE, l) for l in range(sc.robot.nlinks)] + [(OBS_DOF_STATE, 0)]
+                               + [(OBS_FREE_STATE, f) for f in range(sc.model.nfree)] + [(OBS_CONTACT, s) for s in range(sc.model.ncontact_slots)])
         elif self._visualize_link_present and (OBS_LINK_STATE, self._viz_link) not in self._obs_items:
             self._obs_items.append((OBS_LINK_STATE, self._viz_link))
         self._obs_row = {}
@@ -133,16 +134,19 @@ class RolloutSim:
         self._backend.create(sc.model, self.params)
         assert self._backend.obs_size() == self._R
         NS = self._backend.state_size()
-        self._state = self._state0[:, None].repeat(1, K).contiguous()                  # (NS,K)
-        assert self._state.shape[0] == NS
+        self._state = torch.zeros((NS, K), dtype=torch.float32, device=dev)            # (NS,K) step-protocol state
+        self._state_stale = True
         self._obs = torch.zeros((max(self._R, 1), T, K), dtype=torch.float32, device=dev)
         self._cmd = torch.zeros((sc.nu, K), dtype=torch.float32, device=dev)
         self._state_is_broadcast = True
-        self._state_stale = False
 
     def _sync_step_state(self):
+        """(NS,K) step-protocol state <- the broadcast world state (DOF row + initial states of the free bodies)."""
         if self._state_stale:
-            self._state.copy_(self._state0[:, None].expand(-1, self.num_envs))
+            nd2 = 2 * self.scene.ndof
+            self._state[:nd2].copy_(self._state0[:, None].expand(-1, self.num_envs))
+            for actor_idx, f in self.scene.free_actor.items():
+                self._state[nd2 + 13 * f: nd2 + 13 * (f + 1)].copy_(self._root0[actor_idx][:, None].expand(-1, self.num_envs))
             self._state_stale = False
 
     @property
@@ -210,7 +214,7 @@ class RolloutSim:
     def _refresh_initial(self):
         """Observe the current state into slot 0 (reference: refresh_* right after a reset)."""
         self._sync_step_state()
-        self._backend.rollout(None, self._state, self._cmd, 0, 0, self._obs, act_t0=0)
+        self._backend.rollout(None, self._state, self._cmd, 0, 0, self._obs, act_t0=0, root0=self._root0)
         self._have_obs = True
         self._slot = 0
 
@@ -423,7 +427,7 @@ class RolloutSim:
         self._mode = "step"
         self._sync_step_state()
         t = self._t % self._T
-        self._backend.rollout(None, self._state, self._cmd, t, 1, self._obs, act_t0=t)
+        self._backend.rollout(None, self._state, self._cmd, t, 1, self._obs, act_t0=t, root0=self._root0)
         self._state_is_broadcast = False
         self._have_obs = True
         self._slot = t
@@ -433,7 +437,7 @@ class RolloutSim:
 
     def rollout_all(self, actions: torch.Tensor):
         """Whole horizon in ONE launch from the broadcast world state; switches getters to batched views."""
-        self._backend.rollout(self._state0, None, actions, 0, self._T, self._obs, act_t0=0)
+        self._backend.rollout(self._state0, None, actions, 0, self._T, self._obs, act_t0=0, root0=self._root0)
         self.mark_batched()
 
     def mark_batched(self):

@@ -48,7 +48,7 @@ class OracleBackend:
         if noise is not None:
             noise.copy_(torch.from_numpy(n))
 
-    def rollout(self, state0, state, actions, t0, nsteps, obs, act_t0=0):
+    def rollout(self, state0, state, actions, t0, nsteps, obs, act_t0=0, root0=None):
         T, K, nu = self.params.T, self.params.K, self.model.nu
         a = np.zeros((T, nu, K), np.float32)
         src = _np(actions).reshape(-1, nu, K)
@@ -60,8 +60,9 @@ class OracleBackend:
         o = _np(obs)
         assert o is None or o.flags["C_CONTIGUOUS"]
         assert st is None or st.flags["C_CONTIGUOUS"]
+        r0 = None if root0 is None else np.ascontiguousarray(_np(root0), np.float32)
         orc.lib().oracle_rollout(C.byref(self.model), C.byref(self.params), f(None if s0 is None else np.ascontiguousarray(s0, np.float32)),
-                                 f(st), f(a), C.c_int32(t0), C.c_int32(nsteps), f(o), C.c_int32(int(self.use_double)), C.c_int32(self.nthreads))
+                                 f(r0), f(st), f(a), C.c_int32(t0), C.c_int32(nsteps), f(o), C.c_int32(int(self.use_double)), C.c_int32(self.nthreads))
 
     def reduce(self, cost, x, U, partial):
         p, _ = orc.reduce(self.model, self.params, _np(cost.contiguous()), _np(x), _np(U))

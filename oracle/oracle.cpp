@@ -193,14 +193,35 @@ struct Articulation {
         }
     }
 
+    // world pose / velocity of every body from the last kinematics() call
+    M3<S> Rw[MPPIB_MAX_BODIES]; S pw[MPPIB_MAX_BODIES][3], ww[MPPIB_MAX_BODIES][3], vw[MPPIB_MAX_BODIES][3];
+    void world_frames(const M3<S>& Rb, const S* pb) {
+        for (int i = 0; i < nb; ++i) {
+            const M3<S>& Rp = m->parent[i] >= 0 ? Rw[m->parent[i]] : Rb;
+            const S* pp = m->parent[i] >= 0 ? pw[m->parent[i]] : pb;
+            for (int r = 0; r < 3; ++r) {
+                S s = 0; for (int j = 0; j < 3; ++j) s += Rp.a[r][j] * pl[i][j];
+                pw[i][r] = pp[r] + s;
+                for (int cc = 0; cc < 3; ++cc) { S s2 = 0; for (int j = 0; j < 3; ++j) s2 += Rp.a[r][j] * Rl[i].a[j][cc]; Rw[i].a[r][cc] = s2; }
+            }
+            for (int r = 0; r < 3; ++r) {   // angular velocity and velocity of the body origin, world coordinates
+                S a = 0, b = 0; for (int j = 0; j < 3; ++j) { a += Rw[i].a[r][j] * v[i].a[j]; b += Rw[i].a[r][j] * v[i].a[3 + j]; }
+                ww[i][r] = a; vw[i][r] = b;
+            }
+        }
+    }
+
     // one ABA solve; tau = explicit joint force, dimp = implicit diagonal added to D (h*(kd+damping)+armature)
-    void aba(const S* tau, const S* dimp, S* qdd) {
+    // fext[i]: external wrench on body i in BODY coordinates about the body origin (contacts), may be null
+    S D[MPPIB_MAX_BODIES];   // joint-space articulated diagonal (incl. the implicit drive term) of the last solve
+    void aba(const S* tau, const S* dimp, S* qdd, const V6<S>* fext = nullptr) {
         M6<S> IA[MPPIB_MAX_BODIES]; V6<S> pA[MPPIB_MAX_BODIES];
-        V6<S> U[MPPIB_MAX_BODIES]; S D[MPPIB_MAX_BODIES], u[MPPIB_MAX_BODIES];
+        V6<S> U[MPPIB_MAX_BODIES]; S u[MPPIB_MAX_BODIES];
         for (int i = 0; i < nb; ++i) {
             IA[i] = spatial_inertia<S>((S)m->mass[i], m->mcom[i], m->inertia[i]);
             V6<S> Iv = mulXv(IA[i], v[i]);
             pA[i] = crf(v[i], Iv);
+            if (fext) for (int k = 0; k < 6; ++k) pA[i].a[k] -= fext[i].a[k];
         }
         for (int i = nb - 1; i >= 0; --i) {
             int s = m->jtype[i] == MPPIB_JOINT_REVOLUTE ? 2 : 5;
@@ -235,14 +256,277 @@ struct Articulation {
     }
 };
 
+// ------------------------------------------------------------------------------------------
+// free rigid bodies + contacts (replaces PhysX rigid bodies / contact solve on this path).
+// Spec: boxes only; contact points = the 26 surface sample points of one box that lie
+// inside the other box (both directions) or below the ground plane; normal = face of least penetration;
+// penalty spring-damper (contact_kp, contact_kd) integrated IMPLICITLY as a soft constraint
+//     d_lambda = (-v_n + beta d / h - gamma lambda) / (k_n + gamma),  gamma = 1/(h (h kp + kd)),  beta = h kp / (h kp + kd)
+// solved by `contact_iters` Gauss-Seidel sweeps with box friction |lambda_t| <= mu lambda_n on the PREDICTED velocities
+// (after gravity and the drive have acted for this substep).  Articulation links take part with a DIAGONAL joint-space
+// compliance: an impulse P at point x of body b changes the velocity of joint j (ancestors of b) by J_j(x).P / D_j, D_j the
+// articulated joint-space diagonal of the ABA solve (inertia + armature + h (k_d + b)); the implicit drive dominates it on
+// this path (h k_d = 15..60 kg-equivalent), so the off-diagonal coupling that is dropped is small.
+// ------------------------------------------------------------------------------------------
+enum { REF_STATIC = -1, REF_FREE0 = 64 };
+
+template <class S> struct FreeBody { S x[3], q[4], v[3], w[3], mass, half[3], Iinv[3]; M3<S> R, IinvW; };
+template <class S> struct ShapeW { M3<S> R; S c[3], half[3], mu, rad; int ref, slot, kind; };
+template <class S> struct Contact { int refA, refB, slotA, slotB, penalty; S p[3], n[3], d, mu, ln, lt1, lt2, t1[3], t2[3]; };
+
+template <class S> void mat_vec(const M3<S>& R, const S* v, S* o) { for (int r = 0; r < 3; ++r) o[r] = R.a[r][0] * v[0] + R.a[r][1] * v[1] + R.a[r][2] * v[2]; }
+template <class S> void matT_vec(const M3<S>& R, const S* v, S* o) { for (int r = 0; r < 3; ++r) o[r] = R.a[0][r] * v[0] + R.a[1][r] * v[1] + R.a[2][r] * v[2]; }
+
+// per-rollout randomisation (isaacgym_utils.py:29-40 size noise, isaacgym_wrapper.py:450-475 mass / friction noise),
+// made reproducible: Philox counter (global sample, actor, 0x5EED, draw), key (rand_seed, "MPPI")
+inline void actor_noise(const MppibParams* p, uint32_t kg, int actor, float* nsize, float* umass, float* ufric) {
+    U4 r0 = philox4x32_10({kg, (uint32_t)actor, 0x5EEDu, 0u}, p->rand_seed, 0x4D505049u);
+    U4 r1 = philox4x32_10({kg, (uint32_t)actor, 0x5EEDu, 1u}, p->rand_seed, 0x4D505049u);
+    float dummy;
+    box_muller(r0.x, r0.y, &nsize[0], &nsize[1]);
+    box_muller(r0.z, r0.w, &nsize[2], &dummy);
+    *umass = 2.0f * u01(r1.x) - 1.0f;
+    *ufric = 2.0f * u01(r1.y) - 1.0f;
+}
+
 template <class S>
-void rollout_one(const MppibModel* m, const MppibParams* p, int K, int k, S* q, S* qd,
+struct ContactWorld {
+    const MppibModel* m; const MppibParams* p;
+    FreeBody<S> fb[MPPIB_MAX_FREE];
+    S shalf[MPPIB_MAX_SHAPES][3], smu[MPPIB_MAX_SHAPES];     // per-rollout shape parameters
+    ShapeW<S> sh[MPPIB_MAX_SHAPES];
+    Contact<S> ct[MPPIB_MAX_CONTACTS]; int nc;
+    S net[MPPIB_MAX_SLOTS][3];                                // net contact force per slot (last substep)
+    S dqv[MPPIB_MAX_BODIES], Dj[MPPIB_MAX_BODIES];            // virtual joint-velocity change inside the solve, joint compliance denominators
+
+    void init_params(uint32_t kg) {
+        for (int s = 0; s < m->nshapes; ++s) {
+            for (int r = 0; r < 3; ++r) shalf[s][r] = (S)m->shape_half[s][r];
+            smu[s] = (S)m->shape_friction[s];
+            if (m->shape_actor[s] >= 0) {
+                float ns[3], um, uf; actor_noise(p, kg, m->shape_actor[s], ns, &um, &uf);
+                for (int r = 0; r < 3; ++r) shalf[s][r] += (S)0.5 * (S)m->shape_size_sigma[s][r] * (S)ns[r];
+                smu[s] *= (S)1 + (S)m->shape_fric_pct[s] * (S)uf;
+            }
+        }
+        for (int f = 0; f < m->nfree; ++f) {
+            float ns[3], um, uf; actor_noise(p, kg, m->free_actor[f], ns, &um, &uf);
+            fb[f].mass = (S)m->free_mass[f] * ((S)1 + (S)m->free_mass_pct[f] * (S)um);
+            // size noise of the body = size noise of its (first) shape
+            S sg[3] = {0, 0, 0};
+            for (int s = 0; s < m->nshapes; ++s) if (m->shape_owner_kind[s] == MPPIB_OWNER_FREE && m->shape_owner[s] == f) { for (int r = 0; r < 3; ++r) sg[r] = (S)m->shape_size_sigma[s][r]; break; }
+            for (int r = 0; r < 3; ++r) fb[f].half[r] = (S)m->free_half[f][r] + (S)0.5 * sg[r] * (S)ns[r];
+            const S hx = fb[f].half[0], hy = fb[f].half[1], hz = fb[f].half[2], m3 = fb[f].mass / (S)3;
+            fb[f].Iinv[0] = (S)1 / (m3 * (hy * hy + hz * hz)); fb[f].Iinv[1] = (S)1 / (m3 * (hx * hx + hz * hz)); fb[f].Iinv[2] = (S)1 / (m3 * (hx * hx + hy * hy));
+        }
+    }
+    void refresh_free(int f) {
+        fb[f].R = quat_to_R(fb[f].q);
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { S s = 0; for (int j = 0; j < 3; ++j) s += fb[f].R.a[r][j] * fb[f].Iinv[j] * fb[f].R.a[c][j]; fb[f].IinvW.a[r][c] = s; }
+    }
+    // velocity of point pt of body b per unit velocity of joint j (world): a_j x (pt - o_j) (revolute) or a_j (prismatic)
+    void joint_jac(const Articulation<S>& art, int j, const S* pt, S* J) const {
+        S a[3] = {art.Rw[j].a[0][2], art.Rw[j].a[1][2], art.Rw[j].a[2][2]};
+        if (m->jtype[j] == MPPIB_JOINT_REVOLUTE) { S r[3] = {pt[0] - art.pw[j][0], pt[1] - art.pw[j][1], pt[2] - art.pw[j][2]}; cross3(a, r, J); }
+        else { J[0] = a[0]; J[1] = a[1]; J[2] = a[2]; }
+    }
+    void point_velocity(int ref, const S* pt, const Articulation<S>& art, S* o) const {
+        if (ref == REF_STATIC) { o[0] = o[1] = o[2] = 0; return; }
+        S r[3], wxr[3];
+        if (ref >= REF_FREE0) { const FreeBody<S>& b = fb[ref - REF_FREE0]; for (int i = 0; i < 3; ++i) r[i] = pt[i] - b.x[i]; cross3(b.w, r, wxr); for (int i = 0; i < 3; ++i) o[i] = b.v[i] + wxr[i]; }
+        else {
+            for (int i = 0; i < 3; ++i) r[i] = pt[i] - art.pw[ref][i]; cross3(art.ww[ref], r, wxr); for (int i = 0; i < 3; ++i) o[i] = art.vw[ref][i] + wxr[i];
+            for (int j = ref; j >= 0; j = m->parent[j]) { S J[3]; joint_jac(art, j, pt, J); for (int i = 0; i < 3; ++i) o[i] += J[i] * dqv[j]; }
+        }
+    }
+    // effective inverse mass of the free bodies of a contact along direction dir at point pt
+    S inv_mass(const Contact<S>& c, const S* dir, const Articulation<S>& art) const {
+        S k = 0;
+        const int refs[2] = {c.refA, c.refB};
+        for (int e = 0; e < 2; ++e) if (refs[e] >= 0 && refs[e] < REF_FREE0) {
+            for (int j = refs[e]; j >= 0; j = m->parent[j]) { S J[3]; joint_jac(art, j, c.p, J); const S jd = J[0] * dir[0] + J[1] * dir[1] + J[2] * dir[2]; k += jd * jd / Dj[j]; }
+        } else if (refs[e] >= REF_FREE0) {
+            const FreeBody<S>& b = fb[refs[e] - REF_FREE0];
+            S r[3], rxn[3], t[3], u[3];
+            for (int i = 0; i < 3; ++i) r[i] = c.p[i] - b.x[i];
+            cross3(r, dir, rxn); mat_vec(b.IinvW, rxn, t); cross3(t, r, u);
+            k += (S)1 / b.mass + u[0] * dir[0] + u[1] * dir[1] + u[2] * dir[2];
+        }
+        return k;
+    }
+    void apply_impulse(const Contact<S>& c, const S* dir, S mag, const Articulation<S>& art) {
+        const int refs[2] = {c.refA, c.refB};
+        for (int e = 0; e < 2; ++e) if (refs[e] >= 0 && refs[e] < REF_FREE0) {
+            const S sgn = e == 0 ? mag : -mag;
+            for (int j = refs[e]; j >= 0; j = m->parent[j]) { S J[3]; joint_jac(art, j, c.p, J); dqv[j] += sgn * (J[0] * dir[0] + J[1] * dir[1] + J[2] * dir[2]) / Dj[j]; }
+        } else if (refs[e] >= REF_FREE0) {
+            FreeBody<S>& b = fb[refs[e] - REF_FREE0];
+            const S sgn = e == 0 ? mag : -mag;
+            S r[3], rxd[3], dw[3];
+            for (int i = 0; i < 3; ++i) { r[i] = c.p[i] - b.x[i]; b.v[i] += sgn * dir[i] / b.mass; }
+            cross3(r, dir, rxd); mat_vec(b.IinvW, rxd, dw);
+            for (int i = 0; i < 3; ++i) b.w[i] += sgn * dw[i];
+        }
+    }
+    void add_contact(int refA, int refB, int slotA, int slotB, const S* pt, const S* n, S d, S mu, int penalty) {
+        if (nc >= MPPIB_MAX_CONTACTS) return;
+        Contact<S>& c = ct[nc++];
+        c.refA = refA; c.refB = refB; c.slotA = slotA; c.slotB = slotB; c.penalty = penalty; c.d = d; c.mu = mu; c.ln = c.lt1 = c.lt2 = 0;
+        for (int i = 0; i < 3; ++i) { c.p[i] = pt[i]; c.n[i] = n[i]; }
+        S e[3] = {0, 0, 0}; if (std::fabs(n[0]) < (S)0.9) e[0] = 1; else e[1] = 1;
+        cross3(n, e, c.t1); S l = std::sqrt(c.t1[0] * c.t1[0] + c.t1[1] * c.t1[1] + c.t1[2] * c.t1[2]);
+        for (int i = 0; i < 3; ++i) c.t1[i] /= l;
+        cross3(n, c.t1, c.t2);
+    }
+    // sample points of box a that are inside box b -> contacts; `flip`: a is the B side of the pair
+    void points_in_box(const ShapeW<S>& a, const ShapeW<S>& b, bool flip, int penalty) {
+        const S mu = (S)0.5 * (a.mu + b.mu);
+        // candidate normal axes: slabs of b that the CENTRE of a lies outside of (a thin box must not push sideways hits
+        // up or down); if the centre is inside b, all three axes compete
+        S crel[3], cl[3]; for (int i = 0; i < 3; ++i) crel[i] = a.c[i] - b.c[i];
+        matT_vec(b.R, crel, cl);
+        bool cand[3]; int ncand = 0;
+        for (int i = 0; i < 3; ++i) { cand[i] = std::fabs(cl[i]) > b.half[i]; ncand += cand[i]; }
+        if (ncand == 0) cand[0] = cand[1] = cand[2] = true;
+        for (int ix = -1; ix <= 1; ++ix) for (int iy = -1; iy <= 1; ++iy) for (int iz = -1; iz <= 1; ++iz) {
+            if (ix == 0 && iy == 0 && iz == 0) continue;
+            S loc[3] = {ix * a.half[0], iy * a.half[1], iz * a.half[2]}, pt[3], rel[3], x[3];
+            mat_vec(a.R, loc, pt); for (int i = 0; i < 3; ++i) { pt[i] += a.c[i]; rel[i] = pt[i] - b.c[i]; }
+            matT_vec(b.R, rel, x);
+            S pen[3]; bool inside = true;
+            const S mg = (S)m->contact_margin;                       // speculative margin
+            for (int i = 0; i < 3; ++i) { pen[i] = b.half[i] - std::fabs(x[i]); if (!(pen[i] + mg > 0)) inside = false; }
+            if (!inside) continue;
+            int ax = -1;
+            for (int i = 0; i < 3; ++i) if (cand[i] && (ax < 0 || pen[i] < pen[ax])) ax = i;
+            S nl[3] = {0, 0, 0}; nl[ax] = x[ax] >= 0 ? (S)1 : (S)-1;
+            S n[3]; mat_vec(b.R, nl, n);      // outward normal of b: pushes a out of b
+            if (!flip) add_contact(a.ref, b.ref, a.slot, b.slot, pt, n, pen[ax], mu, penalty);
+            else { S nn[3] = {-n[0], -n[1], -n[2]}; add_contact(b.ref, a.ref, b.slot, a.slot, pt, nn, pen[ax], mu, penalty); }
+        }
+    }
+    void shapes_world(const Articulation<S>& art, const M3<S>& Rb, const S* pb, const float* root0) {
+        for (int s = 0; s < m->nshapes; ++s) {
+            ShapeW<S>& w = sh[s];
+            S ql[4] = {(S)m->shape_quat[s][0], (S)m->shape_quat[s][1], (S)m->shape_quat[s][2], (S)m->shape_quat[s][3]};
+            S pl[3] = {(S)m->shape_pos[s][0], (S)m->shape_pos[s][1], (S)m->shape_pos[s][2]};
+            M3<S> Rl = quat_to_R(ql), Ro; S po[3];
+            w.kind = m->shape_owner_kind[s]; w.slot = m->shape_slot[s];
+            if (w.kind == MPPIB_OWNER_STATIC) {
+                const float* rs = root0 + 13 * m->shape_actor[s];
+                S q[4] = {(S)rs[3], (S)rs[4], (S)rs[5], (S)rs[6]}; Ro = quat_to_R(q); for (int i = 0; i < 3; ++i) po[i] = (S)rs[i];
+                w.ref = REF_STATIC;
+            } else if (w.kind == MPPIB_OWNER_LINK) {
+                const int b = m->shape_owner[s];
+                if (b >= 0) { Ro = art.Rw[b]; for (int i = 0; i < 3; ++i) po[i] = art.pw[b][i]; w.ref = b; }
+                else { Ro = Rb; for (int i = 0; i < 3; ++i) po[i] = pb[i]; w.ref = REF_STATIC; }
+            } else {
+                const FreeBody<S>& b = fb[m->shape_owner[s]]; Ro = b.R; for (int i = 0; i < 3; ++i) po[i] = b.x[i];
+                w.ref = REF_FREE0 + m->shape_owner[s];
+            }
+            for (int r = 0; r < 3; ++r) {
+                S acc = 0; for (int j = 0; j < 3; ++j) acc += Ro.a[r][j] * pl[j]; w.c[r] = po[r] + acc;
+                for (int c = 0; c < 3; ++c) { S a2 = 0; for (int j = 0; j < 3; ++j) a2 += Ro.a[r][j] * Rl.a[j][c]; w.R.a[r][c] = a2; }
+                w.half[r] = shalf[s][r];
+            }
+            w.mu = smu[s];
+            w.rad = std::sqrt(w.half[0] * w.half[0] + w.half[1] * w.half[1] + w.half[2] * w.half[2]);
+        }
+    }
+    bool near(const ShapeW<S>& a, const ShapeW<S>& b) const {
+        S d2 = 0; for (int i = 0; i < 3; ++i) d2 += (a.c[i] - b.c[i]) * (a.c[i] - b.c[i]);
+        const S r = a.rad + b.rad; return d2 <= r * r;
+    }
+    void detect() {
+        nc = 0;
+        const int ns = m->nshapes;
+        for (int a = 0; a < ns; ++a) {
+            if (sh[a].kind != MPPIB_OWNER_FREE) continue;
+            if (m->ground_plane) {
+                const S mu = (S)0.5 * (sh[a].mu + (S)m->ground_friction);
+                for (int ix = -1; ix <= 1; ix += 2) for (int iy = -1; iy <= 1; iy += 2) for (int iz = -1; iz <= 1; iz += 2) {
+                    S loc[3] = {ix * sh[a].half[0], iy * sh[a].half[1], iz * sh[a].half[2]}, pt[3];
+                    mat_vec(sh[a].R, loc, pt); for (int i = 0; i < 3; ++i) pt[i] += sh[a].c[i];
+                    if (pt[2] < (S)m->ground_margin) { S n[3] = {0, 0, 1}; add_contact(sh[a].ref, REF_STATIC, sh[a].slot, -1, pt, n, -pt[2], mu, 0); }
+                }
+            }
+            for (int b = 0; b < ns; ++b) {
+                if (b == a || sh[b].ref == sh[a].ref) continue;
+                if (sh[b].kind == MPPIB_OWNER_FREE && b < a) continue;       // free-free pairs once
+                if (!near(sh[a], sh[b])) continue;
+                points_in_box(sh[a], sh[b], false, 0);
+                points_in_box(sh[b], sh[a], true, 0);
+            }
+        }
+        for (int a = 0; a < ns; ++a) {                                        // articulation link vs static box
+            if (sh[a].kind != MPPIB_OWNER_LINK || sh[a].ref == REF_STATIC) continue;
+            for (int b = 0; b < ns; ++b) {
+                if (sh[b].kind != MPPIB_OWNER_STATIC || !near(sh[a], sh[b])) continue;
+                points_in_box(sh[a], sh[b], false, 1);
+                points_in_box(sh[b], sh[a], true, 1);
+            }
+        }
+    }
+    void solve(const Articulation<S>& art, S h) {
+        const S kp = (S)m->contact_kp, kd = (S)m->contact_kd;
+        const S gamma = (S)1 / (h * (h * kp + kd)), beta = h * kp / (h * kp + kd);
+        for (int j = 0; j < m->nb; ++j) { dqv[j] = 0; Dj[j] = std::max((S)1e-6, art.D[j]); }
+        for (int it = 0; it < m->contact_iters; ++it) for (int i = 0; i < nc; ++i) {
+            Contact<S>& c = ct[i];
+            S va[3], vb[3], vr[3];
+            point_velocity(c.refA, c.p, art, va); point_velocity(c.refB, c.p, art, vb);
+            for (int r = 0; r < 3; ++r) vr[r] = va[r] - vb[r];
+            const S vn = vr[0] * c.n[0] + vr[1] * c.n[1] + vr[2] * c.n[2];
+            const S kn = inv_mass(c, c.n, art);
+            if (!(kn > 0)) continue;
+            // penetration: push out (at most max_depen m/s, so squeezed bodies are not shot out); gap: may close at most gap / h
+            const S bias = c.d > 0 ? std::min(beta * c.d / h, (S)m->max_depen) : c.d / h;
+            S dl = (-vn + bias - gamma * c.ln) / (kn + gamma);
+            const S ln_new = std::max((S)0, c.ln + dl); dl = ln_new - c.ln; c.ln = ln_new;
+            apply_impulse(c, c.n, dl, art);
+            S* lts[2] = {&c.lt1, &c.lt2}; const S* ts[2] = {c.t1, c.t2};
+            for (int e = 0; e < 2; ++e) {
+                point_velocity(c.refA, c.p, art, va); point_velocity(c.refB, c.p, art, vb);
+                const S vt = (va[0] - vb[0]) * ts[e][0] + (va[1] - vb[1]) * ts[e][1] + (va[2] - vb[2]) * ts[e][2];
+                const S kt = inv_mass(c, ts[e], art);
+                if (!(kt > 0)) continue;
+                const S lim = c.mu * c.ln;
+                const S lt_new = std::min(std::max(*lts[e] - vt / kt, -lim), lim);
+                apply_impulse(c, ts[e], lt_new - *lts[e], art); *lts[e] = lt_new;
+            }
+        }
+        // totals: net force per slot, reaction wrench on articulation bodies
+        for (int s = 0; s < MPPIB_MAX_SLOTS; ++s) net[s][0] = net[s][1] = net[s][2] = 0;
+        for (int i = 0; i < nc; ++i) {
+            Contact<S>& c = ct[i];
+            S F[3];
+            for (int r = 0; r < 3; ++r) F[r] = (c.ln * c.n[r] + c.lt1 * c.t1[r] + c.lt2 * c.t2[r]) / h;
+            if (c.slotA >= 0) for (int r = 0; r < 3; ++r) net[c.slotA][r] += F[r];
+            if (c.slotB >= 0) for (int r = 0; r < 3; ++r) net[c.slotB][r] -= F[r];
+        }
+    }
+    void integrate(S h) {
+        for (int f = 0; f < m->nfree; ++f) {
+            FreeBody<S>& b = fb[f];
+            for (int i = 0; i < 3; ++i) b.x[i] += h * b.v[i];
+            S wq[4] = {b.w[0], b.w[1], b.w[2], 0}, dq[4]; quat_mul(wq, b.q, dq);
+            S l = 0; for (int i = 0; i < 4; ++i) { b.q[i] += (S)0.5 * h * dq[i]; l += b.q[i] * b.q[i]; }
+            l = (S)1 / std::sqrt(l); for (int i = 0; i < 4; ++i) b.q[i] *= l;
+            refresh_free(f);
+        }
+    }
+};
+
+template <class S>
+void rollout_one(const MppibModel* m, const MppibParams* p, int K, int k, S* q, S* qd, ContactWorld<S>* cw, const float* root0,
                  const float* actions, int t0, int nsteps, float* obs) {
     const int nb = m->nb, nu = m->nu, T = p->T;
     const S h = (S)p->dt / (S)p->substeps;
+    const bool contacts = cw != nullptr;
     Articulation<S> art; art.m = m; art.nb = nb;
     // base frame and gravity (Featherstone: a_base = -g expressed in base coordinates)
     S bq[4] = {(S)m->base_quat[0], (S)m->base_quat[1], (S)m->base_quat[2], (S)m->base_quat[3]};
+    S bp[3] = {(S)m->base_pos[0], (S)m->base_pos[1], (S)m->base_pos[2]};
     M3<S> Rb = quat_to_R(bq);
     std::memset(&art.a0, 0, sizeof(art.a0));
     if (m->gravity_on) for (int i = 0; i < 3; ++i) { S s = 0; for (int j = 0; j < 3; ++j) s += Rb.a[j][i] * (S)m->gravity[j]; art.a0.a[3 + i] = -s; }
@@ -285,28 +569,34 @@ void rollout_one(const MppibModel* m, const MppibParams* p, int K, int k, S* q, 
                 }
                 if (any) art.aba(tau, dimp, qdd);
             }
+            S qdn[MPPIB_MAX_BODIES];
+            for (int i = 0; i < nb; ++i) qdn[i] = qd[i] + h * qdd[i];          // predicted (contact-free) joint velocities
+            if (contacts) {
+                // contacts act on the predicted velocities: poses of the start of the substep, velocities after gravity / drive
+                art.kinematics(q, qdn);
+                art.world_frames(Rb, bp);
+                cw->shapes_world(art, Rb, bp, root0);
+                cw->detect();
+                for (int f = 0; f < m->nfree; ++f) if (m->free_gravity[f]) for (int i = 0; i < 3; ++i) cw->fb[f].v[i] += h * (S)m->gravity[i];
+                cw->solve(art, h);
+                for (int i = 0; i < nb; ++i) qdn[i] += cw->dqv[i];
+            }
             for (int i = 0; i < nb; ++i) {           // semi-implicit Euler + velocity / position limits
-                S v = qd[i] + h * qdd[i];
-                v = std::min(std::max(v, -(S)m->qd_max[i]), (S)m->qd_max[i]);
+                S v = std::min(std::max(qdn[i], -(S)m->qd_max[i]), (S)m->qd_max[i]);
                 S x = q[i] + h * v;
                 if (x < (S)m->q_lo[i]) { x = (S)m->q_lo[i]; if (v < 0) v = 0; }
                 if (x > (S)m->q_hi[i]) { x = (S)m->q_hi[i]; if (v > 0) v = 0; }
                 q[i] = x; qd[i] = v;
             }
+            if (contacts) cw->integrate(h);
         }
         if (!obs) continue;
         // observe (refresh_* tensors, isaacgym_wrapper.py:642-645) -------------------------------------
         art.kinematics(q, qd);
-        M3<S> Rw[MPPIB_MAX_BODIES]; S pw[MPPIB_MAX_BODIES][3], qw[MPPIB_MAX_BODIES][4];
+        art.world_frames(Rb, bp);
+        S qw[MPPIB_MAX_BODIES][4];
         for (int i = 0; i < nb; ++i) {
-            const M3<S>& Rp = m->parent[i] >= 0 ? Rw[m->parent[i]] : Rb;
             const S* qp = m->parent[i] >= 0 ? qw[m->parent[i]] : bq;
-            S pp[3]; for (int r = 0; r < 3; ++r) pp[r] = m->parent[i] >= 0 ? pw[m->parent[i]][r] : (S)m->base_pos[r];
-            for (int r = 0; r < 3; ++r) {
-                S s = 0; for (int j = 0; j < 3; ++j) s += Rp.a[r][j] * art.pl[i][j];
-                pw[i][r] = pp[r] + s;
-                for (int cc = 0; cc < 3; ++cc) { S s2 = 0; for (int j = 0; j < 3; ++j) s2 += Rp.a[r][j] * art.Rl[i].a[j][cc]; Rw[i].a[r][cc] = s2; }
-            }
             S qt[4] = {(S)m->tree_quat[i][0], (S)m->tree_quat[i][1], (S)m->tree_quat[i][2], (S)m->tree_quat[i][3]};
             S tmp[4]; quat_mul(qp, qt, tmp);
             if (m->jtype[i] == MPPIB_JOINT_REVOLUTE) {
@@ -318,27 +608,36 @@ void rollout_one(const MppibModel* m, const MppibParams* p, int K, int k, S* q, 
         const size_t TK = (size_t)T * K;
         for (int o = 0; o < p->nobs; ++o) {
             float vals[2 * MPPIB_MAX_BODIES > 13 ? 2 * MPPIB_MAX_BODIES : 13]; int w = 0;
-            if (p->obs[o].kind == MPPIB_OBS_LINK_STATE) {
-                int l = p->obs[o].index, b = m->link_body[l];
-                const M3<S>& R = b >= 0 ? Rw[b] : Rb;
+            const int kind = p->obs[o].kind, idx = p->obs[o].index;
+            if (kind == MPPIB_OBS_LINK_STATE) {
+                int l = idx, b = m->link_body[l];
+                const M3<S>& R = b >= 0 ? art.Rw[b] : Rb;
                 S lp[3] = {(S)m->link_p[l][0], (S)m->link_p[l][1], (S)m->link_p[l][2]};
-                S off[3]; for (int r = 0; r < 3; ++r) { S s = 0; for (int j = 0; j < 3; ++j) s += R.a[r][j] * lp[j]; off[r] = s; }
+                S off[3]; mat_vec(R, lp, off);
                 S ql[4] = {(S)m->link_quat[l][0], (S)m->link_quat[l][1], (S)m->link_quat[l][2], (S)m->link_quat[l][3]};
                 S qo[4]; quat_mul(b >= 0 ? qw[b] : bq, ql, qo);
                 S ww[3] = {0, 0, 0}, vw[3] = {0, 0, 0};
-                if (b >= 0) for (int r = 0; r < 3; ++r) for (int j = 0; j < 3; ++j) { ww[r] += R.a[r][j] * art.v[b].a[j]; vw[r] += R.a[r][j] * art.v[b].a[3 + j]; }
+                if (b >= 0) for (int r = 0; r < 3; ++r) { ww[r] = art.ww[b][r]; vw[r] = art.vw[b][r]; }
                 S wxo[3]; cross3(ww, off, wxo);
-                for (int r = 0; r < 3; ++r) vals[r] = (float)((b >= 0 ? pw[b][r] : (S)m->base_pos[r]) + off[r]);
+                for (int r = 0; r < 3; ++r) vals[r] = (float)((b >= 0 ? art.pw[b][r] : bp[r]) + off[r]);
                 for (int r = 0; r < 4; ++r) vals[3 + r] = (float)qo[r];
                 for (int r = 0; r < 3; ++r) vals[7 + r] = (float)(vw[r] + wxo[r]);
                 for (int r = 0; r < 3; ++r) vals[10 + r] = (float)ww[r];
                 w = 13;
-            } else if (p->obs[o].kind == MPPIB_OBS_DOF_STATE) {
+            } else if (kind == MPPIB_OBS_DOF_STATE) {
                 for (int i = 0; i < nb; ++i) { vals[2 * i] = (float)q[i]; vals[2 * i + 1] = (float)qd[i]; }
                 w = 2 * nb;
+            } else if (kind == MPPIB_OBS_FREE_STATE) {
+                w = 13;
+                for (int r = 0; r < 13; ++r) vals[r] = 0.f;
+                if (contacts && idx < m->nfree) {
+                    const FreeBody<S>& b = cw->fb[idx];
+                    for (int r = 0; r < 3; ++r) { vals[r] = (float)b.x[r]; vals[7 + r] = (float)b.v[r]; vals[10 + r] = (float)b.w[r]; }
+                    for (int r = 0; r < 4; ++r) vals[3 + r] = (float)b.q[r];
+                }
             } else {
-                w = p->obs[o].kind == MPPIB_OBS_CONTACT ? 3 : 13;
-                for (int r = 0; r < w; ++r) vals[r] = 0.f;
+                w = 3;
+                for (int r = 0; r < 3; ++r) vals[r] = contacts && idx < MPPIB_MAX_SLOTS ? (float)cw->net[idx][r] : 0.f;
             }
             for (int r = 0; r < w; ++r) obs[(size_t)(row + r) * TK + (size_t)t * K + k] = vals[r];
             row += w;
@@ -347,18 +646,43 @@ void rollout_one(const MppibModel* m, const MppibParams* p, int K, int k, S* q, 
 }
 
 template <class S>
-void rollout_impl(const MppibModel* m, const MppibParams* p, const float* state0, float* state,
+void rollout_impl(const MppibModel* m, const MppibParams* p, const float* state0, const float* root0, float* state,
                   const float* actions, int t0, int nsteps, float* obs, int nthreads) {
     const int K = p->K, nb = m->nb;
+    const bool contacts = m->nfree > 0 || m->nshapes > 0;
     parallel_for(K, nthreads, [&](int a, int b) {
+        std::vector<ContactWorld<S>> cwv(contacts ? 1 : 0);
         for (int k = a; k < b; ++k) {
             S q[MPPIB_MAX_BODIES], qd[MPPIB_MAX_BODIES];
             for (int i = 0; i < nb; ++i) {
                 q[i] = state0 ? (S)state0[i] : (S)state[(size_t)i * K + k];
                 qd[i] = state0 ? (S)state0[nb + i] : (S)state[(size_t)(nb + i) * K + k];
             }
-            rollout_one<S>(m, p, K, k, q, qd, actions, t0, nsteps, obs);
-            if (state) for (int i = 0; i < nb; ++i) { state[(size_t)i * K + k] = (float)q[i]; state[(size_t)(nb + i) * K + k] = (float)qd[i]; }
+            ContactWorld<S>* cw = contacts ? &cwv[0] : nullptr;
+            if (cw) {
+                cw->m = m; cw->p = p; cw->nc = 0;
+                for (int s = 0; s < MPPIB_MAX_SLOTS; ++s) cw->net[s][0] = cw->net[s][1] = cw->net[s][2] = 0;
+                cw->init_params(p->k_offset + (uint32_t)k);
+                for (int f = 0; f < m->nfree; ++f) {
+                    FreeBody<S>& fbd = cw->fb[f];
+                    for (int r = 0; r < 13; ++r) {
+                        const S v = state0 ? (S)root0[13 * m->free_actor[f] + r] : (S)state[(size_t)(2 * nb + 13 * f + r) * K + k];
+                        if (r < 3) fbd.x[r] = v; else if (r < 7) fbd.q[r - 3] = v; else if (r < 10) fbd.v[r - 7] = v; else fbd.w[r - 10] = v;
+                    }
+                    cw->refresh_free(f);
+                }
+            }
+            rollout_one<S>(m, p, K, k, q, qd, cw, root0, actions, t0, nsteps, obs);
+            if (state) {
+                for (int i = 0; i < nb; ++i) { state[(size_t)i * K + k] = (float)q[i]; state[(size_t)(nb + i) * K + k] = (float)qd[i]; }
+                if (cw) for (int f = 0; f < m->nfree; ++f) {
+                    const FreeBody<S>& fbd = cw->fb[f];
+                    for (int r = 0; r < 13; ++r) {
+                        const S v = r < 3 ? fbd.x[r] : (r < 7 ? fbd.q[r - 3] : (r < 10 ? fbd.v[r - 7] : fbd.w[r - 10]));
+                        state[(size_t)(2 * nb + 13 * f + r) * K + k] = (float)v;
+                    }
+                }
+            }
         }
     });
 }
@@ -414,10 +738,10 @@ void oracle_sample(const MppibModel* m, const MppibParams* p, uint64_t seed, uin
     });
 }
 
-void oracle_rollout(const MppibModel* m, const MppibParams* p, const float* state0, float* state, const float* actions,
+void oracle_rollout(const MppibModel* m, const MppibParams* p, const float* state0, const float* root0, float* state, const float* actions,
                     int32_t t0, int32_t nsteps, float* obs, int32_t use_double, int32_t nthreads) {
-    if (use_double) rollout_impl<double>(m, p, state0, state, actions, t0, nsteps, obs, nthreads);
-    else rollout_impl<float>(m, p, state0, state, actions, t0, nsteps, obs, nthreads);
+    if (use_double) rollout_impl<double>(m, p, state0, root0, state, actions, t0, nsteps, obs, nthreads);
+    else rollout_impl<float>(m, p, state0, root0, state, actions, t0, nsteps, obs, nthreads);
 }
 
 // K3 restatement (double accumulation).  partial = (beta, eta, W[T][nu]).

@@ -61,8 +61,8 @@ def sample(model, params, seed, plan_idx, U, k_offset=0, k_total=None, prior_row
     return actions, noise
 
 
-def rollout(model, params, state0, actions, t0=0, nsteps=None, state=None, want_obs=True, use_double=False, nthreads=1):
-    """state0: (NS,) broadcast row or None (continue from `state` (NS,K) in place)."""
+def rollout(model, params, state0, actions, t0=0, nsteps=None, state=None, want_obs=True, use_double=False, nthreads=1, root0=None):
+    """state0: (2*ndof,) broadcast row or None (continue from `state` (NS,K) in place); root0: (A,13) actor root states."""
     K, T = params.K, params.T
     nsteps = T if nsteps is None else nsteps
     NS = lib().oracle_state_size(C.byref(model))
@@ -72,7 +72,8 @@ def rollout(model, params, state0, actions, t0=0, nsteps=None, state=None, want_
         state = np.zeros((NS, K), np.float32)
     s0 = None if state0 is None else np.ascontiguousarray(state0, np.float32)
     actions = np.ascontiguousarray(actions, np.float32)
-    lib().oracle_rollout(C.byref(model), C.byref(params), _f(s0), _f(state), _f(actions), C.c_int32(t0), C.c_int32(nsteps),
+    r0 = None if root0 is None else np.ascontiguousarray(root0, np.float32)
+    lib().oracle_rollout(C.byref(model), C.byref(params), _f(s0), _f(r0), _f(state), _f(actions), C.c_int32(t0), C.c_int32(nsteps),
                          _f(obs), C.c_int32(int(use_double)), C.c_int32(nthreads))
     return state, obs
 

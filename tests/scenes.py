@@ -3,7 +3,7 @@ import copy
 
 import numpy as np
 
-from mppi_isaac_b200.model.blob import (OBS_DOF_STATE, OBS_LINK_STATE, build_scene, make_params)
+from mppi_isaac_b200.model.blob import (OBS_CONTACT, OBS_DOF_STATE, OBS_FREE_STATE, OBS_LINK_STATE, build_scene, make_params)
 from mppi_isaac_b200.utils.config_store import IsaacGymConfig, MPPIConfig, load_actor_cfgs, load_isaacgym_config
 
 
@@ -61,9 +61,49 @@ def gripper_setup(K=64, T=30, mode="simple", **kw):
     return sc, p, state0
 
 
+def push_setup(K=32, T=10, noise=False, block_pos=(1.0, 1.5, 0.1), robot_pos=(0.0, 1.5, 0.05), dt=0.1, substeps=1, obstacles=True, **kw):
+    """heijn omni base + pushable block (+ two static boxes): BASELINE config C4 geometry, contact path."""
+    names = ["heijn", "block"] + (["paper_obst1", "paper_obst2"] if obstacles else []) + ["goal"]
+    actors = load_actor_cfgs(names)
+    actors[0].init_pos = list(robot_pos)
+    actors[1].init_pos = list(block_pos)
+    if not noise:
+        for a in actors:
+            a.noise_sigma_size, a.noise_percentage_mass, a.noise_percentage_friction = None, 0.0, 0.0
+    sim = IsaacGymConfig(dt=dt, substeps=substeps)
+    sc = build_scene(actors, substep=dt / substeps)
+    rn = sc.robot.link_names
+    obs = [(OBS_LINK_STATE, rn.index("front_link")), (OBS_DOF_STATE, 0), (OBS_FREE_STATE, 0), (OBS_CONTACT, sc.contact_slot[sc.body_offset[1]])]
+    if obstacles:
+        obs += [(OBS_CONTACT, sc.contact_slot[sc.body_offset[2]]), (OBS_CONTACT, sc.contact_slot[sc.body_offset[3]])]
+    mc = MPPIConfig(num_samples=K, horizon=T, mppi_mode="simple", sampling_method="random", noise_sigma=[[0.5, 0, 0], [0, 0.5, 0], [0, 0, 1.8]],
+                    u_min=[-0.6, -0.6, -1.0], u_max=[0.6, 0.6, 1.0], lambda_=0.05, sample_null_action=True, **kw)
+    p = make_params(mc, sim, sc.nu, K, obs)
+    state0 = np.zeros(6, np.float32)
+    return sc, p, state0
+
+
 def panda_cfg(K=64, T=30, device="cpu", **mppi_kw):
     cfg = load_isaacgym_config("config_panda_b200")
     cfg = copy.deepcopy(cfg)
+    cfg.mppi.num_samples, cfg.mppi.horizon, cfg.mppi.device = K, T, device
+    for k, v in mppi_kw.items():
+        setattr(cfg.mppi, k, v)
+    return cfg
+
+
+def push_cfg(K=64, T=10, device="cpu", **mppi_kw):
+    """BASELINE config C4 (heijn_push) at a test-sized K / T."""
+    cfg = copy.deepcopy(load_isaacgym_config("config_heijn_push_b200"))
+    cfg.mppi.num_samples, cfg.mppi.horizon, cfg.mppi.device = K, T, device
+    for k, v in mppi_kw.items():
+        setattr(cfg.mppi, k, v)
+    return cfg
+
+
+def pick_cfg(K=32, T=9, device="cpu", **mppi_kw):
+    """BASELINE config C5 (panda_pick) at a test-sized K / T."""
+    cfg = copy.deepcopy(load_isaacgym_config("config_panda_pick_b200"))
     cfg.mppi.num_samples, cfg.mppi.horizon, cfg.mppi.device = K, T, device
     for k, v in mppi_kw.items():
         setattr(cfg.mppi, k, v)

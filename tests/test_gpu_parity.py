@@ -13,7 +13,7 @@ import pytest
 import torch
 
 from mppi_isaac_b200.model.blob import MODE_SIMPLE, OBS_DOF_STATE, OBS_LINK_STATE
-from scenes import gripper_setup, panda_cfg, panda_setup, point_cfg, point_setup
+from scenes import gripper_setup, panda_cfg, panda_setup, pick_cfg, point_cfg, point_setup, push_cfg, push_setup
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -235,3 +235,98 @@ def test_stepwise_protocol_on_gpu_matches_batched():
         ua, ub = a.compute_action(q, [0] * 7), b.compute_action(q, [0] * 7)
         assert float((ua - ub).abs().max()) <= 1e-6
     assert torch.equal(a.mppi.actions, b.mppi.actions)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# free bodies + contacts (configs C4 / C5).  Contact dynamics are discontinuous (a sample point flips between "inside"
+# and "outside"), so the tight gate is LOCK-STEP: the oracle's state is re-injected before every step.  Free-running
+# agreement is checked statistically ("drift reported, not gated").
+# ---------------------------------------------------------------------------------------------------------------
+def _push_actions(T, K, seed=0, vx=0.5):
+    a = np.random.default_rng(seed).uniform(-0.6, 0.6, (T, 3, K)).astype(np.float32)
+    a[:, 0] = vx + 0.1 * a[:, 0]
+    return a
+
+
+def test_contact_rollout_lockstep_parity(oracle):
+    K, T = 128, 12
+    sc, p, s0 = push_setup(K=K, T=T, noise=True, block_pos=(0.62, 1.5, 0.1))
+    be = gpu_backend(sc, p)
+    actions = _push_actions(T, K)
+    a_d, root_d = dev(actions), dev(sc.root_state0)
+    NS = be.state_size()
+    assert NS == 6 + 13
+    state_ref = np.zeros((NS, K), np.float32)
+    state_ref[6:] = sc.root_state0[1][:, None]
+    R = be.obs_size()
+    obs = torch.zeros((R, T, K), device=DEV)
+    worst_q, worst_x, worst_v, touched = 0.0, 0.0, 0.0, 0
+    for t in range(T):
+        st = dev(state_ref)
+        be.rollout(None, st, a_d, t, 1, obs, root0=root_d)
+        state_ref, o_ref = oracle.rollout(sc.model, p, None, actions, t, 1, state=state_ref.copy(), root0=sc.root_state0)
+        g = st.cpu().numpy()
+        worst_q = max(worst_q, float(np.abs(g[:6] - state_ref[:6]).max()))
+        worst_x = max(worst_x, float(np.abs(g[6:13] - state_ref[6:13]).max()))
+        worst_v = max(worst_v, float(np.abs(g[13:19] - state_ref[13:19]).max()))
+        f_g, f_r = obs[32:35, t].cpu().numpy(), o_ref[32:35, t]
+        touched += int((np.abs(f_r[0]) > 1.0).sum())
+        assert np.abs(f_g - f_r).max() <= 5e-2 * max(1.0, np.abs(f_r).max())          # net contact force on the block [N]
+    assert touched > K                                                                 # the robot really pushes the block in this test
+    assert worst_q <= 1e-4 and worst_x <= 1e-4 and worst_v <= 2e-3                     # one-step root state: 1e-4 (m, -), 2e-3 m/s
+
+
+def test_contact_rollout_free_running_statistics(oracle):
+    K, T = 512, 15
+    sc, p, s0 = push_setup(K=K, T=T, noise=True, block_pos=(0.62, 1.5, 0.1))
+    be = gpu_backend(sc, p)
+    actions = _push_actions(T, K, seed=1)
+    obs = torch.zeros((be.obs_size(), T, K), device=DEV)
+    be.rollout(dev(s0), None, dev(actions), 0, T, obs, root0=dev(sc.root_state0))
+    _, o_ref = oracle.rollout(sc.model, p, s0, actions, root0=sc.root_state0, nthreads=8)
+    o = obs.cpu().numpy()
+    assert np.isfinite(o).all()
+    dx = np.abs(o[19:22, -1] - o_ref[19:22, -1]).max(axis=0)                           # final block position per rollout
+    assert np.median(dx) <= 1e-4 and np.mean(dx < 5e-3) >= 0.95, (np.median(dx), np.mean(dx < 5e-3))
+    assert abs(o[19, -1].mean() - o_ref[19, -1].mean()) <= 2e-3                        # ensemble mean of the pushed distance
+    np.testing.assert_allclose(o[13:19], o_ref[13:19], atol=5e-3)                      # robot DOF state (velocity drive dominates)
+
+
+def test_contact_randomisation_and_shard_offset_on_device(oracle):
+    sc, p, s0 = push_setup(K=64, T=2, noise=True, block_pos=(3.0, 3.0, 0.1), obstacles=False, dt=0.05)
+    root0 = sc.root_state0.copy(); root0[1, 7] = 1.0
+    a = np.zeros((2, 3, 64), np.float32)
+    be = gpu_backend(sc, p)
+    obs = torch.zeros((be.obs_size(), 2, 64), device=DEV)
+    be.rollout(dev(s0), None, dev(a), 0, 2, obs, root0=dev(root0))
+    _, o_ref = oracle.rollout(sc.model, p, s0, a, root0=root0)
+    np.testing.assert_allclose(obs.cpu().numpy(), o_ref, atol=2e-4)                   # same per-rollout size / mass / friction draws
+    p2 = copy.copy(p); p2.K, p2.k_offset = 32, 32
+    be2 = gpu_backend(sc, p2)
+    obs2 = torch.zeros((be2.obs_size(), 2, 32), device=DEV)
+    be2.rollout(dev(s0), None, dev(a[:, :, :32]), 0, 2, obs2, root0=dev(root0))
+    assert torch.equal(obs2, obs[:, :, 32:])                                           # global sample index keys the draws
+
+
+@pytest.mark.parametrize("task", ["push", "pick"])
+def test_contact_plan_through_planner_api(task):
+    """First plan from the same world state, GPU (CUDA graph) vs checker backend, configs C4 / C5 at test size."""
+    from mppi_isaac_b200 import MPPIisaacPlanner
+    from mppi_isaac_b200.objectives import PandaPickObjective, PushObjective
+    from oracle.backend import OracleBackend
+    if task == "push":
+        mk, obj, q = (lambda d: push_cfg(K=512, T=10, device=d)), PushObjective, [0.0, 0.0, 0.0]
+    else:
+        mk, obj, q = (lambda d: pick_cfg(K=256, T=12, device=d)), PandaPickObjective, [0.0, -0.94, 0.0, -2.8, 0.0, 1.8675, 0.0, 0.02, 0.02]
+    gpu = MPPIisaacPlanner(mk(DEV), obj(), use_cuda_graph=True)
+    cpu = MPPIisaacPlanner(mk("cpu"), obj(), backend=OracleBackend(nthreads=8))
+    ag, ac = gpu.compute_action(q, [0.0] * len(q)), cpu.compute_action(q, [0.0] * len(q))
+    assert torch.isfinite(ag).all()
+    lim = float(gpu.mppi.backend.params.u_max[0])
+    assert float((ag - ac).abs().max()) <= 2e-2 * lim
+    for _ in range(3):
+        ag = gpu.compute_action(q, [0.0] * len(q))
+    assert gpu.mppi._graph is not None and torch.isfinite(ag).all()
+    blk = "block" if task == "push" else "panda_pick_block"
+    zg, zc = gpu.sim.get_actor_position_by_name(blk)[:, 2], cpu.sim.get_actor_position_by_name(blk)[:, 2]
+    assert abs(float(zg.mean()) - float(zc.mean())) <= 5e-3

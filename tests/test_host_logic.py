@@ -5,14 +5,14 @@ import pytest
 import torch
 
 from mppi_isaac_b200 import MPPIisaacPlanner
-from mppi_isaac_b200.objectives import PandaReachObjective, PointReachObjective
+from mppi_isaac_b200.objectives import PandaPickObjective, PandaReachObjective, PointReachObjective, PushObjective
 from mppi_isaac_b200.planner.mppi import shard_samples
 from mppi_isaac_b200.planner.rollout_sim import ObservationError, RolloutSim
 from mppi_isaac_b200.utils.config_store import IsaacGymConfig
 from mppi_isaac_b200.utils.conversions import matrix_to_euler_angles, quaternion_to_matrix, quaternion_to_yaw
 from mppi_isaac_b200.utils.transport import bytes_to_torch, torch_to_bytes
 from oracle.backend import OracleBackend
-from scenes import panda_cfg, point_cfg
+from scenes import panda_cfg, pick_cfg, point_cfg, push_cfg
 
 Q0 = [0.0, -0.94, 0.0, -2.8, 0.0, 1.8675, 0.0]
 
@@ -171,3 +171,46 @@ def test_transport_and_conversions():
     np.testing.assert_allclose(ours, rot.as_euler("ZYX"), atol=1e-9)
     wxyz = np.roll(rot.as_quat(), 1, axis=1)
     np.testing.assert_allclose(quaternion_to_matrix(torch.tensor(wxyz)).numpy(), rot.as_matrix(), atol=1e-12)
+
+
+def test_heijn_push_c4_through_the_planner():
+    """BASELINE config C4 geometry: free block + static obstacles + contact-force cost through the drop-in surface."""
+    p = make(push_cfg(K=64, T=10), PushObjective())
+    s = p.sim
+    assert s.scene.model.nfree == 1 and s.scene.num_bodies == 12                       # SURVEY section 8 table, C4: 8 / 12 bodies
+    a = p.compute_action([0.0, 0.0, 0.0], [0.0, 0.0, 0.0])
+    assert a.shape == (3,) and torch.isfinite(a).all()
+    blk = s.get_actor_position_by_name("block")
+    assert blk.shape == (640, 3) and blk.stride(0) != 0                                # per-rollout rows, not the static expand
+    assert s.get_actor_velocity_by_name("block").shape == (640, 3) and s.get_actor_orientation_by_name("block").shape == (640, 4)
+    assert s.get_actor_link_by_name("block", "box").shape == (640, 13)
+    f = s.get_actor_contact_forces_by_name(actor_name="paper_obst1", link_name="box")
+    assert f.shape == (640, 3)
+    np.testing.assert_allclose(blk[:, 2].numpy(), 0.1, atol=0.02)                      # the block rests on the ground in every rollout
+    assert s._root_state.shape == (640, 5, 13)
+    with pytest.raises(ObservationError):
+        s._net_contact_force                                                               # dense tensors need observe='all'
+    dense = make(push_cfg(K=8, T=4), PushObjective(), observe="all")
+    dense.compute_action([0.0] * 3, [0.0] * 3)
+    assert dense.sim._net_contact_force.shape == (32, 12, 3) and dense.sim._rigid_body_state.shape == (32, 12, 13)
+    # closed loop: the planner drives the base towards the block (robot_to_block / push_align terms)
+    q = np.zeros(3)
+    d0 = np.hypot(2.5 - 0.31, 1.8 - 1.5)
+    for it in range(6):
+        a = p.compute_action(q, np.zeros(3)).numpy()
+        q = q + 0.1 * a
+    front = np.array([q[0] + 0.31 * np.cos(q[2]), 1.5 + q[1] + 0.31 * np.sin(q[2])])
+    assert np.hypot(2.5 - front[0], 1.8 - front[1]) < d0
+
+
+def test_panda_pick_c5_scene_and_cost():
+    p = make(pick_cfg(K=16, T=9), PandaPickObjective())
+    s = p.sim
+    assert s.scene.num_bodies == 17 and s.scene.model.nfree == 1 and s.scene.nu == 9   # SURVEY section 8 table, C5
+    q0 = [0.0, -0.94, 0.0, -2.8, 0.0, 1.8675, 0.0, 0.02, 0.02]
+    a = p.compute_action(q0, [0.0] * 9)
+    assert a.shape == (9,) and torch.isfinite(a).all()
+    blk = s.get_actor_position_by_name("panda_pick_block")
+    assert blk.shape == (144, 3)
+    assert float(blk[-16:, 2].min()) > 0.14 - 0.02 + 0.02 - 0.01                       # the cube fell onto the table (top at 0.14), not through it
+    assert s.get_actor_contact_forces_by_name("table", "box").shape == (144, 3)
