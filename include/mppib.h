@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MPPIB_ABI_VERSION 4
+#define MPPIB_ABI_VERSION 5
 
 #define MPPIB_MAX_BODIES 16   /* moving (1-DoF) bodies of the articulation            */
 #define MPPIB_MAX_LINKS  32   /* URDF links whose state can be observed               */
@@ -117,6 +117,10 @@ typedef struct MppibModel {
     int32_t cmd_i1[MPPIB_MAX_BODIES];
     float   cmd_c0[MPPIB_MAX_BODIES];
     float   cmd_c1[MPPIB_MAX_BODIES];
+    /* differential-drive base reduced to a planar chain: bodies 0,1,2 are VIRTUAL joints (world x, world y, yaw) whose
+       velocity targets follow the commanded body twist u = (v, omega): (v f(yaw), omega), f = forward axis rotated by yaw */
+    int32_t planar_base;
+    float   fwd_axis[2];
 
     /* observable links: pose of the link frame in its owning body's frame */
     int32_t link_body[MPPIB_MAX_LINKS];    /* -1 = rigidly attached to the base                   */

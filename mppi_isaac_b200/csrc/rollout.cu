@@ -229,6 +229,15 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
         const int nsub = nsteps > 0 ? p.substeps : 0;
 #pragma unroll 1
         for (int sub = 0; sub < nsub; ++sub) {
+            if (m.planar_base) {
+                // differential drive reduced to a planar base: body twist (v, omega) -> world-frame velocity targets of the
+                // three virtual joints; the forward axis turns with the current yaw (no lateral slip by construction)
+                const float v = p.u_scale * actions[((size_t)t * nu + 0) * K + k], w = p.u_scale * actions[((size_t)t * nu + 1) * K + k];
+                float sy, cy; sincosf(SM(2, F_Q), &sy, &cy);
+                SM(0, F_TGT) = v * (m.fwd_axis[0] * cy - m.fwd_axis[1] * sy);
+                SM(1, F_TGT) = v * (m.fwd_axis[0] * sy + m.fwd_axis[1] * cy);
+                SM(2, F_TGT) = w;
+            }
             // ------------------------------------------------------------------ sweep 1: root -> leaves
             {
                 Frame par = base;

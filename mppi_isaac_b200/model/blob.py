@@ -18,7 +18,7 @@ import numpy as np
 
 from .urdf import RobotModel, compile_urdf, load_compiled, quat_xyzw_to_R, R_to_quat_xyzw
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_BODIES, MAX_LINKS, MAX_NU, MAX_OBS, MAX_FREE, MAX_SHAPES = 16, 32, 16, 64, 4, 24
 MAX_CONTACTS, MAX_SLOTS = 24, 8
 
@@ -44,7 +44,7 @@ class MppibModel(C.Structure):
         ("effort", f32 * MAX_BODIES), ("damping", f32 * MAX_BODIES), ("kd", f32 * MAX_BODIES),
         ("armature", f32 * MAX_BODIES),
         ("cmd_i0", i32 * MAX_BODIES), ("cmd_i1", i32 * MAX_BODIES),
-        ("cmd_c0", f32 * MAX_BODIES), ("cmd_c1", f32 * MAX_BODIES),
+        ("cmd_c0", f32 * MAX_BODIES), ("cmd_c1", f32 * MAX_BODIES), ("planar_base", i32), ("fwd_axis", f32 * 2),
         ("link_body", i32 * MAX_LINKS), ("link_R", (f32 * 9) * MAX_LINKS), ("link_p", (f32 * 3) * MAX_LINKS), ("link_quat", (f32 * 4) * MAX_LINKS),
         ("free_actor", i32 * MAX_FREE), ("free_mass", f32 * MAX_FREE), ("free_mass_pct", f32 * MAX_FREE),
         ("free_half", (f32 * 3) * MAX_FREE), ("free_gravity", i32 * MAX_FREE), ("free_slot", i32 * MAX_FREE),
@@ -98,6 +98,7 @@ class Scene:
     contact_slot: Dict[int, int] = field(default_factory=dict)  # env rigid-body index -> slot
     ndof: int = 0
     nu: int = 0
+    virtual_dofs: int = 0                 # leading virtual joints of a planar (differential-drive) base: x, y, yaw
 
     @property
     def num_bodies(self) -> int:
@@ -163,9 +164,12 @@ def build_scene(actor_cfgs: list, gravity=(0.0, 0.0, -9.8), assets_dirs=None, su
                                   "(the reference's own initial-pose code is single-robot too: isaacgym_wrapper.py:220-229)")
     ra = robots[0]
     rcfg = actor_cfgs[ra]
-    if not rcfg.fixed:
-        raise NotImplementedError("floating-base robots (fixed: false) are not supported yet")
-    robot = load_robot(rcfg.urdf_file, fixed=True, assets_dirs=assets_dirs)
+    planar = not rcfg.fixed
+    if planar and not rcfg.differential_drive:
+        raise NotImplementedError("floating-base robots are supported as differential-drive bases only (planar reduction)")
+    robot = load_robot(rcfg.urdf_file, fixed=not planar, assets_dirs=assets_dirs)
+    if planar != bool(robot.planar_base):
+        raise ValueError(f"compiled model of {rcfg.urdf_file} does not match `fixed: {rcfg.fixed}`")
     if robot.nb > MAX_BODIES or robot.nlinks > MAX_LINKS:
         raise ValueError("robot exceeds MPPIB_MAX_BODIES / MPPIB_MAX_LINKS")
 
@@ -174,8 +178,12 @@ def build_scene(actor_cfgs: list, gravity=(0.0, 0.0, -9.8), assets_dirs=None, su
     m.nb, m.nlinks = robot.nb, robot.nlinks
     m.gravity_on = 1 if rcfg.gravity else 0
     _set(m.gravity, gravity)
-    _set(m.base_pos, rcfg.init_pos)
-    _set(m.base_quat, rcfg.init_ori)
+    if planar:      # the pose lives in the virtual joints (x, y, yaw); only the height of the plane is a constant
+        _set(m.base_pos, [0.0, 0.0, float(rcfg.init_pos[2])])
+        _set(m.base_quat, [0.0, 0.0, 0.0, 1.0])
+    else:
+        _set(m.base_pos, rcfg.init_pos)
+        _set(m.base_quat, rcfg.init_ori)
     if rcfg.dof_mode == "velocity":
         m.drive_mode, kd, arm = DRIVE_VELOCITY, 600.0, 0.0       # isaacgym_wrapper.py:497-500
     elif rcfg.dof_mode == "effort":
@@ -195,12 +203,28 @@ def build_scene(actor_cfgs: list, gravity=(0.0, 0.0, -9.8), assets_dirs=None, su
         m.q_lo[i], m.q_hi[i] = max(robot.q_lo[i], -1e30), min(robot.q_hi[i], 1e30)
         m.qd_max[i], m.effort[i] = min(robot.qd_max[i], 1e30), min(robot.effort[i], 1e30)
         m.damping[i], m.kd[i], m.armature[i] = robot.damping[i], kd, arm
+    if planar:
+        # wheel traction reduced to drives on the virtual joints: n wheels of radius r with velocity gain kd give a linear
+        # gain n kd / r^2 and a yaw gain kd sum(x_i^2) / r^2 (x_i = +-L/2); the reachable force is the friction cone mu m g
+        r, L, nw = float(rcfg.wheel_radius), float(rcfg.wheel_base), int(rcfg.wheel_count or 2)
+        mtot, mu, g = float(np.sum(robot.mass)), float(rcfg.friction), float(np.linalg.norm(gravity))
+        for j, (gain, lim) in enumerate(((nw * kd / r**2, mu * mtot * g), (nw * kd / r**2, mu * mtot * g),
+                                         (nw * kd * (L / 2) ** 2 / r**2, mu * mtot * g * L / 2))):
+            m.kd[j], m.effort[j], m.damping[j] = gain, lim, 0.0
+        wheels = [i for i, n in enumerate(robot.dof_names) if n in (rcfg.left_wheel_joints or []) + (rcfg.right_wheel_joints or [])]
+        axis = np.asarray(robot.tree_R[wheels[0]])[:, 2]                     # wheel axis in the root-link frame
+        fwd = np.cross(axis, [0.0, 0.0, 1.0])                                # a wheel turning +omega about `axis` rolls the base along axis x z
+        m.planar_base = 1
+        _set(m.fwd_axis, fwd[:2] / np.linalg.norm(fwd[:2]))
     # command map (apply_robot_cmd, isaacgym_wrapper.py:524-559)
     u_idx = 0
     if rcfg.differential_drive:
         r, L = float(rcfg.wheel_radius), float(rcfg.wheel_base)
         u_idx = 2
     for i, name in enumerate(robot.dof_names):
+        if planar and i < 3:
+            m.cmd_i0[i], m.cmd_c0[i], m.cmd_i1[i], m.cmd_c1[i] = 0, 0.0, 0, 0.0     # targets come from the planar-base rule
+            continue
         if rcfg.differential_drive and name in (rcfg.left_wheel_joints or []):
             m.cmd_i0[i], m.cmd_c0[i], m.cmd_i1[i], m.cmd_c1[i] = 0, 1.0 / r, 1, -L / (2 * r)   # _ik :510-522
         elif rcfg.differential_drive and name in (rcfg.right_wheel_joints or []):
@@ -289,12 +313,18 @@ def build_scene(actor_cfgs: list, gravity=(0.0, 0.0, -9.8), assets_dirs=None, su
     m.contact_margin = 0.01                                           # isaacgym_wrapper.py:33 contact_offset
 
     ndof = robot.nb
+    nvirt = 3 if planar else 0
     dof0 = np.zeros(2 * ndof, np.float32)
     if rcfg.init_joint_pose:
-        dof0[:] = np.asarray(rcfg.init_joint_pose, np.float32)[: 2 * ndof]
+        real = np.asarray(rcfg.init_joint_pose, np.float32)[: 2 * (ndof - nvirt)]
+        dof0[2 * nvirt: 2 * nvirt + len(real)] = real
+    if planar:
+        qx, qy, qz, qw = (float(v) for v in rcfg.init_ori)
+        dof0[0], dof0[2] = float(rcfg.init_pos[0]), float(rcfg.init_pos[1])
+        dof0[4] = math.atan2(2 * (qw * qz + qx * qy), 1 - 2 * (qy * qy + qz * qz))
     return Scene(model=m, robot=robot, actor_cfgs=actor_cfgs, actor_names=[a.name for a in actor_cfgs],
                  robot_actor=ra, body_names=body_names, body_offset=body_offset, free_actor=free_actor,
-                 root_state0=root0, dof_state0=dof0, contact_slot=contact_slot, ndof=ndof, nu=int(m.nu))
+                 root_state0=root0, dof_state0=dof0, contact_slot=contact_slot, ndof=ndof, nu=int(m.nu), virtual_dofs=nvirt)
 
 
 def make_params(mppi_cfg, sim_cfg, nu: int, K_local: int, obs_items: Sequence[tuple]) -> MppibParams:

@@ -378,6 +378,7 @@ class RobotModel:
     link_R: np.ndarray      # (nl,3,3) link frame in owning-body frame
     link_p: np.ndarray      # (nl,3)
     link_collisions: List[List[dict]] = field(default_factory=list)  # per link, primitives in link frame
+    planar_base: bool = False   # bodies 0,1,2 are virtual joints (world x, world y, yaw) of a floating base reduced to the plane
 
     @property
     def nb(self) -> int:
@@ -483,9 +484,17 @@ def compile_urdf(urdf_path: str, fixed_base: bool = True, density: float = DEFAU
             else:
                 raise NotImplementedError(f"joint type {j.jtype} ({j.name}) not supported")
 
-    if not fixed_base:
-        raise NotImplementedError("floating-base robots are not supported by this compiler yet")
-    add_link(root, -1, np.eye(3), np.zeros(3))
+    if fixed_base:
+        add_link(root, -1, np.eye(3), np.zeros(3))
+    else:
+        # floating base reduced to the plane: three virtual joints (world x, world y, yaw) carry the root link
+        Ax, Ay = axis_to_z_rotation(np.array([1.0, 0, 0])), axis_to_z_rotation(np.array([0, 1.0, 0]))
+        for name, jt, Rt, par in (("__base_x", 1, Ax, -1), ("__base_y", 1, Ax.T @ Ay, 0), ("__base_yaw", 0, Ay.T, 1)):
+            body["parent"].append(par); body["jtype"].append(jt); body["tree_R"].append(_snap(Rt)); body["tree_p"].append(np.zeros(3))
+            body["q_lo"].append(-1e30); body["q_hi"].append(1e30); body["qd_max"].append(1e30); body["effort"].append(1e30); body["damping"].append(0.0)
+            dof_names.append(name)
+            acc_m.append(0.0); acc_h.append(np.zeros(3)); acc_I.append(np.zeros((3, 3)))
+        add_link(root, 2, np.eye(3), np.zeros(3))
 
     nb = len(body["parent"])
     return RobotModel(
@@ -509,6 +518,7 @@ def compile_urdf(urdf_path: str, fixed_base: bool = True, density: float = DEFAU
         link_R=np.asarray([t[0] for t in link_T], float).reshape(-1, 3, 3),
         link_p=np.asarray([t[1] for t in link_T], float).reshape(-1, 3),
         link_collisions=link_cols,
+        planar_base=not fixed_base,
     )
 
 

@@ -18,12 +18,28 @@ import torch
 from .utils.conversions import matrix_to_euler_angles, quaternion_to_matrix, quaternion_to_yaw
 
 
+def _zyx_first_two(quat: torch.Tensor) -> torch.Tensor:
+    """|euler_ZYX(R(q))[:, 0:2]| for a (N,4) quaternion handed REAL-FIRST to the matrix formula (so the xyzw tensor of
+    the simulator is read as w=x, x=y, y=z, z=w: the reference's literal arithmetic, Appendix A #11).  Only the three
+    matrix entries the two angles need are formed -- same numbers as
+    ``matrix_to_euler_angles(quaternion_to_matrix(q), "ZYX")[:, 0:2]`` with a fraction of the element-wise kernels."""
+    r, i, j, k = quat[:, 0], quat[:, 1], quat[:, 2], quat[:, 3]
+    two_s = 2.0 / (quat * quat).sum(-1)
+    m00 = 1 - two_s * (j * j + k * k)
+    m10 = two_s * (i * j + k * r)
+    m20 = two_s * (i * k - j * r)
+    yaw = torch.atan2(m10, m00)
+    pitch = torch.asin(-m20)
+    return torch.sqrt(yaw * yaw + pitch * pitch)
+
+
 class PandaReachObjective:
     """w_goal * |p_ee - p_goal| + w_ori * |euler_ZYX(R(q_ee))[:2]| for the stick tip."""
 
-    def __init__(self, cfg=None, actor: str = "panda", link: str = "panda_ee_tip", goal: str = "goal"):
+    def __init__(self, cfg=None, actor: str = "panda", link: str = "panda_ee_tip", goal: str = "goal", literal: bool = False):
         self.weights = {"robot_to_goal": 1.0, "robot_ori": 0.5}
         self.actor, self.link, self.goal = actor, link, goal
+        self.literal = literal          # True: the reference's op-by-op formulation (full 3x3 matrix, stack, norm)
 
     def reset(self):
         pass
@@ -32,9 +48,12 @@ class PandaReachObjective:
         ee = sim.get_actor_link_by_name(self.actor, self.link)
         goal = sim.get_actor_position_by_name(self.goal)
         dist = torch.linalg.norm(ee[:, 0:3] - goal[:, 0:3], axis=1)
-        # the reference hands the xyzw quaternion to a real-first API; reproduced literally (Appendix A #11)
-        zyx = matrix_to_euler_angles(quaternion_to_matrix(ee[:, 3:7]), "ZYX")[:, 0:2]
-        ori = torch.linalg.norm(zyx, axis=1)
+        if self.literal:
+            # the reference hands the xyzw quaternion to a real-first API; reproduced literally (Appendix A #11)
+            zyx = matrix_to_euler_angles(quaternion_to_matrix(ee[:, 3:7]), "ZYX")[:, 0:2]
+            ori = torch.linalg.norm(zyx, axis=1)
+        else:
+            ori = _zyx_first_two(ee[:, 3:7])
         return self.weights["robot_to_goal"] * dist + self.weights["robot_ori"] * ori
 
 
@@ -115,8 +134,7 @@ class PandaPickObjective:
         f_table = sim.get_actor_contact_forces_by_name(self.table, "box")
         r2b = torch.linalg.norm(ee[:, 0:3] - blk[:, 0:3], axis=1)
         b2g = torch.linalg.norm(blk[:, 0:3] - goal[:, 0:3], axis=1)
-        zyx = matrix_to_euler_angles(quaternion_to_matrix(ee[:, 3:7]), "ZYX")[:, 0:2]
         forces = torch.sum(torch.abs(f_table[:, 0:3]), axis=1)
         w = self.weights
         self.prev_block_to_goal_dist = b2g
-        return w["robot_to_block"] * r2b + w["block_to_goal"] * b2g + w["collision"] * forces + w["robot_ori"] * torch.linalg.norm(zyx, axis=1)
+        return w["robot_to_block"] * r2b + w["block_to_goal"] * b2g + w["collision"] * forces + w["robot_ori"] * _zyx_first_two(ee[:, 3:7])

@@ -231,6 +231,8 @@ class RolloutSim:
         actor_idx = int(actor_idx)
         if actor_idx in self.scene.free_actor:
             return self._rows(OBS_FREE_STATE, self.scene.free_actor[actor_idx], 13)
+        if actor_idx == self.scene.robot_actor and self.scene.virtual_dofs:
+            return self._rows(OBS_LINK_STATE, 0, 13)          # planar (differential-drive) base: the root link moves
         return self._root0[actor_idx].unsqueeze(0).expand(self._n(), 13)
 
     def get_actor_position_by_actor_index(self, actor_idx: int):
@@ -291,8 +293,9 @@ class RolloutSim:
 
     @property
     def _dof_state(self):
-        """(N, 2*ndof) interleaved q0,qd0,q1,qd1,... (isaacgym_wrapper.py:190-192)."""
-        return self._rows(OBS_DOF_STATE, 0, 2 * self.scene.ndof)
+        """(N, 2*ndof) interleaved q0,qd0,q1,qd1,... (isaacgym_wrapper.py:190-192); the virtual joints of a planar base
+        are not DOFs of the reference's robot and are left out."""
+        return self._rows(OBS_DOF_STATE, 0, 2 * self.scene.ndof)[:, 2 * self.scene.virtual_dofs:]
 
     @property
     def _root_state(self):
@@ -377,6 +380,19 @@ class RolloutSim:
     def _sync_base_pose_from(self, row):
         row = row.numpy() if hasattr(row, "numpy") else row
         m = self.scene.model
+        if self.scene.virtual_dofs:
+            # planar base: the pose is STATE (virtual joints), only the height of the plane is a kernel constant
+            x, y, yaw, vx, vy, wz = self._base_from_root(row)
+            nd = self.scene.ndof
+            vals = torch.tensor([x, y, yaw, vx, vy, wz], dtype=torch.float32)
+            self._stage[0:3] = vals[0:3]; self._stage[nd:nd + 3] = vals[3:6]
+            self._state0[0:3].copy_(vals[0:3].to(self.device)); self._state0[nd:nd + 3].copy_(vals[3:6].to(self.device))
+            self._state_stale = True
+            if m.base_pos[2] != float(row[2]):
+                m.base_pos[2] = float(row[2])
+                self._backend.set_model(m)
+                return True
+            return False
         changed = False
         for i in range(3):
             if m.base_pos[i] != float(row[i]):
@@ -388,10 +404,28 @@ class RolloutSim:
             self._backend.set_model(m)
         return changed
 
+    def _base_from_root(self, root_row):
+        """(x, y, yaw, vx, vy, wz) of a planar base from a 13-float root state (host tensor / array)."""
+        r = [float(v) for v in root_row]
+        yaw = math.atan2(2 * (r[6] * r[5] + r[3] * r[4]), 1 - 2 * (r[4] * r[4] + r[5] * r[5]))
+        return r[0], r[1], yaw, r[7], r[8], r[12]
+
     def set_actor_dof_state(self, state):
-        """(K, 2*ndof) or (2*ndof,) interleaved DOF state -> per-rollout simulator state."""
+        """(K, 2*ndof) or (2*ndof,) interleaved DOF state -> per-rollout simulator state (real DOFs; a planar base keeps its pose)."""
         state = torch.as_tensor(state, dtype=torch.float32, device=self.device)
-        nd = self.scene.ndof
+        nd, nv = self.scene.ndof, self.scene.virtual_dofs
+        if nv:
+            nr = nd - nv
+            if not (state.dim() == 1 or state.shape[0] == 1):
+                raise NotImplementedError("per-rollout DOF states are not supported for planar-base robots")
+            row = state.reshape(-1)
+            self._state0[nv:nd].copy_(row[0:2 * nr:2])
+            self._state0[nd + nv:2 * nd].copy_(row[1:2 * nr:2])
+            self._state_is_broadcast = True
+            self._state_stale = True
+            self._have_obs = False
+            self._t = 0
+            return
         if state.dim() == 1 or state.shape[0] == 1:
             row = state.reshape(-1)
             self._state0.copy_(torch.cat([row[0:2 * nd:2], row[1:2 * nd:2]]))   # in place: the pointer is baked into CUDA graphs
@@ -475,9 +509,18 @@ class RolloutSim:
         for actor in self.env_cfg:
             if actor.type != "robot":
                 continue
-            n = self.scene.ndof
+            n = self.scene.ndof - self.scene.virtual_dofs
             if actor.differential_drive:
-                raise NotImplementedError("differential-drive robots are not supported on this path yet")
+                # (x, y, yaw) + remaining joints; the wheel DOFs sit at the back and start at rest (isaacgym_wrapper.py:588-604)
+                nw = int(actor.wheel_count)
+                n_q = n - (nw - 3)
+                actor_q, actor_qdot = list(q[q_idx:q_idx + n_q]), list(qdot[q_idx:q_idx + n_q])
+                self.set_state_tensor_by_pos_vel(actor.handle, actor_q[:3], actor_qdot[:3])
+                actor_q, actor_qdot = actor_q[3:] + [0.0] * nw, actor_qdot[3:] + [0.0] * nw
+                for _q, _qdot in zip(actor_q, actor_qdot):
+                    dof_state += [float(_q), float(_qdot)]
+                q_idx += n_q
+                continue
             actor_q, actor_qdot = q[q_idx:q_idx + n], qdot[q_idx:q_idx + n]
             for _q, _qdot in zip(actor_q, actor_qdot):
                 dof_state += [float(_q), float(_qdot)]
@@ -497,9 +540,14 @@ class RolloutSim:
             self.set_actor_dof_state(dof.to(self.device, dtype=torch.float32))
             return self.sync_base_pose()
         st = self._stage
-        st[:nd] = dof[0:2 * nd:2]
-        st[nd:2 * nd] = dof[1:2 * nd:2]
+        nv = self.scene.virtual_dofs
+        nr = nd - nv
+        st[nv:nd] = dof[0:2 * nr:2]
+        st[nd + nv:2 * nd] = dof[1:2 * nr:2]
         st[2 * nd:] = root.reshape(-1)
+        if nv:
+            x, y, yaw, vx, vy, wz = self._base_from_root(root[self.scene.robot_actor])
+            st[0], st[1], st[2], st[nd], st[nd + 1], st[nd + 2] = x, y, yaw, vx, vy, wz
         self._world.copy_(st, non_blocking=True)
         self._state_is_broadcast = True
         self._state_stale = True
@@ -528,7 +576,8 @@ class RolloutSim:
         yaw = float(pos[2])
         self._root0[handle, 0:2] = self._as_row(pos[:2], 2)
         self._root0[handle, 3:7] = torch.tensor([0.0, 0.0, math.sin(yaw / 2), math.cos(yaw / 2)], device=self.device)
-        self._root0[handle, 7:10] = self._as_row(vel, 3)
+        self._root0[handle, 7:9] = self._as_row(vel[:2], 2)
+        self._root0[handle, 12] = float(vel[2])               # yaw rate (the reference writes vel into the linear slots, :693)
         self._root_changed(int(handle))
 
     def update_root_state_tensor_by_obstacles(self, obstacles):

@@ -542,6 +542,13 @@ void rollout_one(const MppibModel* m, const MppibParams* p, int K, int k, S* q, 
         }
         // step (isaacgym_wrapper.py:639-641): `substeps` solver substeps of h = dt/substeps
         for (int s = 0; s < (nsteps > 0 ? p->substeps : 0); ++s) {
+            if (m->planar_base) {
+                // differential drive reduced to a planar base: body twist (v, omega) -> world-frame velocity targets of the
+                // three virtual joints; the forward axis turns with the current yaw (no lateral slip by construction)
+                const S v = (S)p->u_scale * (S)actions[((size_t)t * nu + 0) * K + k], w = (S)p->u_scale * (S)actions[((size_t)t * nu + 1) * K + k];
+                const S cy = std::cos(q[2]), sy = std::sin(q[2]), fx = (S)m->fwd_axis[0], fy = (S)m->fwd_axis[1];
+                target[0] = v * (fx * cy - fy * sy); target[1] = v * (fx * sy + fy * cy); target[2] = w;
+            }
             art.kinematics(q, qd);
             S tau[MPPIB_MAX_BODIES], dimp[MPPIB_MAX_BODIES], qdd[MPPIB_MAX_BODIES];
             for (int i = 0; i < nb; ++i) {

@@ -110,6 +110,35 @@ def pick_cfg(K=32, T=9, device="cpu", **mppi_kw):
     return cfg
 
 
+def boxer_cfg(K=64, T=12, device="cpu", **mppi_kw):
+    """BASELINE config C3 (boxer_push: differential-drive base reduced to the plane) at a test-sized K / T."""
+    cfg = copy.deepcopy(load_isaacgym_config("config_boxer_push_b200"))
+    cfg.mppi.num_samples, cfg.mppi.horizon, cfg.mppi.device = K, T, device
+    for k, v in mppi_kw.items():
+        setattr(cfg.mppi, k, v)
+    return cfg
+
+
+def boxer_setup(K=32, T=10, noise=True):
+    actors = load_actor_cfgs(["boxer", "block", "paper_obst1", "paper_obst2", "goal"])
+    actors[0].init_pos = [0.0, 2.5, 0.05]
+    actors[1].init_pos = [0.0, 1.75, 0.1]                  # block right in front of the chassis (the base drives along -y)
+    if not noise:
+        for a in actors:
+            a.noise_sigma_size, a.noise_percentage_mass, a.noise_percentage_friction = None, 0.0, 0.0
+    sim = IsaacGymConfig(dt=0.05, substeps=2)
+    sc = build_scene(actors, substep=0.025)
+    rn = sc.robot.link_names
+    obs = [(OBS_LINK_STATE, rn.index("ee_link")), (OBS_LINK_STATE, 0), (OBS_DOF_STATE, 0), (OBS_FREE_STATE, 0),
+           (OBS_CONTACT, sc.contact_slot[sc.body_offset[2]])]
+    mc = MPPIConfig(num_samples=K, horizon=T, mppi_mode="simple", sampling_method="random", noise_sigma=[[2.0, 0], [0, 8.0]],
+                    u_min=[-1.2, -3.5], u_max=[1.2, 3.5], lambda_=0.01, sample_null_action=True)
+    p = make_params(mc, sim, sc.nu, K, obs)
+    dof0 = sc.dof_state0
+    state0 = np.concatenate([dof0[0::2], dof0[1::2]]).astype(np.float32)
+    return sc, p, state0
+
+
 def point_cfg(K=128, T=12, device="cpu", **mppi_kw):
     cfg = copy.deepcopy(load_isaacgym_config("config_point_robot_b200"))
     cfg.mppi.num_samples, cfg.mppi.horizon, cfg.mppi.device = K, T, device

@@ -13,7 +13,7 @@ import pytest
 import torch
 
 from mppi_isaac_b200.model.blob import MODE_SIMPLE, OBS_DOF_STATE, OBS_LINK_STATE
-from scenes import gripper_setup, panda_cfg, panda_setup, pick_cfg, point_cfg, point_setup, push_cfg, push_setup
+from scenes import boxer_cfg, boxer_setup, gripper_setup, panda_cfg, panda_setup, pick_cfg, point_cfg, point_setup, push_cfg, push_setup
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -330,3 +330,42 @@ def test_contact_plan_through_planner_api(task):
     blk = "block" if task == "push" else "panda_pick_block"
     zg, zc = gpu.sim.get_actor_position_by_name(blk)[:, 2], cpu.sim.get_actor_position_by_name(blk)[:, 2]
     assert abs(float(zg.mean()) - float(zc.mean())) <= 5e-3
+
+
+def test_boxer_planar_base_rollout_parity(oracle):
+    """Config C3 geometry: differential-drive planar base + block + obstacles, lock-step against the oracle."""
+    K, T = 64, 10
+    sc, p, s0 = boxer_setup(K=K, T=T)
+    be = gpu_backend(sc, p)
+    rng = np.random.default_rng(0)
+    actions = np.stack([rng.uniform(0.3, 1.2, (T, K)), rng.uniform(-1.0, 1.0, (T, K))], axis=1).astype(np.float32)
+    a_d, root_d = dev(actions), dev(sc.root_state0)
+    NS = be.state_size()
+    state_ref = np.zeros((NS, K), np.float32)
+    state_ref[:10] = s0[:, None]
+    state_ref[10:] = sc.root_state0[1][:, None]
+    obs = torch.zeros((be.obs_size(), T, K), device=DEV)
+    worst, moved = 0.0, 0.0
+    for t in range(T):
+        st = dev(state_ref)
+        be.rollout(None, st, a_d, t, 1, obs, root0=root_d)
+        state_ref, _ = oracle.rollout(sc.model, p, None, actions, t, 1, state=state_ref.copy(), root0=sc.root_state0)
+        g = st.cpu().numpy()
+        worst = max(worst, float(np.abs(g[[0, 1, 2, 10, 11, 12]] - state_ref[[0, 1, 2, 10, 11, 12]]).max()))
+        assert np.abs(g[5:10] - state_ref[5:10]).max() <= 5e-3                # joint velocities incl. the wheels
+        moved = max(moved, float(np.abs(state_ref[11] - 1.75).max()))
+    assert worst <= 1e-4 and moved > 0.05                                     # base / block positions to 1e-4; the block really gets pushed
+
+
+def test_boxer_plan_through_planner_api():
+    from mppi_isaac_b200 import MPPIisaacPlanner
+    from mppi_isaac_b200.objectives import PushObjective
+    from oracle.backend import OracleBackend
+    gpu = MPPIisaacPlanner(boxer_cfg(K=512, T=12, device=DEV), PushObjective(robot="boxer", link="ee_link"))
+    cpu = MPPIisaacPlanner(boxer_cfg(K=512, T=12, device="cpu"), PushObjective(robot="boxer", link="ee_link"), backend=OracleBackend(nthreads=8))
+    q = [0.0, 2.5, 0.0]
+    ag, ac = gpu.compute_action(q, [0.0] * 3), cpu.compute_action(q, [0.0] * 3)
+    assert torch.isfinite(ag).all() and float((ag - ac).abs().max()) <= 2e-2 * 3.5
+    for _ in range(2):
+        gpu.compute_action(q, [0.0] * 3)
+    assert gpu.mppi._graph is not None

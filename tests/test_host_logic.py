@@ -12,7 +12,7 @@ from mppi_isaac_b200.utils.config_store import IsaacGymConfig
 from mppi_isaac_b200.utils.conversions import matrix_to_euler_angles, quaternion_to_matrix, quaternion_to_yaw
 from mppi_isaac_b200.utils.transport import bytes_to_torch, torch_to_bytes
 from oracle.backend import OracleBackend
-from scenes import panda_cfg, pick_cfg, point_cfg, push_cfg
+from scenes import boxer_cfg, panda_cfg, pick_cfg, point_cfg, push_cfg
 
 Q0 = [0.0, -0.94, 0.0, -2.8, 0.0, 1.8675, 0.0]
 
@@ -214,3 +214,52 @@ def test_panda_pick_c5_scene_and_cost():
     assert blk.shape == (144, 3)
     assert float(blk[-16:, 2].min()) > 0.14 - 0.02 + 0.02 - 0.01                       # the cube fell onto the table (top at 0.14), not through it
     assert s.get_actor_contact_forces_by_name("table", "box").shape == (144, 3)
+
+
+def test_streamlined_orientation_cost_equals_the_literal_formulation():
+    """PandaReachObjective's default arithmetic (3 matrix entries) == the reference's op-by-op version (full matrix)."""
+    a = make(panda_cfg(K=64, T=12), PandaReachObjective())
+    a.compute_action(Q0, [0] * 7)
+    fast = a.objective.compute_cost(a.sim)
+    a.objective.literal = True
+    lit = a.objective.compute_cost(a.sim)
+    np.testing.assert_allclose(fast.numpy(), lit.numpy(), rtol=0, atol=2e-6)
+    q = torch.nn.functional.normalize(torch.randn(500, 4, dtype=torch.float64), dim=1)
+    from mppi_isaac_b200.objectives import _zyx_first_two
+    ref = torch.linalg.norm(matrix_to_euler_angles(quaternion_to_matrix(q), "ZYX")[:, 0:2], axis=1)
+    np.testing.assert_allclose(_zyx_first_two(q).numpy(), ref.numpy(), atol=1e-12)
+
+
+def test_boxer_push_c3_planar_differential_drive():
+    """BASELINE config C3: floating differential-drive base (reduced to the plane), 2 wheel DOFs, (v, omega) command."""
+    p = make(boxer_cfg(K=32, T=12), PushObjective(robot="boxer", link="ee_link"), observe="all")
+    s = p.sim
+    assert s.scene.num_bodies == 12 and s.scene.nu == 2 and s.scene.virtual_dofs == 3              # SURVEY section 8 table, C3
+    a = p.compute_action([0.0, 2.5, 0.0], [0.0, 0.0, 0.0])
+    assert a.shape == (2,) and torch.isfinite(a).all()
+    assert s._dof_state.shape == (32 * 12, 4)                                                       # only the wheel DOFs are DOFs
+    # diff-drive kinematics: u = (v, 0) for 0.5 s moves the base along its forward axis (-y of the root link) by ~v t
+    s.begin_step_mode()
+    u = torch.zeros(32, 2); u[:, 0] = 0.8
+    for _ in range(10):
+        p.dynamics(None, u)
+    pos = s.get_actor_position_by_name("boxer")[0].numpy()
+    assert abs(pos[0]) < 1e-3 and abs((2.5 - pos[1]) - 0.8 * 0.5) < 0.06
+    wheels = s._dof_state[0].numpy()
+    np.testing.assert_allclose(wheels[[1, 3]], 0.8 / 0.08, rtol=0.02)                               # both wheels v / r (isaacgym_wrapper.py:510-522)
+    u[:, 0], u[:, 1] = 0.0, 1.0
+    for _ in range(10):
+        p.dynamics(None, u)
+    quat = s.get_actor_orientation_by_name("boxer")[0:1]
+    assert abs(abs(float(quaternion_to_yaw(quat)[0])) - 0.5) < 0.03                                 # yaw = omega t
+    w = s._dof_state[0].numpy()[[1, 3]]
+    np.testing.assert_allclose(w, [0.494 / (2 * 0.08), -0.494 / (2 * 0.08)], rtol=0.03)             # right +, left - for a left turn
+    # world-state round trip: the base pose arrives in the root state, the wheels in the DOF state
+    dof = torch.zeros(1, 4)
+    root = torch.from_numpy(s.scene.root_state0.copy()).unsqueeze(0)
+    root[0, 0, 0:3] = torch.tensor([0.3, 2.0, 0.05]); root[0, 0, 3:7] = torch.tensor([0.0, 0.0, np.sin(0.35), np.cos(0.35)])
+    p.reset_rollout_sim(torch_to_bytes(dof), torch_to_bytes(root))
+    np.testing.assert_allclose(s._state0[:3].numpy(), [0.3, 2.0, 0.7], atol=1e-6)
+    out = bytes_to_torch(p.command())
+    assert out.shape == (2,)
+    np.testing.assert_allclose(s.get_actor_position_by_name("boxer")[:32, 0:2].numpy(), [[0.3, 2.0]] * 32, atol=0.08)

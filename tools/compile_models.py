@@ -19,6 +19,7 @@ ROBOTS = [
     "panda_isaac/robots/franka_panda_stick.urdf",
     "panda_isaac/robots/franka_panda_gripper.urdf",
 ]
+FLOATING = ["boxer/boxer.urdf"]          # differential-drive bases: compiled with the planar virtual-joint root
 
 
 def main():
@@ -28,6 +29,11 @@ def main():
         out = compiled_path(rel)
         save_compiled(model, out)
         print(f"{rel}: nb={model.nb} links={model.nlinks} -> {os.path.relpath(out)}")
+    for rel in FLOATING:
+        model = compile_urdf(os.path.join(assets, "urdf", rel), fixed_base=False, root_mass_override=1.0)   # ActorWrapper.mass default
+        out = compiled_path(rel)
+        save_compiled(model, out)
+        print(f"{rel}: nb={model.nb} links={model.nlinks} planar base -> {os.path.relpath(out)}")
 
 
 if __name__ == "__main__":
