@@ -15,7 +15,7 @@ import torch
 
 from .model.blob import ABI_VERSION, MppibModel, MppibParams
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmppib.so")
+_LIB_PATH = os.environ.get("MPPIB_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmppib.so")   # MPPIB_LIB: tuning builds
 _lib = None
 
 SYMBOLS = [

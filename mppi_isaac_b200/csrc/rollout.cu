@@ -30,6 +30,20 @@
 // After the last substep of a model step the observed rows are written to obs[R][T][K].
 #include "common.cuh"
 
+// tuning knobs (profiles/r1_rollout_tuning.md records what each one bought)
+#ifndef ROLL_UNROLL_S1
+#define ROLL_UNROLL_S1 1      // unroll factor of sweep 1 (kinematics / inertia: bodies are independent apart from the frame recursion)
+#endif
+#ifndef ROLL_UNROLL_S3
+#define ROLL_UNROLL_S3 1      // unroll factor of sweep 3 (accelerations)
+#endif
+#ifndef ROLL_FAST_SINCOS
+#define ROLL_FAST_SINCOS 0    // 1: __sincosf (2^-21 abs error) instead of sincosf
+#endif
+#define MPPIB_STR2(x) #x
+#define MPPIB_STR(x) MPPIB_STR2(x)
+#define MPPIB_UNROLL(n) _Pragma(MPPIB_STR(unroll n))
+
 namespace {
 
 struct V3 { float x, y, z; };
@@ -168,7 +182,12 @@ __device__ __forceinline__ void body_kinematics(const MppibModel& m, int i, floa
     V3 oi = par.o + mul(par.R, mk(m.tree_p[i][0], m.tree_p[i][1], m.tree_p[i][2]));
     const V3 axis = mk(Rt.m02, Rt.m12, Rt.m22);
     if (m.jtype[i] == MPPIB_JOINT_REVOLUTE) {
-        float sq, cq; sincosf(q, &sq, &cq);
+        float sq, cq;
+#if ROLL_FAST_SINCOS
+        __sincosf(q, &sq, &cq);
+#else
+        sincosf(q, &sq, &cq);
+#endif
         out.R = Rt;   // Rt * Rz(q)
         out.R.m00 = Rt.m00 * cq + Rt.m01 * sq; out.R.m01 = Rt.m01 * cq - Rt.m00 * sq;
         out.R.m10 = Rt.m10 * cq + Rt.m11 * sq; out.R.m11 = Rt.m11 * cq - Rt.m10 * sq;
@@ -241,7 +260,7 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
             // ------------------------------------------------------------------ sweep 1: root -> leaves
             {
                 Frame par = base;
-#pragma unroll 1
+                MPPIB_UNROLL(ROLL_UNROLL_S1)
                 for (int i = 0; i < nb; ++i) {
                     if (!CHAIN) {
                         const int pi = m.parent[i];
@@ -346,7 +365,7 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
                 // -------------------------------------------------------------- sweep 3: root -> leaves
                 V6 ap = a0;
                 bool any = false;
-#pragma unroll 1
+                MPPIB_UNROLL(ROLL_UNROLL_S3)
                 for (int i = 0; i < nb; ++i) {
                     if (!CHAIN) { const int pi = m.parent[i]; ap = pi >= 0 ? ld6(sm, pi * NSLOT + F_ACC, lane) : a0; }
                     const V6 S = ld6(sm, i * NSLOT + F_S, lane), c = ld6(sm, i * NSLOT + F_C, lane), U = ld6(sm, i * NSLOT + F_U, lane);
