@@ -344,7 +344,25 @@ def run_gpu_arm(args, rank, world, local_rank):
                                     "plan_hz_at_K10000_est": 1.0 / (dt * K_PER_GPU / k_s)}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        shutdown_distributed(planner)
+
+
+def shutdown_distributed(planner):
+    """Tear NCCL down without hanging: a live CUDA graph that holds NCCL kernels blocks destroy_process_group(), so the
+    captured plan is released first; a watchdog force-exits if the teardown still does not return."""
+    import gc
+    import torch.distributed as dist
+    planner.mppi.invalidate_graph()
+    del planner
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    timer = threading.Timer(20.0, lambda: os._exit(0))
+    timer.daemon = True
+    timer.start()
+    dist.destroy_process_group()
+    timer.cancel()
 
 
 def main():

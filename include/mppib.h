@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MPPIB_ABI_VERSION 5
+#define MPPIB_ABI_VERSION 6
 
 #define MPPIB_MAX_BODIES 16   /* moving (1-DoF) bodies of the articulation            */
 #define MPPIB_MAX_LINKS  32   /* URDF links whose state can be observed               */
@@ -214,6 +214,17 @@ int32_t mppib_obs_size(MppibHandle h);     /* R: rows of the obs buffer         
 int32_t mppib_sample(MppibHandle h, uint64_t seed, uint64_t plan_idx, const uint32_t* plan_ctr,
                      uint32_t k_offset, uint32_t k_total, const float* U, const float* prior_row,
                      float* actions, float* noise, void* stream);
+
+/* Halton-spline noise library (mppi_torch `sampling_method: halton` / `mppi_mode: halton-spline`, conf/mppi/panda.yaml:4-5;
+ * SURVEY.md 8(a) M4, 8(f) N3): Gaussian knots from a scrambled Halton sequence (dimension n*nu + i, bases / digit multipliers
+ * in halton_tab[2][n_knots*nu], index = global sample + 1), z = sqrt(2) erfinv(2u - 1), interpolated to T points by the fixed
+ * spline operator B[T][n_knots], coloured by the Cholesky factor of Sigma:  Z[t][j][k] = sum_n B[t][n] sum_i L[j][i] z[n][i].
+ * Drawn ONCE per planner; global row k_total-1 is the zero-noise sample.                                                   */
+int32_t mppib_noise_library(MppibHandle h, uint32_t k_offset, uint32_t k_total, const int32_t* halton_tab,
+                            const float* B, int32_t n_knots, float* Z, void* stream);
+/* K1 (library variant): action = clamp(U + Z), null / prior rows, noise = action - U.                                      */
+int32_t mppib_sample_library(MppibHandle h, uint32_t k_offset, uint32_t k_total, const float* U, const float* prior_row,
+                             const float* Z, float* actions, float* noise, void* stream);
 
 /* K2: broadcast initial state state0[2*ndof] (+ free bodies from root0) to all K rollouts, or continue
  * from state[NS][K] when state0 == NULL; root0[nactors][13] holds the world's actor root states (poses of

@@ -21,7 +21,7 @@ _lib = None
 SYMBOLS = [
     "mppib_abi_version", "mppib_last_error", "mppib_create", "mppib_destroy", "mppib_set_params",
     "mppib_set_model", "mppib_state_size", "mppib_obs_size", "mppib_sample", "mppib_rollout",
-    "mppib_reduce", "mppib_finalize", "mppib_shift",
+    "mppib_reduce", "mppib_finalize", "mppib_shift", "mppib_noise_library", "mppib_sample_library",
 ]
 
 
@@ -117,6 +117,16 @@ class CudaBackend:
         self.launches += 1
         self._check(self.lib.mppib_sample(self.handle, C.c_uint64(seed), C.c_uint64(plan_idx), _ptr(plan_ctr), C.c_uint32(k_offset), C.c_uint32(k_total),
                                           _ptr(U), _ptr(prior_row), _ptr(actions), _ptr(noise), self._stream()), "mppib_sample")
+
+    def noise_library(self, k_offset, k_total, halton_tab, B, n_knots, Z):
+        self.launches += 1
+        self._check(self.lib.mppib_noise_library(self.handle, C.c_uint32(k_offset), C.c_uint32(k_total), _ptr(halton_tab), _ptr(B), C.c_int32(n_knots),
+                                                 _ptr(Z), self._stream()), "mppib_noise_library")
+
+    def sample_library(self, k_offset, k_total, U, prior_row, Z, actions, noise):
+        self.launches += 1
+        self._check(self.lib.mppib_sample_library(self.handle, C.c_uint32(k_offset), C.c_uint32(k_total), _ptr(U), _ptr(prior_row), _ptr(Z),
+                                                  _ptr(actions), _ptr(noise), self._stream()), "mppib_sample_library")
 
     def rollout(self, state0, state, actions, t0, nsteps, obs, act_t0=0, root0=None):
         """``actions`` holds time slices [act_t0, ...) laid out [t][nu][K]; steps t0..t0+nsteps-1 are executed."""

@@ -132,6 +132,20 @@ int32_t mppib_sample(MppibHandle h, uint64_t seed, uint64_t plan_idx, const uint
     return launch_sample(h, seed, plan_idx, plan_ctr, k_offset, k_total, U, prior_row, actions, noise, (cudaStream_t)stream);
 }
 
+int32_t mppib_noise_library(MppibHandle h, uint32_t k_offset, uint32_t k_total, const int32_t* halton_tab, const float* B, int32_t n_knots,
+                            float* Z, void* stream) {
+    MPPIB_REQUIRE(h && halton_tab && B && Z, "mppib_noise_library: null argument");
+    MPPIB_REQUIRE((uint64_t)k_offset + (uint64_t)h->params.K <= (uint64_t)k_total, "mppib_noise_library: shard exceeds k_total");
+    return launch_noise_library(h, k_offset, k_total, halton_tab, B, n_knots, Z, (cudaStream_t)stream);
+}
+
+int32_t mppib_sample_library(MppibHandle h, uint32_t k_offset, uint32_t k_total, const float* U, const float* prior_row, const float* Z,
+                             float* actions, float* noise, void* stream) {
+    MPPIB_REQUIRE(h && U && Z && actions, "mppib_sample_library: null argument");
+    MPPIB_REQUIRE((uint64_t)k_offset + (uint64_t)h->params.K <= (uint64_t)k_total, "mppib_sample_library: shard exceeds k_total");
+    return launch_sample_library(h, k_offset, k_total, U, prior_row, Z, actions, noise, (cudaStream_t)stream);
+}
+
 int32_t mppib_rollout(MppibHandle h, const float* state0, const float* root0, float* state, const float* actions, int32_t t0, int32_t nsteps,
                       float* obs, void* stream) {
     MPPIB_REQUIRE(h && actions, "mppib_rollout: null argument");

@@ -72,7 +72,92 @@ mppib_sample_kernel(const __grid_constant__ MppibParams p, int nu, uint32_t key0
     }
 }
 
+// generalised Halton: radical inverse of `index` in base b with multiplicative digit scrambling (digit -> mult * digit mod b)
+__device__ __forceinline__ float halton(uint32_t index, uint32_t base, uint32_t mult) {
+    const float inv_b = 1.0f / (float)base;
+    float f = inv_b, r = 0.f;
+    while (index > 0u) {
+        const uint32_t digit = index % base;
+        r += (float)((digit * mult) % base) * f;
+        index /= base;
+        f *= inv_b;
+    }
+    return r;
+}
+
+constexpr int MAX_KNOTS = 32;
+
+// one thread per sample k: Gaussian knots (n_knots x nu) -> coloured -> spline-interpolated to T points
+__global__ void __launch_bounds__(128)
+mppib_noise_library_kernel(const __grid_constant__ MppibParams p, int nu, uint32_t k_offset, uint32_t k_total,
+                           const int32_t* __restrict__ tab, const float* __restrict__ B, int n_knots, float* __restrict__ Z) {
+    const int K = p.K, T = p.T;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const uint32_t kg = k_offset + (uint32_t)k;
+    const bool null_row = p.sample_null_action && kg == k_total - 1;
+    const int nd = n_knots * nu;
+    for (int j = 0; j < nu; ++j) {
+        // coloured knots of control dimension j:  c[n] = sum_i L[j][i] z[n][i]
+        float cn[MAX_KNOTS];
+        for (int n = 0; n < n_knots; ++n) {
+            float acc = 0.f;
+            for (int i = 0; i <= j; ++i) {
+                const int d = n * nu + i;
+                const float u = halton(kg + 1u, (uint32_t)tab[d], (uint32_t)tab[nd + d]);
+                acc += p.sigma_chol[j * nu + i] * (1.41421356237f * erfinvf(2.0f * u - 1.0f));
+            }
+            cn[n] = acc;
+        }
+        for (int t = 0; t < T; ++t) {
+            float z = 0.f;
+            for (int n = 0; n < n_knots; ++n) z += B[t * n_knots + n] * cn[n];
+            Z[((size_t)t * nu + j) * K + k] = null_row ? 0.f : z;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+mppib_sample_library_kernel(const __grid_constant__ MppibParams p, int nu, uint32_t k_offset, uint32_t k_total, const float* __restrict__ U,
+                            const float* __restrict__ prior_row, const float* __restrict__ Z, float* __restrict__ actions,
+                            float* __restrict__ noise) {
+    const int K = p.K;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+    if (k >= K) return;
+    const uint32_t kg = k_offset + (uint32_t)k;
+    const bool is_null = p.sample_null_action && kg == k_total - 1;
+    const bool is_prior = prior_row != nullptr && kg == k_total - 2;
+    for (int j = 0; j < nu; ++j) {
+        const size_t idx = ((size_t)t * nu + j) * K + k;
+        const float u = U[t * nu + j];
+        float a = u + Z[idx];
+        if (is_null) a = 0.f;
+        a = fminf(fmaxf(a, p.u_min[j]), p.u_max[j]);
+        if (is_prior) a = prior_row[t * nu + j];
+        actions[idx] = a;
+        if (noise) noise[idx] = a - u;
+    }
+}
+
 }  // namespace
+
+int launch_noise_library(MppibContext* c, uint32_t k_offset, uint32_t k_total, const int32_t* halton_tab, const float* B, int n_knots,
+                         float* Z, cudaStream_t s) {
+    MPPIB_REQUIRE(n_knots >= 1 && n_knots <= MAX_KNOTS, "mppib_noise_library: n_knots = %d out of range [1, %d]", n_knots, MAX_KNOTS);
+    const int K = c->params.K;
+    mppib_noise_library_kernel<<<(K + 127) / 128, 128, 0, s>>>(c->params, c->model.nu, k_offset, k_total, halton_tab, B, n_knots, Z);
+    MPPIB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_sample_library(MppibContext* c, uint32_t k_offset, uint32_t k_total, const float* U, const float* prior_row, const float* Z,
+                          float* actions, float* noise, cudaStream_t s) {
+    const int K = c->params.K, T = c->params.T;
+    dim3 block(128), grid((K + 127) / 128, T);
+    mppib_sample_library_kernel<<<grid, block, 0, s>>>(c->params, c->model.nu, k_offset, k_total, U, prior_row, Z, actions, noise);
+    MPPIB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int launch_sample(MppibContext* c, uint64_t seed, uint64_t plan_idx, const uint32_t* plan_ctr, uint32_t k_offset, uint32_t k_total,
                   const float* U, const float* prior_row, float* actions, float* noise, cudaStream_t s) {

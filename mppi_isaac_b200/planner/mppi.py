@@ -27,6 +27,39 @@ import torch
 from ..model.blob import MODE_SIMPLE
 
 
+def _primes(n: int):
+    out, c = [], 2
+    while len(out) < n:
+        if all(c % q for q in out if q * q <= c):
+            out.append(c)
+        c += 1
+    return out
+
+
+def halton_table(ndims: int, seed: int):
+    """[2][ndims] int32: bases (first primes) and digit multipliers of the scrambled Halton sequence (mult in [1, b-1], seeded).
+    ghalton's EA_PERMS table, which mppi_torch uses, is not available offline: multiplicative scrambling instead."""
+    import numpy as np
+    bases = np.asarray(_primes(ndims), np.int64)
+    rng = np.random.RandomState(int(seed) & 0x7FFFFFFF)
+    mult = 1 + rng.randint(0, 1 << 30, size=ndims) % np.maximum(bases - 1, 1)
+    return np.stack([bases, mult]).astype(np.int32)
+
+
+def halton_spline_operator(T: int, n_knots: int):
+    """(T, n_knots) float32 matrix of the interpolating degree-2 B-spline (FITPACK splrep s=0 / splev, as mppi_torch's bspline
+    helper): the map knots -> horizon points is linear, so it is evaluated once on the host and applied in the kernel."""
+    import numpy as np
+    from scipy import interpolate as si
+    t_arr = np.linspace(0.0, 1.0, n_knots)
+    x = np.linspace(0.0, 1.0, T)
+    B = np.zeros((T, n_knots))
+    for n in range(n_knots):
+        e = np.zeros(n_knots); e[n] = 1.0
+        B[:, n] = si.splev(x, si.splrep(t_arr, e, k=2, s=0))
+    return B.astype(np.float32)
+
+
 def shard_samples(k_total: int, rank: int, world: int):
     """Split k_total samples over `world` ranks in units of 4 (128-bit loads need K_local % 4 == 0)."""
     if k_total % 4 != 0:
@@ -65,10 +98,9 @@ class MPPIPlanner:
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(self.pg)
-        if str(cfg.sampling_method) != "random" and not getattr(MPPIPlanner, "_warned_halton", False):
-            MPPIPlanner._warned_halton = True
-            print("[mppi_isaac_b200] sampling_method 'halton' (Halton-spline) is not built yet: drawing Philox Gaussian "
-                  "noise with the same Sigma/bounds/lambda (SURVEY.md section 7, config-compat note)")
+        if str(cfg.sampling_method) not in ("random", "halton"):
+            raise ValueError(f"unknown sampling_method {cfg.sampling_method}")
+        self.use_library = str(cfg.sampling_method) == "halton"     # Halton-spline noise library, drawn once
         if getattr(cfg, "update_cov", False) or getattr(cfg, "update_lambda", False):
             raise NotImplementedError("update_cov / update_lambda are False in every shipped config and not provided")
         sim.configure(mppi_cfg=cfg, horizon=self.T)      # (re)bakes Sigma / bounds / lambda into the kernel parameter block
@@ -106,6 +138,28 @@ class MPPIPlanner:
         self._graph = None
         self._graph_failed = False
         self._plans = 0
+        if self.use_library:
+            self._build_library()
+
+    def _build_library(self):
+        """Halton-spline perturbations Z[T][nu][K]: scrambled-Halton Gaussian knots (T//4 per control, at least degree+1) interpolated
+        by a degree-2 B-spline to the T horizon points and coloured by chol(Sigma); drawn once and reused by every plan."""
+        dev, T, nu, K = self.device, self.T, self.nu, self.K
+        n_knots = max(T // 4, 3)
+        B = halton_spline_operator(T, n_knots)
+        tab = halton_table(n_knots * nu, self.seed)
+        self.n_knots = n_knots
+        self._spline_B = torch.from_numpy(B).to(dev)
+        self._halton_tab = torch.from_numpy(tab).to(dev)
+        self.Z = torch.zeros((T, nu, K), dtype=torch.float32, device=dev)
+        self.backend.noise_library(self.k_offset, self.K_total, self._halton_tab, self._spline_B, n_knots, self.Z)
+
+    def _sample(self):
+        be = self.backend
+        if self.use_library:
+            be.sample_library(self.k_offset, self.K_total, self.U, None, self.Z, self.actions, self.noise)
+        else:
+            be.sample(self.seed, 0, self.k_offset, self.K_total, self.U, None, self.actions, self.noise, self.plan_ctr)
 
     @property
     def mean_action(self):
@@ -142,7 +196,7 @@ class MPPIPlanner:
     def _plan_batched(self):
         be = self.backend
         be.shift(self.U, self.plan_ctr)
-        be.sample(self.seed, 0, self.k_offset, self.K_total, self.U, None, self.actions, self.noise, self.plan_ctr)
+        self._sample()
         self.sim.rollout_all(self.actions)
         cost = self._cost_batched()
         x = self.noise if be.params.mode == MODE_SIMPLE else self.actions
@@ -153,7 +207,7 @@ class MPPIPlanner:
     def _plan_stepwise(self, state):
         be, sim, T = self.backend, self.sim, self.T
         be.shift(self.U, self.plan_ctr)
-        be.sample(self.seed, 0, self.k_offset, self.K_total, self.U, None, self.actions, self.noise, self.plan_ctr)
+        self._sample()
         sim.begin_step_mode()
         prior_local = self.use_priors and (self.k_offset <= self.K_total - 2 < self.k_offset + self.K)
         for t in range(T):

@@ -48,6 +48,15 @@ class OracleBackend:
         if noise is not None:
             noise.copy_(torch.from_numpy(n))
 
+    def noise_library(self, k_offset, k_total, halton_tab, B, n_knots, Z):
+        Z.copy_(torch.from_numpy(orc.noise_library(self.model, self.params, _np(halton_tab), _np(B), n_knots, k_offset, k_total)))
+
+    def sample_library(self, k_offset, k_total, U, prior_row, Z, actions, noise):
+        a, n = orc.sample_library(self.model, self.params, _np(U), _np(Z), k_offset, k_total, _np(prior_row))
+        actions.copy_(torch.from_numpy(a))
+        if noise is not None:
+            noise.copy_(torch.from_numpy(n))
+
     def rollout(self, state0, state, actions, t0, nsteps, obs, act_t0=0, root0=None):
         T, K, nu = self.params.T, self.params.K, self.model.nu
         a = np.zeros((T, nu, K), np.float32)

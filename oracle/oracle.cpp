@@ -335,7 +335,9 @@ struct ContactWorld {
         S r[3], wxr[3];
         if (ref >= REF_FREE0) { const FreeBody<S>& b = fb[ref - REF_FREE0]; for (int i = 0; i < 3; ++i) r[i] = pt[i] - b.x[i]; cross3(b.w, r, wxr); for (int i = 0; i < 3; ++i) o[i] = b.v[i] + wxr[i]; }
         else {
-            for (int i = 0; i < 3; ++i) r[i] = pt[i] - art.pw[ref][i]; cross3(art.ww[ref], r, wxr); for (int i = 0; i < 3; ++i) o[i] = art.vw[ref][i] + wxr[i];
+            for (int i = 0; i < 3; ++i) r[i] = pt[i] - art.pw[ref][i];
+            cross3(art.ww[ref], r, wxr);
+            for (int i = 0; i < 3; ++i) o[i] = art.vw[ref][i] + wxr[i];
             for (int j = ref; j >= 0; j = m->parent[j]) { S J[3]; joint_jac(art, j, pt, J); for (int i = 0; i < 3; ++i) o[i] += J[i] * dqv[j]; }
         }
     }
@@ -711,6 +713,81 @@ int32_t oracle_state_size(const MppibModel* m) { return 2 * m->nb + 13 * m->nfre
 void oracle_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
     U4 r = philox4x32_10({c0, c1, c2, c3}, k0, k1);
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+// inverse of the standard normal CDF (Wichura AS241, PPND16; |rel err| < 1e-16): z = sqrt(2) erfinv(2u - 1)
+static double norm_ppf(double pu) {
+    const double q = pu - 0.5;
+    if (std::fabs(q) <= 0.425) {
+        const double r = 0.180625 - q * q;
+        return q * (((((((2.5090809287301226727e3 * r + 3.3430575583588128105e4) * r + 6.7265770927008700853e4) * r + 4.5921953931549871457e4) * r +
+                         1.3731693765509461125e4) * r + 1.9715909503065514427e3) * r + 1.3314166789178437745e2) * r + 3.3871328727963666080e0) /
+               (((((((5.2264952788528545610e3 * r + 2.8729085735721942674e4) * r + 3.9307895800092710610e4) * r + 2.1213794301586595867e4) * r +
+                    5.3941960214247511077e3) * r + 6.8718700749205790830e2) * r + 4.2313330701600911252e1) * r + 1.0);
+    }
+    double r = q < 0 ? pu : 1.0 - pu;
+    r = std::sqrt(-std::log(r));
+    double val;
+    if (r <= 5.0) {
+        r -= 1.6;
+        val = (((((((7.74545014278341407640e-4 * r + 2.27238449892691845833e-2) * r + 2.41780725177450611770e-1) * r + 1.27045825245236838258e0) * r +
+                   3.64784832476320460504e0) * r + 5.76949722146069140550e0) * r + 4.63033784615654529590e0) * r + 1.42343711074968357734e0) /
+              (((((((1.05075007164441684324e-9 * r + 5.47593808499534494600e-4) * r + 1.51986665636164571966e-2) * r + 1.48103976427480074590e-1) * r +
+                   6.89767334985100004550e-1) * r + 1.67638483018380384940e0) * r + 2.05319162663775882187e0) * r + 1.0);
+    } else {
+        r -= 5.0;
+        val = (((((((2.01033439929228813265e-7 * r + 2.71155556874348757815e-5) * r + 1.24266094738807843860e-3) * r + 2.65321895265761230930e-2) * r +
+                   2.96560571828504891230e-1) * r + 1.78482653991729133580e0) * r + 5.46378491116411436990e0) * r + 6.65790464350110377720e0) /
+              (((((((2.04426310338993978564e-15 * r + 1.42151175831644588870e-7) * r + 1.84631831751005468180e-5) * r + 7.86869131145613259100e-4) * r +
+                   1.48753612908506148525e-2) * r + 1.36929880922735805310e-1) * r + 5.99832206555887937690e-1) * r + 1.0);
+    }
+    return q < 0 ? -val : val;
+}
+
+// generalised Halton point: radical inverse of `index` in base b, digits scrambled by digit -> mult * digit mod b
+static double halton_point(uint32_t index, uint32_t base, uint32_t mult) {
+    double f = 1.0 / base, r = 0.0;
+    while (index > 0) { r += (double)((index % base) * mult % base) * f; index /= base; f /= base; }
+    return r;
+}
+double oracle_halton(uint32_t index, uint32_t base, uint32_t mult) { return halton_point(index, base, mult); }
+double oracle_norm_ppf(double u) { return norm_ppf(u); }
+
+// Halton-spline noise library restatement (mppi_torch sampling_method "halton": Gaussian knots -> spline -> scale)
+void oracle_noise_library(const MppibModel* m, const MppibParams* p, uint32_t k_offset, uint32_t k_total, const int32_t* tab,
+                          const float* B, int32_t n_knots, float* Z) {
+    const int K = p->K, T = p->T, nu = m->nu, nd = n_knots * nu;
+    std::vector<double> z((size_t)nd), cn((size_t)n_knots);
+    for (int k = 0; k < K; ++k) {
+        const uint32_t kg = k_offset + (uint32_t)k;
+        const bool null_row = p->sample_null_action && kg == k_total - 1;
+        for (int d = 0; d < nd; ++d) z[d] = norm_ppf((double)(float)halton_point(kg + 1u, (uint32_t)tab[d], (uint32_t)tab[nd + d]));
+        for (int j = 0; j < nu; ++j) {
+            for (int n = 0; n < n_knots; ++n) { double a = 0; for (int i = 0; i <= j; ++i) a += (double)p->sigma_chol[j * nu + i] * z[n * nu + i]; cn[n] = a; }
+            for (int t = 0; t < T; ++t) {
+                double v = 0; for (int n = 0; n < n_knots; ++n) v += (double)B[t * n_knots + n] * cn[n];
+                Z[((size_t)t * nu + j) * K + k] = null_row ? 0.f : (float)v;
+            }
+        }
+    }
+}
+
+void oracle_sample_library(const MppibModel* m, const MppibParams* p, uint32_t k_offset, uint32_t k_total, const float* U,
+                           const float* prior_row, const float* Z, float* actions, float* noise) {
+    const int K = p->K, T = p->T, nu = m->nu;
+    for (int k = 0; k < K; ++k) {
+        const uint32_t kg = k_offset + (uint32_t)k;
+        for (int t = 0; t < T; ++t) for (int j = 0; j < nu; ++j) {
+            const size_t idx = ((size_t)t * nu + j) * K + k;
+            const float u = U[t * nu + j];
+            float a = u + Z[idx];
+            if (p->sample_null_action && kg == k_total - 1) a = 0.f;
+            a = std::min(std::max(a, p->u_min[j]), p->u_max[j]);
+            if (prior_row && kg == k_total - 2) a = prior_row[t * nu + j];
+            actions[idx] = a;
+            if (noise) noise[idx] = a - u;
+        }
+    }
 }
 
 // K1 restatement.  All buffers are host pointers with the device layouts of include/mppib.h.

@@ -32,6 +32,8 @@ def lib():
         _LIB = C.CDLL(build())
         _LIB.oracle_obs_size.restype = C.c_int32
         _LIB.oracle_state_size.restype = C.c_int32
+        _LIB.oracle_halton.restype = C.c_double
+        _LIB.oracle_norm_ppf.restype = C.c_double
     return _LIB
 
 
@@ -58,6 +60,28 @@ def sample(model, params, seed, plan_idx, U, k_offset=0, k_total=None, prior_row
     pr = None if prior_row is None else np.ascontiguousarray(prior_row, np.float32)
     lib().oracle_sample(C.byref(model), C.byref(params), C.c_uint64(seed), C.c_uint64(plan_idx), C.c_uint32(k_offset),
                         C.c_uint32(k_total), _f(U), _f(pr), _f(actions), _f(noise), C.c_int(nthreads))
+    return actions, noise
+
+
+def noise_library(model, params, halton_tab, B, n_knots, k_offset=0, k_total=None):
+    K, T, nu = params.K, params.T, model.nu
+    k_total = K if k_total is None else k_total
+    tab = np.ascontiguousarray(halton_tab, np.int32)
+    Bm = np.ascontiguousarray(B, np.float32)
+    Z = np.zeros((T, nu, K), np.float32)
+    lib().oracle_noise_library(C.byref(model), C.byref(params), C.c_uint32(k_offset), C.c_uint32(k_total), tab.ctypes.data_as(C.POINTER(C.c_int32)),
+                               _f(Bm), C.c_int32(n_knots), _f(Z))
+    return Z
+
+
+def sample_library(model, params, U, Z, k_offset=0, k_total=None, prior_row=None):
+    K, T, nu = params.K, params.T, model.nu
+    k_total = K if k_total is None else k_total
+    U = np.ascontiguousarray(U, np.float32).reshape(T, nu)
+    Z = np.ascontiguousarray(Z, np.float32)
+    actions, noise = np.empty((T, nu, K), np.float32), np.empty((T, nu, K), np.float32)
+    pr = None if prior_row is None else np.ascontiguousarray(prior_row, np.float32)
+    lib().oracle_sample_library(C.byref(model), C.byref(params), C.c_uint32(k_offset), C.c_uint32(k_total), _f(U), _f(pr), _f(Z), _f(actions), _f(noise))
     return actions, noise
 
 

@@ -369,3 +369,36 @@ def test_boxer_plan_through_planner_api():
     for _ in range(2):
         gpu.compute_action(q, [0.0] * 3)
     assert gpu.mppi._graph is not None
+
+
+def test_halton_library_parity(oracle):
+    from mppi_isaac_b200.planner.mppi import halton_spline_operator, halton_table
+    K, T, nk = 1000, 30, 7
+    sc, p, _ = panda_setup(K=K, T=T, mode="halton-spline")
+    be = gpu_backend(sc, p)
+    B, tab = halton_spline_operator(T, nk), halton_table(nk * 7, 11)
+    Z = torch.zeros((T, 7, K), device=DEV)
+    be.noise_library(0, K, dev(tab, torch.int32), dev(B), nk, Z)
+    Z_ref = oracle.noise_library(sc.model, p, tab, B, nk)
+    assert np.abs(Z.cpu().numpy() - Z_ref).max() <= 5e-6 * max(1.0, np.abs(Z_ref).max())          # erfinvf vs AS241 in double
+    U = np.random.default_rng(0).uniform(-0.1, 0.1, (T, 7)).astype(np.float32)
+    a, n = torch.zeros_like(Z), torch.zeros_like(Z)
+    be.sample_library(0, K, dev(U), None, Z, a, n)
+    a_ref, n_ref = oracle.sample_library(sc.model, p, U, Z.cpu().numpy())
+    np.testing.assert_array_equal(a.cpu().numpy(), a_ref)
+    np.testing.assert_array_equal(n.cpu().numpy(), n_ref)
+
+
+def test_halton_spline_plan_through_planner_api():
+    from mppi_isaac_b200 import MPPIisaacPlanner
+    from mppi_isaac_b200.objectives import PandaReachObjective
+    from oracle.backend import OracleBackend
+    kw = dict(mppi_mode="halton-spline", sampling_method="halton")
+    gpu = MPPIisaacPlanner(panda_cfg(K=1000, T=30, device=DEV, **kw), PandaReachObjective())
+    cpu = MPPIisaacPlanner(panda_cfg(K=1000, T=30, device="cpu", **kw), PandaReachObjective(), backend=OracleBackend(nthreads=8))
+    q = np.array([0.0, -0.94, 0.0, -2.8, 0.0, 1.8675, 0.0])
+    for it in range(4):
+        ag, ac = gpu.compute_action(q, np.zeros(7)), cpu.compute_action(q, np.zeros(7))
+        assert float((ag - ac).abs().max()) <= 2e-4, f"plan {it}"
+        q = q + 0.05 * ac.numpy()
+    assert gpu.mppi._graph is not None

@@ -263,3 +263,16 @@ def test_boxer_push_c3_planar_differential_drive():
     out = bytes_to_torch(p.command())
     assert out.shape == (2,)
     np.testing.assert_allclose(s.get_actor_position_by_name("boxer")[:32, 0:2].numpy(), [[0.3, 2.0]] * 32, atol=0.08)
+
+
+def test_halton_spline_mode_runs_the_shipped_style_config():
+    """mppi_mode halton-spline + sampling_method halton (what 17 of the 18 shipped conf/mppi files select)."""
+    p = make(panda_cfg(K=128, T=12, mppi_mode="halton-spline", sampling_method="halton"), PandaReachObjective())
+    assert p.mppi.use_library and p.mppi.n_knots == 3 and p.mppi.backend.params.mode == 1
+    z0 = p.mppi.Z.clone()
+    a1 = p.compute_action(Q0, [0] * 7)
+    a2 = p.compute_action(Q0, [0] * 7)
+    assert torch.equal(p.mppi.Z, z0)                                       # the library is drawn once and reused
+    assert a1.shape == (7,) and torch.isfinite(a2).all() and float(a1.abs().max()) <= 0.2 + 1e-6
+    # mean update: U <- 0.02 U + 0.98 sum_k w_k a_k stays inside the bounds
+    assert float(p.mppi.U.abs().max()) <= 0.2 + 1e-6

@@ -50,5 +50,5 @@ acts = [torch.zeros_like(a) for _ in range(world)]
 dist.all_gather(acts, a.contiguous())
 assert all(torch.equal(acts[0], t) for t in acts), "ranks disagree on the action"
 say("all ranks hold the same action")
-dist.destroy_process_group()
+bench.shutdown_distributed(planner)
 say("done")
