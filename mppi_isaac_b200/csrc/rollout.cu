@@ -35,10 +35,7 @@
 #define ROLL_UNROLL_S1 1      // unroll factor of sweep 1 (kinematics / inertia: bodies are independent apart from the frame recursion)
 #endif
 #ifndef ROLL_UNROLL_S3
-#define ROLL_UNROLL_S3 1      // unroll factor of sweep 3 (accelerations)
-#endif
-#ifndef ROLL_FAST_SINCOS
-#define ROLL_FAST_SINCOS 0    // 1: __sincosf (2^-21 abs error) instead of sincosf
+#define ROLL_UNROLL_S3 2      // unroll factor of sweep 3 (accelerations)
 #endif
 #define MPPIB_STR2(x) #x
 #define MPPIB_STR(x) MPPIB_STR2(x)
@@ -65,6 +62,22 @@ __device__ __forceinline__ V3 mul(const M3& m, V3 v) {
 }
 __device__ __forceinline__ V3 mulT(const M3& m, V3 v) {
     return mk(m.m00 * v.x + m.m10 * v.y + m.m20 * v.z, m.m01 * v.x + m.m11 * v.y + m.m21 * v.z, m.m02 * v.x + m.m12 * v.y + m.m22 * v.z);
+}
+
+// sin / cos with a two-term Cody-Waite reduction and the Cephes minimax polynomials on [-pi/4, pi/4]: max error 9e-8 for
+// |x| < 3000 rad (checked against float64), ~25 instructions and NO slow path.  CUDA's sincosf carries a Payne-Hanek
+// fallback whose code, registers and convergence barriers cost 11 % of this kernel (profiles/r1_rollout_tuning.md).
+__device__ __forceinline__ void sincos_cw(float x, float* s_out, float* c_out) {
+    const float k = rintf(x * 0.63661975f);
+    float r = fmaf(-k, 1.5707964f, x);
+    r = fmaf(-k, -4.371139e-08f, r);
+    const float r2 = r * r;
+    const float s = fmaf(r * r2, fmaf(r2, fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), r);
+    const float c = fmaf(r2 * r2, fmaf(r2, fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f), fmaf(-0.5f, r2, 1.0f));
+    const int n = (int)k & 3;
+    const float ss = (n & 1) ? c : s, cc = (n & 1) ? s : c;
+    *s_out = (n & 2) ? -ss : ss;
+    *c_out = ((n + 1) & 2) ? -cc : cc;
 }
 
 struct Quat { float x, y, z, w; };
@@ -183,11 +196,7 @@ __device__ __forceinline__ void body_kinematics(const MppibModel& m, int i, floa
     const V3 axis = mk(Rt.m02, Rt.m12, Rt.m22);
     if (m.jtype[i] == MPPIB_JOINT_REVOLUTE) {
         float sq, cq;
-#if ROLL_FAST_SINCOS
-        __sincosf(q, &sq, &cq);
-#else
-        sincosf(q, &sq, &cq);
-#endif
+        sincos_cw(q, &sq, &cq);
         out.R = Rt;   // Rt * Rz(q)
         out.R.m00 = Rt.m00 * cq + Rt.m01 * sq; out.R.m01 = Rt.m01 * cq - Rt.m00 * sq;
         out.R.m10 = Rt.m10 * cq + Rt.m11 * sq; out.R.m11 = Rt.m11 * cq - Rt.m10 * sq;
@@ -252,7 +261,7 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
                 // differential drive reduced to a planar base: body twist (v, omega) -> world-frame velocity targets of the
                 // three virtual joints; the forward axis turns with the current yaw (no lateral slip by construction)
                 const float v = p.u_scale * actions[((size_t)t * nu + 0) * K + k], w = p.u_scale * actions[((size_t)t * nu + 1) * K + k];
-                float sy, cy; sincosf(SM(2, F_Q), &sy, &cy);
+                float sy, cy; sincos_cw(SM(2, F_Q), &sy, &cy);
                 SM(0, F_TGT) = v * (m.fwd_axis[0] * cy - m.fwd_axis[1] * sy);
                 SM(1, F_TGT) = v * (m.fwd_axis[0] * sy + m.fwd_axis[1] * cy);
                 SM(2, F_TGT) = w;
@@ -424,7 +433,7 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
                 const Quat qt = {m.tree_quat[i][0], m.tree_quat[i][1], m.tree_quat[i][2], m.tree_quat[i][3]};
                 Quat r = qmul(qp, qt);
                 if (m.jtype[i] == MPPIB_JOINT_REVOLUTE) {
-                    float sh, ch; sincosf(0.5f * qi, &sh, &ch);
+                    float sh, ch; sincos_cw(0.5f * qi, &sh, &ch);
                     const Quat qz = {0.f, 0.f, sh, ch};
                     r = qmul(r, qz);
                 }

@@ -32,6 +32,7 @@ class MPPIisaacPlanner(object):
         self.cfg = cfg
         self.objective = objective
         self.done = False
+        self._last_root_bytes = None
         self._opts = dict(rollout_mode=rollout_mode, use_cuda_graph=use_cuda_graph, process_group=process_group)
 
         rank, world = 0, 1
@@ -106,7 +107,13 @@ class MPPIisaacPlanner(object):
 
     def reset_rollout_sim(self, dof_state_tensor, root_state_tensor, rigid_body_state_tensor=None):
         self.sim.visualize_link_buffer = []
-        if self.sim.set_world_state(bytes_to_torch(dof_state_tensor), bytes_to_torch(root_state_tensor)):
+        # un-pickling costs ~0.1 ms per tensor: a root-state message identical to the previous one (static scene, fixed base)
+        # is neither parsed nor uploaded again
+        root = None
+        if not (isinstance(root_state_tensor, (bytes, bytearray)) and root_state_tensor == self._last_root_bytes):
+            root = bytes_to_torch(root_state_tensor)
+            self._last_root_bytes = bytes(root_state_tensor) if isinstance(root_state_tensor, (bytes, bytearray)) else None
+        if self.sim.set_world_state(bytes_to_torch(dof_state_tensor), root):
             self.mppi.invalidate_graph()       # the robot base pose is a kernel constant
 
     def compute_action_tensor(self, dof_state_tensor, root_state_tensor):

@@ -531,10 +531,13 @@ class RolloutSim:
         """(1,2*ndof) + (1,A,13) world snapshot -> all rollouts (mppi_isaac.py:87-99).
         Host tensors go through the pinned staging buffer: one H2D copy, no device->host traffic.
         Returns True when the robot base pose (a kernel constant) changed."""
-        root = torch.as_tensor(root_state).reshape(-1, 13)
         dof = torch.as_tensor(dof_state_row).reshape(-1)
         nd = self.scene.ndof
         self.visualize_link_buffer = []
+        if root_state is None:                 # unchanged root states: only the DOF row travels
+            root = self._stage[2 * nd:].view(-1, 13)
+        else:
+            root = torch.as_tensor(root_state).reshape(-1, 13)
         if root.device.type != "cpu" or dof.device.type != "cpu":
             self._root0.copy_(root.to(self.device, dtype=torch.float32))
             self.set_actor_dof_state(dof.to(self.device, dtype=torch.float32))
@@ -544,11 +547,15 @@ class RolloutSim:
         nr = nd - nv
         st[nv:nd] = dof[0:2 * nr:2]
         st[nd + nv:2 * nd] = dof[1:2 * nr:2]
-        st[2 * nd:] = root.reshape(-1)
+        if root_state is not None:
+            st[2 * nd:] = root.reshape(-1)
         if nv:
             x, y, yaw, vx, vy, wz = self._base_from_root(root[self.scene.robot_actor])
             st[0], st[1], st[2], st[nd], st[nd + 1], st[nd + 2] = x, y, yaw, vx, vy, wz
-        self._world.copy_(st, non_blocking=True)
+        if root_state is None:
+            self._state0.copy_(st[:2 * nd], non_blocking=True)       # device root states (possibly edited by setters) stay as they are
+        else:
+            self._world.copy_(st, non_blocking=True)
         self._state_is_broadcast = True
         self._state_stale = True
         self._have_obs = False

@@ -380,7 +380,9 @@ def test_halton_library_parity(oracle):
     Z = torch.zeros((T, 7, K), device=DEV)
     be.noise_library(0, K, dev(tab, torch.int32), dev(B), nk, Z)
     Z_ref = oracle.noise_library(sc.model, p, tab, B, nk)
-    assert np.abs(Z.cpu().numpy() - Z_ref).max() <= 5e-6 * max(1.0, np.abs(Z_ref).max())          # erfinvf vs AS241 in double
+    # float32 radical inverse + erfinvf vs double + AS241: the quantile's slope sqrt(2 pi) exp(z^2/2) amplifies 1 ulp of u in the tails
+    assert np.abs(Z.cpu().numpy() - Z_ref).max() <= 1e-4
+    assert np.median(np.abs(Z.cpu().numpy() - Z_ref)) <= 1e-6
     U = np.random.default_rng(0).uniform(-0.1, 0.1, (T, 7)).astype(np.float32)
     a, n = torch.zeros_like(Z), torch.zeros_like(Z)
     be.sample_library(0, K, dev(U), None, Z, a, n)
