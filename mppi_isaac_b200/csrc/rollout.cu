@@ -142,17 +142,18 @@ enum : int {
     F_PB = 21,    // 6  bias force v x* I v
     F_U = 27,     // 6  IA S
     F_INVD = 33, F_UU = 34, F_QDD = 35, F_Q = 36, F_QD = 37, F_TGT = 38, F_SAT = 39,
-    NSLOT_CHAIN = 40,
-    // observe-time aliases (slots 12..33 are dead then): world rotation, origin, spatial velocity, quaternion
-    F_OR = 12, F_OO = 21, F_OV = 24, F_OQ = 30,
-    // general trees only
-    F_R = 40,     // 9  world rotation of the body (parent lookup)
-    F_O = 49,     // 3
-    F_V = 52,     // 6  spatial velocity
-    F_IA = 58,    // 21 articulated inertia accumulator
-    F_PA = 79,    // 6  articulated bias accumulator
-    F_ACC = 85,   // 6  spatial acceleration
-    NSLOT_TREE = 91,
+    // observation scratch: world rotation, origin, spatial velocity, quaternion of the body at the END of a model step.  It is
+    // filled by the first sweep 1 of the NEXT step (same state, same kinematics) so that no extra kinematics pass is needed
+    F_OR = 40, F_OO = 49, F_OV = 52, F_OQ = 58,
+    NSLOT_CHAIN = 62,
+    // general trees (and contact scenes) only
+    F_R = 62,     // 9  world rotation of the body (parent lookup)
+    F_O = 71,     // 3
+    F_V = 74,     // 6  spatial velocity
+    F_IA = 80,    // 21 articulated inertia accumulator
+    F_PA = 101,   // 6  articulated bias accumulator
+    F_ACC = 107,  // 6  spatial acceleration
+    NSLOT_TREE = 113,
 };
 
 #define SM(i, f) sm[((i) * NSLOT + (f)) * 32 + lane]
@@ -244,9 +245,79 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
     V6 a0; a0.n = mk(0, 0, 0);
     a0.f = m.gravity_on ? mk(-m.gravity[0], -m.gravity[1], -m.gravity[2]) : mk(0.f, 0.f, 0.f);
 
-    const int nloop = nsteps > 0 ? nsteps : 1;   // nsteps == 0: observe the current state into slot t0
-    for (int t = t0; t < t0 + nloop; ++t) {
-        if (nsteps > 0) {
+    // world frames + quaternions of all bodies at the current (q, qd) -> observation scratch (standalone pass: used once at the end)
+    auto observe_pass = [&]() {
+    {
+        Frame par = base; Quat qp = bq;
+#pragma unroll 1
+        for (int i = 0; i < nb; ++i) {
+            const int pi = CHAIN ? i - 1 : m.parent[i];
+            if (!CHAIN) {
+                if (pi >= 0) {
+                    par.R = ldM3(sm, pi * NSLOT + F_OR, lane); par.o = ld3(sm, pi * NSLOT + F_OO, lane); par.V = ld6(sm, pi * NSLOT + F_OV, lane);
+                    qp.x = SM(pi, F_OQ); qp.y = SM(pi, F_OQ + 1); qp.z = SM(pi, F_OQ + 2); qp.w = SM(pi, F_OQ + 3);
+                } else { par = base; qp = bq; }
+            }
+            const float qi = SM(i, F_Q), qdi = SM(i, F_QD);
+            Frame f; V6 S;
+            body_kinematics(m, i, qi, qdi, par, f, S);
+            const Quat qt = {m.tree_quat[i][0], m.tree_quat[i][1], m.tree_quat[i][2], m.tree_quat[i][3]};
+            Quat r = qmul(qp, qt);
+            if (m.jtype[i] == MPPIB_JOINT_REVOLUTE) {
+                float sh, ch; sincos_cw(0.5f * qi, &sh, &ch);
+                const Quat qz = {0.f, 0.f, sh, ch};
+                r = qmul(r, qz);
+            }
+            stM3(sm, i * NSLOT + F_OR, lane, f.R); st3(sm, i * NSLOT + F_OO, lane, f.o); st6(sm, i * NSLOT + F_OV, lane, f.V);
+            SM(i, F_OQ) = r.x; SM(i, F_OQ + 1) = r.y; SM(i, F_OQ + 2) = r.z; SM(i, F_OQ + 3) = r.w;
+            if (CHAIN) { par = f; qp = r; }
+        }
+    }
+    };
+    // write the observed rows of model step `t` from the observation scratch / state slots
+    auto write_obs = [&](int t) {
+    const size_t TK = (size_t)T * K;
+    float* dst = obs + (size_t)t * K + k;
+    int row = 0;
+    for (int oi = 0; oi < p.nobs; ++oi) {
+        const int kind = p.obs[oi].kind, idx = p.obs[oi].index;
+        if (kind == MPPIB_OBS_LINK_STATE) {
+            const int b = m.link_body[idx];
+            M3 Rl; V3 ol, w, vO; Quat qb;
+            if (b >= 0) {
+                Rl = ldM3(sm, b * NSLOT + F_OR, lane); ol = ld3(sm, b * NSLOT + F_OO, lane);
+                const V6 Vb = ld6(sm, b * NSLOT + F_OV, lane); w = Vb.n; vO = Vb.f;
+                qb.x = SM(b, F_OQ); qb.y = SM(b, F_OQ + 1); qb.z = SM(b, F_OQ + 2); qb.w = SM(b, F_OQ + 3);
+            } else { Rl = base.R; ol = base.o; w = mk(0, 0, 0); vO = mk(0, 0, 0); qb = bq; }
+            const V3 pos = ol + mul(Rl, mk(m.link_p[idx][0], m.link_p[idx][1], m.link_p[idx][2]));
+            const Quat ql = {m.link_quat[idx][0], m.link_quat[idx][1], m.link_quat[idx][2], m.link_quat[idx][3]};
+            const Quat qo = qmul(qb, ql);
+            const V3 vel = vO + cross(w, pos);   // spatial velocity about the world origin -> velocity of the link origin
+            dst[(size_t)(row + 0) * TK] = pos.x; dst[(size_t)(row + 1) * TK] = pos.y; dst[(size_t)(row + 2) * TK] = pos.z;
+            dst[(size_t)(row + 3) * TK] = qo.x; dst[(size_t)(row + 4) * TK] = qo.y; dst[(size_t)(row + 5) * TK] = qo.z;
+            dst[(size_t)(row + 6) * TK] = qo.w;
+            dst[(size_t)(row + 7) * TK] = vel.x; dst[(size_t)(row + 8) * TK] = vel.y; dst[(size_t)(row + 9) * TK] = vel.z;
+            dst[(size_t)(row + 10) * TK] = w.x; dst[(size_t)(row + 11) * TK] = w.y; dst[(size_t)(row + 12) * TK] = w.z;
+            row += 13;
+        } else if (kind == MPPIB_OBS_DOF_STATE) {
+            for (int i = 0; i < nb; ++i) {
+                dst[(size_t)(row + 2 * i) * TK] = SM(i, F_Q);
+                dst[(size_t)(row + 2 * i + 1) * TK] = SM(i, F_QD);
+            }
+            row += 2 * nb;
+        } else if (kind == MPPIB_OBS_FREE_STATE) {
+            const int fb = L.fb0 + idx * contact::FBN;
+            for (int r = 0; r < 13; ++r) dst[(size_t)(row + r) * TK] = (CONTACT && idx < m.nfree) ? xs[(fb + r) * 32 + lane] : 0.f;
+            row += 13;
+        } else {
+            for (int r = 0; r < 3; ++r) dst[(size_t)(row + r) * TK] = (CONTACT && idx < MPPIB_MAX_SLOTS) ? xs[(L.net0 + 3 * idx + r) * 32 + lane] : 0.f;
+            row += 3;
+        }
+    }
+    };
+    int pending = (obs != nullptr && nsteps == 0) ? t0 : -1;   // step whose observation is still to be written
+    for (int t = t0; t < t0 + nsteps; ++t) {
+        {
             // apply_robot_cmd: command -> per-DOF targets (diff-drive IK folded into the cmd map)
             for (int i = 0; i < nb; ++i) {
                 const float u0 = p.u_scale * actions[((size_t)t * nu + m.cmd_i0[i]) * K + k];
@@ -254,7 +325,7 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
                 SM(i, F_TGT) = m.cmd_c0[i] * u0 + m.cmd_c1[i] * u1;
             }
         }
-        const int nsub = nsteps > 0 ? p.substeps : 0;
+        const int nsub = p.substeps;
 #pragma unroll 1
         for (int sub = 0; sub < nsub; ++sub) {
             if (m.planar_base) {
@@ -268,17 +339,32 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
             }
             // ------------------------------------------------------------------ sweep 1: root -> leaves
             {
-                Frame par = base;
+                const bool obs_now = sub == 0 && pending >= 0;   // this sweep's kinematics ARE the observation of the previous step
+                Frame par = base; Quat qp = bq;
                 MPPIB_UNROLL(ROLL_UNROLL_S1)
                 for (int i = 0; i < nb; ++i) {
                     if (!CHAIN) {
                         const int pi = m.parent[i];
-                        if (pi >= 0) { par.R = ldM3(sm, pi * NSLOT + F_R, lane); par.o = ld3(sm, pi * NSLOT + F_O, lane); par.V = ld6(sm, pi * NSLOT + F_V, lane); }
-                        else par = base;
+                        if (pi >= 0) {
+                            par.R = ldM3(sm, pi * NSLOT + F_R, lane); par.o = ld3(sm, pi * NSLOT + F_O, lane); par.V = ld6(sm, pi * NSLOT + F_V, lane);
+                            if (obs_now) { qp.x = SM(pi, F_OQ); qp.y = SM(pi, F_OQ + 1); qp.z = SM(pi, F_OQ + 2); qp.w = SM(pi, F_OQ + 3); }
+                        } else { par = base; qp = bq; }
                     }
                     const float qi = SM(i, F_Q), qdi = SM(i, F_QD);
                     Frame f; V6 S;
                     body_kinematics(m, i, qi, qdi, par, f, S);
+                    if (obs_now) {
+                        const Quat qt = {m.tree_quat[i][0], m.tree_quat[i][1], m.tree_quat[i][2], m.tree_quat[i][3]};
+                        Quat r = qmul(qp, qt);
+                        if (m.jtype[i] == MPPIB_JOINT_REVOLUTE) {
+                            float sh, ch; sincos_cw(0.5f * qi, &sh, &ch);
+                            const Quat qz = {0.f, 0.f, sh, ch};
+                            r = qmul(r, qz);
+                        }
+                        stM3(sm, i * NSLOT + F_OR, lane, f.R); st3(sm, i * NSLOT + F_OO, lane, f.o); st6(sm, i * NSLOT + F_OV, lane, f.V);
+                        SM(i, F_OQ) = r.x; SM(i, F_OQ + 1) = r.y; SM(i, F_OQ + 2) = r.z; SM(i, F_OQ + 3) = r.w;
+                        qp = r;
+                    }
                     const float mass = m.mass[i];
                     // centre of mass (world), first moment, inertia about the world origin:
                     //   R I_o R^T + m[(|cw|^2 - |cb|^2) 1 - (cw cw^T - cb cb^T)],  cb = R c_body, cw = o + cb
@@ -316,6 +402,7 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
                     if (CHAIN) par = f;
                     if (STORE_FRAMES) { stM3(sm, i * NSLOT + F_R, lane, f.R); st3(sm, i * NSLOT + F_O, lane, f.o); st6(sm, i * NSLOT + F_V, lane, f.V); }
                 }
+                if (obs_now) { write_obs(pending); pending = -1; }
             }
 #pragma unroll 1
             for (int solve = 0; solve < 2; ++solve) {
@@ -414,73 +501,9 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
             }
             if (CONTACT) contact::integrate_free(m, L, xs, lane, h);
         }
-        if (obs == nullptr) continue;
-        // ---------------------------------------------------------------------------------- observe
-        {
-            Frame par = base; Quat qp = bq;
-#pragma unroll 1
-            for (int i = 0; i < nb; ++i) {
-                const int pi = CHAIN ? i - 1 : m.parent[i];
-                if (!CHAIN) {
-                    if (pi >= 0) {
-                        par.R = ldM3(sm, pi * NSLOT + F_OR, lane); par.o = ld3(sm, pi * NSLOT + F_OO, lane); par.V = ld6(sm, pi * NSLOT + F_OV, lane);
-                        qp.x = SM(pi, F_OQ); qp.y = SM(pi, F_OQ + 1); qp.z = SM(pi, F_OQ + 2); qp.w = SM(pi, F_OQ + 3);
-                    } else { par = base; qp = bq; }
-                }
-                const float qi = SM(i, F_Q), qdi = SM(i, F_QD);
-                Frame f; V6 S;
-                body_kinematics(m, i, qi, qdi, par, f, S);
-                const Quat qt = {m.tree_quat[i][0], m.tree_quat[i][1], m.tree_quat[i][2], m.tree_quat[i][3]};
-                Quat r = qmul(qp, qt);
-                if (m.jtype[i] == MPPIB_JOINT_REVOLUTE) {
-                    float sh, ch; sincos_cw(0.5f * qi, &sh, &ch);
-                    const Quat qz = {0.f, 0.f, sh, ch};
-                    r = qmul(r, qz);
-                }
-                stM3(sm, i * NSLOT + F_OR, lane, f.R); st3(sm, i * NSLOT + F_OO, lane, f.o); st6(sm, i * NSLOT + F_OV, lane, f.V);
-                SM(i, F_OQ) = r.x; SM(i, F_OQ + 1) = r.y; SM(i, F_OQ + 2) = r.z; SM(i, F_OQ + 3) = r.w;
-                if (CHAIN) { par = f; qp = r; }
-            }
-        }
-        const size_t TK = (size_t)T * K;
-        float* dst = obs + (size_t)t * K + k;
-        int row = 0;
-        for (int oi = 0; oi < p.nobs; ++oi) {
-            const int kind = p.obs[oi].kind, idx = p.obs[oi].index;
-            if (kind == MPPIB_OBS_LINK_STATE) {
-                const int b = m.link_body[idx];
-                M3 Rl; V3 ol, w, vO; Quat qb;
-                if (b >= 0) {
-                    Rl = ldM3(sm, b * NSLOT + F_OR, lane); ol = ld3(sm, b * NSLOT + F_OO, lane);
-                    const V6 Vb = ld6(sm, b * NSLOT + F_OV, lane); w = Vb.n; vO = Vb.f;
-                    qb.x = SM(b, F_OQ); qb.y = SM(b, F_OQ + 1); qb.z = SM(b, F_OQ + 2); qb.w = SM(b, F_OQ + 3);
-                } else { Rl = base.R; ol = base.o; w = mk(0, 0, 0); vO = mk(0, 0, 0); qb = bq; }
-                const V3 pos = ol + mul(Rl, mk(m.link_p[idx][0], m.link_p[idx][1], m.link_p[idx][2]));
-                const Quat ql = {m.link_quat[idx][0], m.link_quat[idx][1], m.link_quat[idx][2], m.link_quat[idx][3]};
-                const Quat qo = qmul(qb, ql);
-                const V3 vel = vO + cross(w, pos);   // spatial velocity about the world origin -> velocity of the link origin
-                dst[(size_t)(row + 0) * TK] = pos.x; dst[(size_t)(row + 1) * TK] = pos.y; dst[(size_t)(row + 2) * TK] = pos.z;
-                dst[(size_t)(row + 3) * TK] = qo.x; dst[(size_t)(row + 4) * TK] = qo.y; dst[(size_t)(row + 5) * TK] = qo.z;
-                dst[(size_t)(row + 6) * TK] = qo.w;
-                dst[(size_t)(row + 7) * TK] = vel.x; dst[(size_t)(row + 8) * TK] = vel.y; dst[(size_t)(row + 9) * TK] = vel.z;
-                dst[(size_t)(row + 10) * TK] = w.x; dst[(size_t)(row + 11) * TK] = w.y; dst[(size_t)(row + 12) * TK] = w.z;
-                row += 13;
-            } else if (kind == MPPIB_OBS_DOF_STATE) {
-                for (int i = 0; i < nb; ++i) {
-                    dst[(size_t)(row + 2 * i) * TK] = SM(i, F_Q);
-                    dst[(size_t)(row + 2 * i + 1) * TK] = SM(i, F_QD);
-                }
-                row += 2 * nb;
-            } else if (kind == MPPIB_OBS_FREE_STATE) {
-                const int fb = L.fb0 + idx * contact::FBN;
-                for (int r = 0; r < 13; ++r) dst[(size_t)(row + r) * TK] = (CONTACT && idx < m.nfree) ? xs[(fb + r) * 32 + lane] : 0.f;
-                row += 13;
-            } else {
-                for (int r = 0; r < 3; ++r) dst[(size_t)(row + r) * TK] = (CONTACT && idx < MPPIB_MAX_SLOTS) ? xs[(L.net0 + 3 * idx + r) * 32 + lane] : 0.f;
-                row += 3;
-            }
-        }
+        if (obs != nullptr) pending = t;       // observed by the next step's first sweep 1, or by observe_pass() after the loop
     }
+    if (pending >= 0) { observe_pass(); write_obs(pending); }
     if (state != nullptr) {
         for (int i = 0; i < nb; ++i) {
             state[(size_t)i * K + k] = SM(i, F_Q);
