@@ -121,10 +121,13 @@ def test_k2_stepwise_equals_batched_and_observe_only(oracle):
     be.rollout(dev(state0), st_a, actions, 0, 6, obs_a)
     for t in range(6):
         be.rollout(None, st_b, actions[t:t + 1], t, 1, obs_b, act_t0=t)
-    assert torch.equal(obs_a, obs_b) and torch.equal(st_a, st_b)
+    assert torch.equal(st_a, st_b)                                         # the dynamics are bit-identical ...
+    # ... the observed rows come from two differently scheduled copies of the same kinematics (the batched launch reuses the
+    # next step's sweep 1, a single step runs the standalone pass): identical up to float32 contraction order
+    torch.testing.assert_close(obs_a, obs_b, atol=2e-6, rtol=0)
     obs_c = torch.zeros_like(obs_a)
     be.rollout(None, st_b, actions, 5, 0, obs_c)                           # observe-only into slot 5
-    assert torch.equal(obs_c[:, 5], obs_a[:, 5])
+    assert torch.equal(obs_c[:, 5], obs_b[:, 5])
 
 
 def test_k2_replica_determinism_full_size():
