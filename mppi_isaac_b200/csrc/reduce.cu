@@ -75,8 +75,8 @@ mppib_reduce_kernel(const __grid_constant__ MppibParams p, const __grid_constant
     float* tiles = reinterpret_cast<float*>(smem_raw);                       // [NS][(NR+T)*W], each stage 128-B aligned
     const int stage_floats = (tile_floats + 31) & ~31;
     float* g = tiles + (size_t)NS * stage_floats;                            // [NR]  lambda * Sigma^-1 U (SIMPLE)
-    float* gp = g + NR;                                                      // [T]   gamma^t
-    float* red = gp + ((T + 1) & ~1);                                        // [8][W]
+    float* gp = g + ((NR + 3) & ~3);                                         // [T]   gamma^t          (every array 16-B aligned:
+    float* red = gp + ((T + 3) & ~3);                                        // [8][W]                  wk is read as float4)
     float* wk = red + 8 * W;                                                 // [W]
     float* misc = wk + W;                                                    // [8]
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (((size_t)((misc + 8) - tiles) * 4 + 15) & ~(size_t)15));  // [NS] mbarriers
@@ -327,7 +327,7 @@ size_t reduce_smem_bytes(int T, int nu) {
     size_t ring = (size_t)NS * stage;
     const size_t fold = MAX_GRID + 4 * (size_t)(2 + NR + 3);  // the last CTA reuses the ring for the fold
     if (ring < fold) ring = (fold + 31) & ~(size_t)31;
-    return sizeof(float) * (ring + NR + T + 1 + 8 * W + W + 8) + 16 + sizeof(uint64_t) * NS + 128;
+    return sizeof(float) * (ring + (NR + 3) + (T + 3) + 8 * W + W + 8) + 16 + sizeof(uint64_t) * NS + 128;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

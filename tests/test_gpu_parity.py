@@ -407,3 +407,24 @@ def test_halton_spline_plan_through_planner_api():
         assert float((ag - ac).abs().max()) <= 2e-4, f"plan {it}"
         q = q + 0.05 * ac.numpy()
     assert gpu.mppi._graph is not None
+
+
+@pytest.mark.parametrize("setup,T", [(point_setup, 12), (point_setup, 25), (point_setup, 9), (gripper_setup, 30), (gripper_setup, 11)])
+def test_k3_shapes_and_alignment(oracle, setup, T):
+    """K3 across (T, nu) shapes: T*nu = 27..270 rows, odd row counts, two TMA boxes for T*nu > 256."""
+    K = 1000
+    sc, p, _ = setup(K=K, T=T) if setup is not gripper_setup else setup(K=K, T=T, filter_u=False)
+    p.filter_u = 0
+    nu = sc.nu
+    be = gpu_backend(sc, p)
+    rng = np.random.default_rng(T)
+    U = rng.uniform(-0.1, 0.1, (T, nu)).astype(np.float32)
+    x = rng.normal(0, 0.3, (T, nu, K)).astype(np.float32)
+    cost = rng.uniform(0, 5, (T, K)).astype(np.float32)
+    partial = torch.zeros(2 + T * nu, device=DEV)
+    be.reduce(dev(cost), dev(x), dev(U), partial)
+    torch.cuda.synchronize()
+    p_ref, _ = oracle.reduce(sc.model, p, cost, x, U)
+    pg = partial.cpu().numpy()
+    np.testing.assert_allclose(pg[:2], p_ref[:2], rtol=2e-5)
+    np.testing.assert_allclose(pg[2:], p_ref[2:], rtol=0, atol=2e-5 * max(1.0, np.abs(p_ref[2:]).max()))
