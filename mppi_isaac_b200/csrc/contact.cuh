@@ -19,7 +19,7 @@ enum : int { FB_X = 0, FB_Q = 3, FB_V = 7, FB_W = 10, FB_MASS = 13, FB_HALF = 14
 // world shape slots
 enum : int { SH_R = 0, SH_C = 9, SH_HALF = 12, SH_MU = 15, SH_RAD = 16, SHN = 17 };
 // contact slots
-enum : int { CT_P = 0, CT_N = 3, CT_D = 6, CT_MU = 7, CT_LN = 8, CT_LT1 = 9, CT_LT2 = 10, CT_IDS = 11, CTN = 12 };
+enum : int { CT_P = 0, CT_N = 3, CT_D = 6, CT_MU = 7, CT_LN = 8, CT_LT1 = 9, CT_LT2 = 10, CT_IDS = 11, CT_KN = 12, CT_KT1 = 13, CT_KT2 = 14, CTN = 15 };
 
 struct Layout {
     int fb0, sh0, ct0, jv0, net0, total;   // offsets in slots
@@ -312,37 +312,41 @@ template <int NSLOT>
 __device__ __forceinline__ void solve(const MppibModel& m, const Layout& L, const float* sm, float* xs, int lane, int nc, float h) {
     const float kp = m.contact_kp, kd = m.contact_kd;
     const float gamma = 1.0f / (h * (h * kp + kd)), beta = h * kp / (h * kp + kd);
+    // effective inverse masses along the contact frame are constant during the sweeps (poses are frozen within a substep)
+#pragma unroll 1
+    for (int c = 0; c < nc; ++c) {
+        const int cb = L.ct0 + c * CTN;
+        const int ids = __float_as_int(XS(cb + CT_IDS));
+        const int refA = (ids & 0xFF) - 2, refB = ((ids >> 8) & 0xFF) - 2;
+        const V3 pt = ldx3(xs, cb + CT_P, lane), n = ldx3(xs, cb + CT_N, lane);
+        V3 t1, t2; tangents(n, t1, t2);
+        XS(cb + CT_KN) = inv_mass<NSLOT>(m, L, sm, xs, lane, refA, refB, pt, n);
+        XS(cb + CT_KT1) = inv_mass<NSLOT>(m, L, sm, xs, lane, refA, refB, pt, t1);
+        XS(cb + CT_KT2) = inv_mass<NSLOT>(m, L, sm, xs, lane, refA, refB, pt, t2);
+    }
 #pragma unroll 1
     for (int it = 0; it < m.contact_iters; ++it) {
 #pragma unroll 1
         for (int c = 0; c < nc; ++c) {
             const int cb = L.ct0 + c * CTN;
+            const float kn = XS(cb + CT_KN);
+            if (!(kn > 0.f)) continue;
             const int ids = __float_as_int(XS(cb + CT_IDS));
             const int refA = (ids & 0xFF) - 2, refB = ((ids >> 8) & 0xFF) - 2;
             const V3 pt = ldx3(xs, cb + CT_P, lane), n = ldx3(xs, cb + CT_N, lane);
-            const float d = XS(cb + CT_D), mu = XS(cb + CT_MU);
-            const float kn = inv_mass<NSLOT>(m, L, sm, xs, lane, refA, refB, pt, n);
-            if (!(kn > 0.f)) continue;
-            V3 vr = point_velocity<NSLOT>(m, L, sm, xs, lane, refA, pt) - point_velocity<NSLOT>(m, L, sm, xs, lane, refB, pt);
-            const float vn = dot(vr, n);
-            const float bias = d > 0.f ? fminf(beta * d / h, m.max_depen) : d / h;
-            float ln = XS(cb + CT_LN);
-            const float ln_new = fmaxf(0.f, ln + (-vn + bias - gamma * ln) / (kn + gamma));
-            apply_impulse<NSLOT>(m, L, sm, xs, lane, refA, refB, pt, n, ln_new - ln);
-            XS(cb + CT_LN) = ln_new;
+            const float d = XS(cb + CT_D), mu = XS(cb + CT_MU), kt1 = XS(cb + CT_KT1), kt2 = XS(cb + CT_KT2);
             V3 t1, t2; tangents(n, t1, t2);
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const V3 t = e == 0 ? t1 : t2;
-                vr = point_velocity<NSLOT>(m, L, sm, xs, lane, refA, pt) - point_velocity<NSLOT>(m, L, sm, xs, lane, refB, pt);
-                const float kt = inv_mass<NSLOT>(m, L, sm, xs, lane, refA, refB, pt, t);
-                if (!(kt > 0.f)) continue;
-                const float lim = mu * ln_new;
-                const float lt = XS(cb + CT_LT1 + e);
-                const float lt_new = fminf(fmaxf(lt - dot(vr, t) / kt, -lim), lim);
-                apply_impulse<NSLOT>(m, L, sm, xs, lane, refA, refB, pt, t, lt_new - lt);
-                XS(cb + CT_LT1 + e) = lt_new;
-            }
+            // one visit = normal row + two friction rows solved from the SAME relative velocity, then one impulse application
+            const V3 vr = point_velocity<NSLOT>(m, L, sm, xs, lane, refA, pt) - point_velocity<NSLOT>(m, L, sm, xs, lane, refB, pt);
+            const float bias = d > 0.f ? fminf(beta * d / h, m.max_depen) : d / h;
+            const float ln = XS(cb + CT_LN), lt1 = XS(cb + CT_LT1), lt2 = XS(cb + CT_LT2);
+            const float ln_new = fmaxf(0.f, ln + (-dot(vr, n) + bias - gamma * ln) / (kn + gamma));
+            const float lim = mu * ln_new;
+            const float lt1_new = kt1 > 0.f ? fminf(fmaxf(lt1 - dot(vr, t1) / kt1, -lim), lim) : lt1;
+            const float lt2_new = kt2 > 0.f ? fminf(fmaxf(lt2 - dot(vr, t2) / kt2, -lim), lim) : lt2;
+            const V3 dP = (ln_new - ln) * n + (lt1_new - lt1) * t1 + (lt2_new - lt2) * t2;
+            XS(cb + CT_LN) = ln_new; XS(cb + CT_LT1) = lt1_new; XS(cb + CT_LT2) = lt2_new;
+            apply_impulse<NSLOT>(m, L, sm, xs, lane, refA, refB, pt, dP, 1.0f);
         }
     }
     for (int s = 0; s < 3 * MPPIB_MAX_SLOTS; ++s) XS(L.net0 + s) = 0.f;

@@ -272,7 +272,7 @@ enum { REF_STATIC = -1, REF_FREE0 = 64 };
 
 template <class S> struct FreeBody { S x[3], q[4], v[3], w[3], mass, half[3], Iinv[3]; M3<S> R, IinvW; };
 template <class S> struct ShapeW { M3<S> R; S c[3], half[3], mu, rad; int ref, slot, kind; };
-template <class S> struct Contact { int refA, refB, slotA, slotB, penalty; S p[3], n[3], d, mu, ln, lt1, lt2, t1[3], t2[3]; };
+template <class S> struct Contact { int refA, refB, slotA, slotB, penalty; S p[3], n[3], d, mu, ln, lt1, lt2, t1[3], t2[3], kn, kt1, kt2; };
 
 template <class S> void mat_vec(const M3<S>& R, const S* v, S* o) { for (int r = 0; r < 3; ++r) o[r] = R.a[r][0] * v[0] + R.a[r][1] * v[1] + R.a[r][2] * v[2]; }
 template <class S> void matT_vec(const M3<S>& R, const S* v, S* o) { for (int r = 0; r < 3; ++r) o[r] = R.a[0][r] * v[0] + R.a[1][r] * v[1] + R.a[2][r] * v[2]; }
@@ -473,29 +473,27 @@ struct ContactWorld {
         const S kp = (S)m->contact_kp, kd = (S)m->contact_kd;
         const S gamma = (S)1 / (h * (h * kp + kd)), beta = h * kp / (h * kp + kd);
         for (int j = 0; j < m->nb; ++j) { dqv[j] = 0; Dj[j] = std::max((S)1e-6, art.D[j]); }
+        // effective inverse masses along the contact frame are constant during the sweeps (poses are frozen within a substep)
+        for (int i = 0; i < nc; ++i) { Contact<S>& c = ct[i]; c.kn = inv_mass(c, c.n, art); c.kt1 = inv_mass(c, c.t1, art); c.kt2 = inv_mass(c, c.t2, art); }
         for (int it = 0; it < m->contact_iters; ++it) for (int i = 0; i < nc; ++i) {
             Contact<S>& c = ct[i];
+            if (!(c.kn > 0)) continue;
+            // one visit = normal row + two friction rows solved from the SAME relative velocity, then one impulse application
             S va[3], vb[3], vr[3];
             point_velocity(c.refA, c.p, art, va); point_velocity(c.refB, c.p, art, vb);
             for (int r = 0; r < 3; ++r) vr[r] = va[r] - vb[r];
             const S vn = vr[0] * c.n[0] + vr[1] * c.n[1] + vr[2] * c.n[2];
-            const S kn = inv_mass(c, c.n, art);
-            if (!(kn > 0)) continue;
+            const S vt1 = vr[0] * c.t1[0] + vr[1] * c.t1[1] + vr[2] * c.t1[2], vt2 = vr[0] * c.t2[0] + vr[1] * c.t2[1] + vr[2] * c.t2[2];
             // penetration: push out (at most max_depen m/s, so squeezed bodies are not shot out); gap: may close at most gap / h
             const S bias = c.d > 0 ? std::min(beta * c.d / h, (S)m->max_depen) : c.d / h;
-            S dl = (-vn + bias - gamma * c.ln) / (kn + gamma);
-            const S ln_new = std::max((S)0, c.ln + dl); dl = ln_new - c.ln; c.ln = ln_new;
-            apply_impulse(c, c.n, dl, art);
-            S* lts[2] = {&c.lt1, &c.lt2}; const S* ts[2] = {c.t1, c.t2};
-            for (int e = 0; e < 2; ++e) {
-                point_velocity(c.refA, c.p, art, va); point_velocity(c.refB, c.p, art, vb);
-                const S vt = (va[0] - vb[0]) * ts[e][0] + (va[1] - vb[1]) * ts[e][1] + (va[2] - vb[2]) * ts[e][2];
-                const S kt = inv_mass(c, ts[e], art);
-                if (!(kt > 0)) continue;
-                const S lim = c.mu * c.ln;
-                const S lt_new = std::min(std::max(*lts[e] - vt / kt, -lim), lim);
-                apply_impulse(c, ts[e], lt_new - *lts[e], art); *lts[e] = lt_new;
-            }
+            const S ln_new = std::max((S)0, c.ln + (-vn + bias - gamma * c.ln) / (c.kn + gamma));
+            const S lim = c.mu * ln_new;
+            const S lt1_new = c.kt1 > 0 ? std::min(std::max(c.lt1 - vt1 / c.kt1, -lim), lim) : c.lt1;
+            const S lt2_new = c.kt2 > 0 ? std::min(std::max(c.lt2 - vt2 / c.kt2, -lim), lim) : c.lt2;
+            S dP[3];
+            for (int r = 0; r < 3; ++r) dP[r] = (ln_new - c.ln) * c.n[r] + (lt1_new - c.lt1) * c.t1[r] + (lt2_new - c.lt2) * c.t2[r];
+            c.ln = ln_new; c.lt1 = lt1_new; c.lt2 = lt2_new;
+            apply_impulse(c, dP, (S)1, art);
         }
         // totals: net force per slot, reaction wrench on articulation bodies
         for (int s = 0; s < MPPIB_MAX_SLOTS; ++s) net[s][0] = net[s][1] = net[s][2] = 0;
