@@ -241,6 +241,7 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
     base.R = quat_to_R(bq);
     base.o = mk(m.base_pos[0], m.base_pos[1], m.base_pos[2]);
     base.V.n = mk(0, 0, 0); base.V.f = mk(0, 0, 0);
+    if (CONTACT) contact::shapes_world<NSLOT>(m, L, sm, xs, lane, base.R, base.o, root0, true);
     // gravity enters as a fictitious base acceleration a0 = [0; -g]
     V6 a0; a0.n = mk(0, 0, 0);
     a0.f = m.gravity_on ? mk(-m.gravity[0], -m.gravity[1], -m.gravity[2]) : mk(0.f, 0.f, 0.f);
@@ -481,7 +482,7 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
             if (CONTACT) {
                 // ------------------------------------------------------------------ contacts on the predicted velocities
                 for (int i = 0; i < nb; ++i) { xs[(L.jv0 + 2 * nb + i) * 32 + lane] = SM(i, F_QD) + h * SM(i, F_QDD); xs[(L.jv0 + i) * 32 + lane] = 0.f; }
-                contact::shapes_world<NSLOT>(m, L, sm, xs, lane, base.R, base.o, root0);
+                contact::shapes_world<NSLOT>(m, L, sm, xs, lane, base.R, base.o, root0, false);
                 const int nc = contact::detect(m, L, xs, lane);
                 for (int f = 0; f < m.nfree; ++f) if (m.free_gravity[f]) {
                     const int fb = L.fb0 + f * contact::FBN;

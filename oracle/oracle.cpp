@@ -435,9 +435,21 @@ struct ContactWorld {
             w.rad = std::sqrt(w.half[0] * w.half[0] + w.half[1] * w.half[1] + w.half[2] * w.half[2]);
         }
     }
+    // broad phase: bounding spheres, then the 6 face axes of the two boxes (conservative: never rejects boxes closer than the margin)
     bool near(const ShapeW<S>& a, const ShapeW<S>& b) const {
-        S d2 = 0; for (int i = 0; i < 3; ++i) d2 += (a.c[i] - b.c[i]) * (a.c[i] - b.c[i]);
-        const S r = a.rad + b.rad; return d2 <= r * r;
+        S d[3], d2 = 0; for (int i = 0; i < 3; ++i) { d[i] = a.c[i] - b.c[i]; d2 += d[i] * d[i]; }
+        const S r = a.rad + b.rad; if (d2 > r * r) return false;
+        const S mg = (S)m->contact_margin;
+        S C[3][3];                                   // C = Rb^T Ra
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { S v = 0; for (int k = 0; k < 3; ++k) v += b.R.a[k][i] * a.R.a[k][j]; C[i][j] = v; }
+        S tb[3], ta[3]; matT_vec(b.R, d, tb); matT_vec(a.R, d, ta);
+        for (int i = 0; i < 3; ++i) {
+            const S ra = std::fabs(C[i][0]) * a.half[0] + std::fabs(C[i][1]) * a.half[1] + std::fabs(C[i][2]) * a.half[2];
+            if (std::fabs(tb[i]) > b.half[i] + ra + mg) return false;
+            const S rb = std::fabs(C[0][i]) * b.half[0] + std::fabs(C[1][i]) * b.half[1] + std::fabs(C[2][i]) * b.half[2];
+            if (std::fabs(ta[i]) > a.half[i] + rb + mg) return false;
+        }
+        return true;
     }
     void detect() {
         nc = 0;
