@@ -302,10 +302,22 @@ def run_gpu_arm(args, rank, world, local_rank):
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     assert all(bytes_to_torch(o).shape == (planner.mppi.nu,) for o in outs)
+    # the reference's in-process entry point: compute_action(q, qdot) with host lists in, host tensor out
+    qs = [list(q0 + rng.uniform(-0.05, 0.05, 7)) for _ in range(args.steps)]
+    qds = [list(rng.uniform(-0.1, 0.1, 7)) for _ in range(args.steps)]
+    for _ in range(3):
+        planner.compute_action(qs[0], qds[0])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        planner.compute_action(qs[i], qds[i])
+    torch.cuda.synchronize()
+    e2e2_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e2_s, op=dist.ReduceOp.MAX)
     total_s = float(total_ms.item()) * 1e-3
     value = k_total * T_HORIZON * args.steps / total_s
     e2e_value = k_total * T_HORIZON * args.steps / float(e2e_s.item())
@@ -321,7 +333,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                        "cuda_graph": graph_on, "l2": "flushed (256 MiB write) before every timed plan",
                        "ms_per_step_p10_p50_p90": [float(np.percentile(per_step_ms, p)) for p in (10, 50, 90)]},
             "e2e": {"value": e2e_value, "unit": UNIT, "plan_hz": args.steps / float(e2e_s.item()), "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": planner.mppi.nu * 4, "api": "MPPIisaacPlanner.compute_action_tensor(dof_bytes, root_bytes) -> bytes"},
+                    "d2h_bytes_per_step": planner.mppi.nu * 4, "api": "MPPIisaacPlanner.compute_action_tensor(dof_bytes, root_bytes) -> bytes",
+                    "compute_action_plan_hz": args.steps / float(e2e2_s.item())},
             "gpu_launches": launches_per_plan * args.steps,
             "clocks": clocks,
         }

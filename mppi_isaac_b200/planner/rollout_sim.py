@@ -92,6 +92,8 @@ class RolloutSim:
         self._stage = torch.from_numpy(host.copy())
         if torch.device(dev).type == "cuda":
             self._stage = self._stage.pin_memory()
+        self._stage_np = self._stage.numpy()
+        self._act_host = None
         if self._visualize_link_present:
             rcfg = self.env_cfg[sc.robot_actor]
             self._viz_link = sc.robot.link_names.index(rcfg.visualize_link)
@@ -377,16 +379,17 @@ class RolloutSim:
     def sync_base_pose(self):
         return self._sync_base_pose_from(self._root0[self.scene.robot_actor].detach().cpu())
 
-    def _sync_base_pose_from(self, row):
+    def _sync_base_pose_from(self, row, staged=False):
         row = row.numpy() if hasattr(row, "numpy") else row
         m = self.scene.model
         if self.scene.virtual_dofs:
             # planar base: the pose is STATE (virtual joints), only the height of the plane is a kernel constant
             x, y, yaw, vx, vy, wz = self._base_from_root(row)
             nd = self.scene.ndof
-            vals = torch.tensor([x, y, yaw, vx, vy, wz], dtype=torch.float32)
-            self._stage[0:3] = vals[0:3]; self._stage[nd:nd + 3] = vals[3:6]
-            self._state0[0:3].copy_(vals[0:3].to(self.device)); self._state0[nd:nd + 3].copy_(vals[3:6].to(self.device))
+            if not staged:                     # the host fast path has already put these into the staged copy
+                vals = torch.tensor([x, y, yaw, vx, vy, wz], dtype=torch.float32)
+                self._stage[0:3] = vals[0:3]; self._stage[nd:nd + 3] = vals[3:6]
+                self._state0[0:3].copy_(vals[0:3].to(self.device)); self._state0[nd:nd + 3].copy_(vals[3:6].to(self.device))
             self._state_stale = True
             if m.base_pos[2] != float(row[2]):
                 m.base_pos[2] = float(row[2])
@@ -525,6 +528,18 @@ class RolloutSim:
             for _q, _qdot in zip(actor_q, actor_qdot):
                 dof_state += [float(_q), float(_qdot)]
             q_idx += n
+        if self.scene.virtual_dofs == 0:
+            # staged upload: one async H2D copy of [q | qd] instead of a pageable tensor + gather kernels
+            nd = self.scene.ndof
+            row = np.asarray(dof_state, dtype=np.float32)
+            self._stage_np[0:nd] = row[0::2]
+            self._stage_np[nd:2 * nd] = row[1::2]
+            self._state0.copy_(self._stage[:2 * nd], non_blocking=True)
+            self._state_is_broadcast = True
+            self._state_stale = True
+            self._have_obs = False
+            self._t = 0
+            return
         self.set_actor_dof_state(torch.tensor(dof_state, dtype=torch.float32))
 
     def set_world_state(self, dof_state_row: torch.Tensor, root_state: torch.Tensor):
@@ -542,25 +557,41 @@ class RolloutSim:
             self._root0.copy_(root.to(self.device, dtype=torch.float32))
             self.set_actor_dof_state(dof.to(self.device, dtype=torch.float32))
             return self.sync_base_pose()
-        st = self._stage
-        nv = self.scene.virtual_dofs
+        return self.set_world_state_host(dof.to(torch.float32).numpy(), None if root_state is None else root.to(torch.float32).reshape(-1).numpy())
+
+    def set_world_state_host(self, dof, root=None):
+        """Host fast path of ``set_world_state``: flat float32 numpy arrays (interleaved DOF row, optional A*13 root rows)
+        -> pinned staging buffer -> ONE async H2D copy.  ``root=None`` keeps the root states already on the device."""
+        nd, nv = self.scene.ndof, self.scene.virtual_dofs
         nr = nd - nv
+        st = self._stage_np
         st[nv:nd] = dof[0:2 * nr:2]
         st[nd + nv:2 * nd] = dof[1:2 * nr:2]
-        if root_state is not None:
-            st[2 * nd:] = root.reshape(-1)
+        if root is not None:
+            st[2 * nd:] = root
+        robot_row = st[2 * nd + 13 * self.scene.robot_actor: 2 * nd + 13 * self.scene.robot_actor + 13]
         if nv:
-            x, y, yaw, vx, vy, wz = self._base_from_root(root[self.scene.robot_actor])
+            x, y, yaw, vx, vy, wz = self._base_from_root(robot_row)
             st[0], st[1], st[2], st[nd], st[nd + 1], st[nd + 2] = x, y, yaw, vx, vy, wz
-        if root_state is None:
-            self._state0.copy_(st[:2 * nd], non_blocking=True)       # device root states (possibly edited by setters) stay as they are
+        self.visualize_link_buffer = []
+        if root is None:
+            self._state0.copy_(self._stage[:2 * nd], non_blocking=True)   # device root states (possibly edited by setters) stay as they are
         else:
-            self._world.copy_(st, non_blocking=True)
+            self._world.copy_(self._stage, non_blocking=True)
         self._state_is_broadcast = True
         self._state_stale = True
         self._have_obs = False
         self._t = 0
-        return self._sync_base_pose_from(st[2 * nd:].view(-1, 13)[self.scene.robot_actor])
+        return self._sync_base_pose_from(robot_row, staged=True)
+
+    def read_action(self, action: torch.Tensor):
+        """Device action -> pinned host buffer (one D2H copy + a stream synchronize); returns a float32 numpy view."""
+        if self._act_host is None or self._act_host.shape != action.shape:
+            self._act_host = torch.empty(action.shape, dtype=torch.float32, pin_memory=self._stage.is_pinned())
+        self._act_host.copy_(action, non_blocking=True)
+        if action.is_cuda:
+            torch.cuda.current_stream(action.device).synchronize()
+        return self._act_host.numpy()
 
     def save_root_state(self):
         self.saved_root_state = self._root0.clone()

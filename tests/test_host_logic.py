@@ -276,3 +276,30 @@ def test_halton_spline_mode_runs_the_shipped_style_config():
     assert a1.shape == (7,) and torch.isfinite(a2).all() and float(a1.abs().max()) <= 0.2 + 1e-6
     # mean update: U <- 0.02 U + 0.98 sum_k w_k a_k stays inside the bounds
     assert float(p.mppi.U.abs().max()) <= 0.2 + 1e-6
+
+
+def test_fast_wire_codec_matches_torch_save_load():
+    """transport.FastDecoder / FastEncoder give exactly what torch.load / torch.save give (reference wire format,
+    mppiisaac/utils/transport.py:5-14), including after a shape change and for tensors the fast path must refuse."""
+    import numpy as np
+    from mppi_isaac_b200.utils.transport import FastDecoder, FastEncoder, bytes_to_torch, torch_to_bytes
+
+    g = torch.Generator().manual_seed(5)
+    dec, enc = FastDecoder(), FastEncoder()
+    for shape in [(1, 14), (1, 14), (1, 9, 13), (2, 7), (1, 14), (3,)]:
+        t = torch.randn(shape, generator=g)
+        flat, shp = dec(torch_to_bytes(t))
+        assert shp == tuple(shape) and np.array_equal(flat, t.reshape(-1).numpy())
+    assert dec._tpl[len(torch_to_bytes(torch.zeros(1, 14)))] is not None        # the template path is really in use
+    view = torch.randn(14, 2, generator=g)[:, 0]                                 # non-contiguous: payload != tensor
+    flat, shp = FastDecoder()(torch_to_bytes(view))
+    assert shp == (14,) and np.array_equal(flat, view.numpy())
+    f64 = torch.randn(4, generator=g, dtype=torch.float64)
+    flat, _ = FastDecoder()(torch_to_bytes(f64))
+    assert flat.dtype == np.float32 and np.allclose(flat, f64.numpy())
+    like = torch.zeros(7)
+    for _ in range(3):
+        v = torch.randn(7, generator=g).numpy()
+        back = bytes_to_torch(enc(like, v))
+        assert back.dtype == torch.float32 and back.shape == (7,) and np.array_equal(back.numpy(), v)
+    assert enc._tpl[((7,), "cpu")] is not None
