@@ -185,6 +185,13 @@ __device__ __forceinline__ SpI ldSpI(const float* sm, int base, int lane) { SpI 
 
 struct Frame { M3 R; V3 o; V6 V; };
 
+// 4-byte asynchronous global -> shared copy (LDGSTS): the warp keeps issuing while the line is in flight
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // world kinematics of body i from its parent's frame (R: body axes as columns in the world, o: origin)
 __device__ __forceinline__ void body_kinematics(const MppibModel& m, int i, float q, float qd, const Frame& par, Frame& out, V6& S) {
     const float* tr = m.tree_R[i];
@@ -317,12 +324,23 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
     }
     };
     int pending = (obs != nullptr && nsteps == 0) ? t0 : -1;   // step whose observation is still to be written
+    // the nu action rows of step t+1 are fetched (asynchronously, double-buffered [2][nu][lane]) while step t integrates: a
+    // plain load at the top of a step left the only resident warp of the SM waiting on HBM for ~9 % of the kernel
+    float* ua = xs + (CONTACT ? (size_t)L.total * 32 : 0);
+    auto fetch_actions = [&](int t, int buf) {
+        for (int j = 0; j < nu; ++j) cp_async4(&ua[(buf * nu + j) * 32 + lane], &actions[((size_t)t * nu + j) * K + k]);
+        cp_async_commit();
+    };
+    if (nsteps > 0) fetch_actions(t0, 0);
     for (int t = t0; t < t0 + nsteps; ++t) {
+        const float* ut = ua + (size_t)((t - t0) & 1) * nu * 32;
+        cp_async_wait_all();
+        if (t + 1 < t0 + nsteps) fetch_actions(t + 1, ((t - t0) & 1) ^ 1);
         {
             // apply_robot_cmd: command -> per-DOF targets (diff-drive IK folded into the cmd map)
             for (int i = 0; i < nb; ++i) {
-                const float u0 = p.u_scale * actions[((size_t)t * nu + m.cmd_i0[i]) * K + k];
-                const float u1 = p.u_scale * actions[((size_t)t * nu + m.cmd_i1[i]) * K + k];
+                const float u0 = p.u_scale * ut[m.cmd_i0[i] * 32 + lane];
+                const float u1 = p.u_scale * ut[m.cmd_i1[i] * 32 + lane];
                 SM(i, F_TGT) = m.cmd_c0[i] * u0 + m.cmd_c1[i] * u1;
             }
         }
@@ -332,7 +350,7 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
             if (m.planar_base) {
                 // differential drive reduced to a planar base: body twist (v, omega) -> world-frame velocity targets of the
                 // three virtual joints; the forward axis turns with the current yaw (no lateral slip by construction)
-                const float v = p.u_scale * actions[((size_t)t * nu + 0) * K + k], w = p.u_scale * actions[((size_t)t * nu + 1) * K + k];
+                const float v = p.u_scale * ut[lane], w = p.u_scale * ut[32 + lane];
                 float sy, cy; sincos_cw(SM(2, F_Q), &sy, &cy);
                 SM(0, F_TGT) = v * (m.fwd_axis[0] * cy - m.fwd_axis[1] * sy);
                 SM(1, F_TGT) = v * (m.fwd_axis[0] * sy + m.fwd_axis[1] * cy);
@@ -520,7 +538,7 @@ int launch_t(MppibContext* c, const float* state0, const float* root0, float* st
     const int K = c->params.K;
     const int nslot = (CHAIN && !CONTACT) ? NSLOT_CHAIN : NSLOT_TREE;
     const contact::Layout L(c->model.nb, c->model.nfree, c->model.nshapes);
-    const size_t smem = sizeof(float) * 32 * ((size_t)c->model.nb * nslot + (CONTACT ? (size_t)L.total : 0));
+    const size_t smem = sizeof(float) * 32 * ((size_t)c->model.nb * nslot + (CONTACT ? (size_t)L.total : 0) + 2 * (size_t)c->model.nu);
     MPPIB_REQUIRE(smem <= 226 * 1024, "mppib_rollout: %zu bytes of shared memory per CTA exceed the SM (too many bodies / shapes)", smem);
     static size_t smem_attr = 48 * 1024;
     if (smem > smem_attr) {
