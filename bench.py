@@ -330,6 +330,7 @@ def run_gpu_arm(args, rank, world, local_rank):
             "ms_per_step": total_s * 1e3 / args.steps, "plan_hz": args.steps / total_s, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "K_per_gpu": K_PER_GPU, "K_total": k_total, "T": T_HORIZON, "parallelism": f"sample-shard x{world}",
+                       "exchange": "none" if world == 1 else ("peer-memory stores fused into K3 (NVLink), flags acquired by K4" if planner.mppi._peer_exchange else "NCCL all-gather"),
                        "cuda_graph": graph_on, "l2": "flushed (256 MiB write) before every timed plan",
                        "ms_per_step_p10_p50_p90": [float(np.percentile(per_step_ms, p)) for p in (10, 50, 90)]},
             "e2e": {"value": e2e_value, "unit": UNIT, "plan_hz": args.steps / float(e2e_s.item()), "h2d_bytes_per_step": h2d,
@@ -366,6 +367,7 @@ def shutdown_distributed(planner):
     import gc
     import torch.distributed as dist
     planner.mppi.invalidate_graph()
+    planner.mppi.close_peers()          # collective: unmap the peer-memory exchange windows before the group goes away
     del planner
     gc.collect()
     torch.cuda.synchronize()

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MPPIB_ABI_VERSION 6
+#define MPPIB_ABI_VERSION 7
 
 #define MPPIB_MAX_BODIES 16   /* moving (1-DoF) bodies of the articulation            */
 #define MPPIB_MAX_LINKS  32   /* URDF links whose state can be observed               */
@@ -242,9 +242,30 @@ int32_t mppib_reduce(MppibHandle h, const float* cost, const float* x, const flo
                      float* partial, void* stream);
 
 /* K4: combine G shard partials, update U in place, optional savgol, write action_out[nu]
- * (= first row of U), and weights statistics stats[2] = (beta, eta).                        */
+ * (= first row of U), and weights statistics stats[2] = (beta, eta).  partials == NULL with an
+ * open peer window: take the G = world rows from the window (see mppib_peer_* below).          */
 int32_t mppib_finalize(MppibHandle h, const float* partials, int32_t G, float* U,
                        float* action_out, float* stats, void* stream);
+
+/* multi-GPU exchange over peer memory (one process per GPU, one box) -----------------------------
+ * Replaces the all-gather between K3 and K4 (the reference has no multi-GPU path; this is the B200
+ * scale-out of its single-GPU mppi_torch reduction).  Every rank owns a small
+ * WINDOW in its HBM: [2 parities][world] rows of 2 + T*nu floats plus one arrival flag per row.
+ * With peers open, the last CTA of mppib_reduce stores this rank's (beta, eta, W) row straight
+ * into the window of EVERY rank over NVLink (st.global + fence.sys + st.release.sys of the flag),
+ * and mppib_finalize (called with partials == NULL) spins on its own window's flags
+ * (ld.acquire.sys) before combining -- no host round trip, no NCCL kernel, graph-capturable.
+ * Exchanges are numbered by a device-side counter inside the window, so every rank must issue the
+ * same sequence of reduce/finalize pairs.  A peer that does not arrive within
+ * MPPIB_PEER_TIMEOUT_S seconds (environment, default 20) traps the kernel (loud failure, no hang).
+ *   mppib_peer_alloc : allocate + zero the local window, return its 64-byte cudaIpcMemHandle_t
+ *   mppib_peer_open  : map the window of rank `peer` from the handle that rank returned
+ *   mppib_peer_close : unmap / free; collective-free, the caller synchronises the ranks first    */
+#define MPPIB_MAX_PEERS 16
+#define MPPIB_IPC_HANDLE_BYTES 64
+int32_t mppib_peer_alloc(MppibHandle h, int32_t world, int32_t rank, unsigned char* ipc_handle_out_h);
+int32_t mppib_peer_open(MppibHandle h, int32_t peer, const unsigned char* ipc_handle_h);
+int32_t mppib_peer_close(MppibHandle h);
 
 /* shift U by one step: U[t] <- U[t+1], U[T-1] <- u_init (mppi_torch command() prologue);
  * increments *plan_ctr (device, nullable) by one.                                            */

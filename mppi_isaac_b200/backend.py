@@ -22,6 +22,7 @@ SYMBOLS = [
     "mppib_abi_version", "mppib_last_error", "mppib_create", "mppib_destroy", "mppib_set_params",
     "mppib_set_model", "mppib_state_size", "mppib_obs_size", "mppib_sample", "mppib_rollout",
     "mppib_reduce", "mppib_finalize", "mppib_shift", "mppib_noise_library", "mppib_sample_library",
+    "mppib_peer_alloc", "mppib_peer_open", "mppib_peer_close",
 ]
 
 
@@ -134,6 +135,20 @@ class CudaBackend:
         base = actions.data_ptr() - act_t0 * self.model.nu * self.params.K * 4
         self._check(self.lib.mppib_rollout(self.handle, _ptr(state0), _ptr(root0), _ptr(state), C.c_void_p(base), C.c_int32(t0), C.c_int32(nsteps),
                                            _ptr(obs), self._stream()), "mppib_rollout")
+
+    # -- multi-GPU exchange over peer memory (include/mppib.h: mppib_peer_*) ----------------------
+    def peer_alloc(self, world: int, rank: int) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        self._check(self.lib.mppib_peer_alloc(self.handle, C.c_int32(world), C.c_int32(rank), buf), "mppib_peer_alloc")
+        return bytes(buf)
+
+    def peer_open(self, peer: int, ipc_handle: bytes):
+        buf = (C.c_ubyte * 64).from_buffer_copy(ipc_handle)
+        self._check(self.lib.mppib_peer_open(self.handle, C.c_int32(peer), buf), "mppib_peer_open")
+
+    def peer_close(self):
+        if self.handle:
+            self.lib.mppib_peer_close(self.handle)
 
     def reduce(self, cost, x, U, partial):
         self.launches += 1

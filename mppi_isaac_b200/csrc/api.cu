@@ -93,9 +93,64 @@ int32_t mppib_create(const MppibModel* model_h, const MppibParams* params_h, int
     return 0;
 }
 
+int32_t mppib_peer_close(MppibHandle h) {
+    MPPIB_REQUIRE(h != nullptr, "null handle");
+    bool any = false;
+    for (int g = 0; g < MPPIB_MAX_PEERS; ++g) any = any || h->peer_win[g] != nullptr;
+    if (!any) { h->peer_world = 0; return 0; }
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (int g = 0; g < MPPIB_MAX_PEERS; ++g) {
+        if (!h->peer_win[g]) continue;
+        if (g == h->peer_rank) cudaFree(h->peer_win[g]); else cudaIpcCloseMemHandle(h->peer_win[g]);
+        h->peer_win[g] = nullptr;
+    }
+    h->peer_world = 0; h->peer_rank = 0; h->peer_pcap = 0;
+    return 0;
+}
+
+int32_t mppib_peer_alloc(MppibHandle h, int32_t world, int32_t rank, unsigned char* ipc_handle_out_h) {
+    MPPIB_REQUIRE(h && ipc_handle_out_h, "mppib_peer_alloc: null argument");
+    MPPIB_REQUIRE(world >= 2 && world <= MPPIB_MAX_PEERS && rank >= 0 && rank < world, "mppib_peer_alloc: world %d / rank %d out of range (max %d ranks)", world, rank, MPPIB_MAX_PEERS);
+    static_assert(sizeof(cudaIpcMemHandle_t) == MPPIB_IPC_HANDLE_BYTES, "IPC handle size");
+    mppib_peer_close(h);
+    MPPIB_CHECK_CUDA(cudaSetDevice(h->device));
+    const int P = 2 + h->params.T * h->model.nu;
+    const int pcap = ((P + 3) >> 2) << 2;
+    void* win = nullptr;
+    MPPIB_CHECK_CUDA(cudaMalloc(&win, peer_window_bytes(world, pcap)));
+    MPPIB_CHECK_CUDA(cudaMemset(win, 0, peer_window_bytes(world, pcap)));
+    MPPIB_CHECK_CUDA(cudaDeviceSynchronize());     // zeroed before the handle leaves this process
+    cudaIpcMemHandle_t hd;
+    cudaError_t e = cudaIpcGetMemHandle(&hd, win);
+    if (e != cudaSuccess) { cudaFree(win); MPPIB_REQUIRE(false, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    memcpy(ipc_handle_out_h, &hd, sizeof(hd));
+    h->peer_world = world; h->peer_rank = rank; h->peer_pcap = pcap;
+    h->peer_win[rank] = win;
+    const char* to = getenv("MPPIB_PEER_TIMEOUT_S");
+    const double sec = to ? atof(to) : 20.0;
+    h->peer_timeout_ns = (unsigned long long)((sec > 0.0 ? sec : 20.0) * 1e9);
+    return 0;
+}
+
+int32_t mppib_peer_open(MppibHandle h, int32_t peer, const unsigned char* ipc_handle_h) {
+    MPPIB_REQUIRE(h && ipc_handle_h, "mppib_peer_open: null argument");
+    MPPIB_REQUIRE(h->peer_world >= 2, "mppib_peer_open: call mppib_peer_alloc first");
+    MPPIB_REQUIRE(peer >= 0 && peer < h->peer_world && peer != h->peer_rank, "mppib_peer_open: peer %d out of range", peer);
+    MPPIB_REQUIRE(h->peer_win[peer] == nullptr, "mppib_peer_open: peer %d is already open", peer);
+    MPPIB_CHECK_CUDA(cudaSetDevice(h->device));
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, ipc_handle_h, sizeof(hd));
+    void* win = nullptr;
+    MPPIB_CHECK_CUDA(cudaIpcOpenMemHandle(&win, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_win[peer] = win;
+    return 0;
+}
+
 int32_t mppib_destroy(MppibHandle h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
+    mppib_peer_close(h);
     if (h->reduce_scratch) cudaFree(h->reduce_scratch);
     if (h->reduce_ticket) cudaFree(h->reduce_ticket);
     delete h;
@@ -106,6 +161,7 @@ int32_t mppib_set_params(MppibHandle h, const MppibParams* params_h) {
     MPPIB_REQUIRE(h != nullptr, "null handle");
     if (int rc = validate(&h->model, params_h)) return rc;
     const bool resize = params_h->T != h->params.T;
+    MPPIB_REQUIRE(h->peer_world <= 1 || 2 + params_h->T * h->model.nu <= h->peer_pcap, "mppib_set_params: T*nu outgrows the open peer window; close and re-open the peers");
     h->params = *params_h;
     derive(h);
     if (resize) { MPPIB_CHECK_CUDA(cudaSetDevice(h->device)); return alloc_scratch(h); }
@@ -116,6 +172,7 @@ int32_t mppib_set_model(MppibHandle h, const MppibModel* model_h) {
     MPPIB_REQUIRE(h != nullptr, "null handle");
     if (int rc = validate(model_h, &h->params)) return rc;
     const bool resize = model_h->nu != h->model.nu;
+    MPPIB_REQUIRE(h->peer_world <= 1 || 2 + h->params.T * model_h->nu <= h->peer_pcap, "mppib_set_model: T*nu outgrows the open peer window; close and re-open the peers");
     h->model = *model_h;
     derive(h);
     if (resize) { MPPIB_CHECK_CUDA(cudaSetDevice(h->device)); return alloc_scratch(h); }
@@ -161,7 +218,11 @@ int32_t mppib_reduce(MppibHandle h, const float* cost, const float* x, const flo
 }
 
 int32_t mppib_finalize(MppibHandle h, const float* partials, int32_t G, float* U, float* action_out, float* stats, void* stream) {
-    MPPIB_REQUIRE(h && partials && U && action_out && G >= 1, "mppib_finalize: bad argument");
+    MPPIB_REQUIRE(h && U && action_out && G >= 1, "mppib_finalize: bad argument");
+    if (!partials) {
+        MPPIB_REQUIRE(h->peer_world >= 2 && G == h->peer_world, "mppib_finalize: partials == NULL needs an open peer window and G == world (G=%d, world=%d)", G, h->peer_world);
+        for (int g = 0; g < h->peer_world; ++g) MPPIB_REQUIRE(h->peer_win[g] != nullptr, "mppib_finalize: peer %d is not open", g);
+    }
     return launch_finalize(h, partials, G, U, action_out, stats, (cudaStream_t)stream);
 }
 

@@ -40,7 +40,27 @@ struct MppibContext {
     float* reduce_scratch;   // [max_ctas][2 + T*nu]
     unsigned int* reduce_ticket;
     int reduce_max_ctas;
+    // peer window (multi-GPU exchange over NVLink peer memory), see include/mppib.h
+    int peer_world, peer_rank, peer_pcap;      // pcap: floats per row (>= 2 + T*nu, multiple of 4)
+    void* peer_win[MPPIB_MAX_PEERS];           // window base of every rank (own entry = local allocation)
+    unsigned long long peer_timeout_ns;
 };
+
+// device view of the peer windows, passed by value to K3 / K4
+struct PeerArgs {
+    int world, rank, pcap;
+    unsigned long long timeout_ns;
+    void* win[MPPIB_MAX_PEERS];
+};
+// window layout (bytes): [0] uint32 seq | [128] uint32 flags[2][MPPIB_MAX_PEERS] | [256] float rows[2][world][pcap]
+#define MPPIB_WIN_FLAGS_OFF 128
+#define MPPIB_WIN_DATA_OFF 256
+static inline size_t peer_window_bytes(int world, int pcap) { return MPPIB_WIN_DATA_OFF + sizeof(float) * 2 * (size_t)world * pcap; }
+static inline PeerArgs peer_args(const MppibContext* c) {
+    PeerArgs a; a.world = c->peer_world; a.rank = c->peer_rank; a.pcap = c->peer_pcap; a.timeout_ns = c->peer_timeout_ns;
+    for (int g = 0; g < MPPIB_MAX_PEERS; ++g) a.win[g] = c->peer_win[g];
+    return a;
+}
 
 // kernel launchers (defined in the .cu files)
 int launch_sample(MppibContext* c, uint64_t seed, uint64_t plan_idx, const uint32_t* plan_ctr, uint32_t k_offset, uint32_t k_total,

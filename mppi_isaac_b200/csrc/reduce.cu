@@ -63,7 +63,7 @@ template <int W, int NS>
 __global__ void __launch_bounds__(NT, 1)
 mppib_reduce_kernel(const __grid_constant__ MppibParams p, const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_c,
               int nu, int xbox_rows, const float* __restrict__ U, float* __restrict__ scratch, unsigned int* __restrict__ ticket,
-              float* __restrict__ partial) {
+              float* __restrict__ partial, const __grid_constant__ PeerArgs peers) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int KPL = W / 32;   // samples per lane
     const int K = p.K, T = p.T, NR = T * nu;
@@ -246,9 +246,24 @@ mppib_reduce_kernel(const __grid_constant__ MppibParams p, const __grid_constant
             reinterpret_cast<float4*>(fold + (size_t)cg * PP)[e] = acc;
         }
         __syncthreads();
+        // fused exchange: this rank's row goes straight into the window of every rank (remote stores over NVLink),
+        // then one release-store of the arrival flag per peer; K4 on each rank acquires its own flags
+        uint32_t seq = 0;
+        if (peers.world > 1) seq = *reinterpret_cast<const volatile uint32_t*>(peers.win[peers.rank]) + 1u;
+        const size_t row_off = MPPIB_WIN_DATA_OFF / sizeof(float) + ((size_t)(seq & 1u) * peers.world + peers.rank) * peers.pcap;
         for (int e = tid; e < P; e += NT) {
-            const float v = fold[e] + fold[PP + e] + fold[2 * PP + e] + fold[3 * PP + e];
-            partial[e] = e == 0 ? bb : v;
+            const float v0 = fold[e] + fold[PP + e] + fold[2 * PP + e] + fold[3 * PP + e];
+            const float v = e == 0 ? bb : v0;
+            partial[e] = v;
+            for (int g = 0; g < peers.world; ++g) reinterpret_cast<float*>(peers.win[g])[row_off + e] = v;
+        }
+        if (peers.world > 1) {
+            __threadfence_system();
+            __syncthreads();
+            if (tid < peers.world) {
+                uint32_t* flag = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(peers.win[tid]) + MPPIB_WIN_FLAGS_OFF) + (seq & 1u) * MPPIB_MAX_PEERS + peers.rank;
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
+            }
         }
         if (tid == 0) *ticket = 0u;
     }
@@ -262,24 +277,50 @@ __constant__ float c_sg_edge[4][9] = {{763.f, 441.f, 189.f, 7.f, -105.f, -147.f,
 
 // K4: combine G shard partials, U update, optional Savitzky-Golay (window 9, order 2, 'interp' edges), action out.
 __global__ void __launch_bounds__(256)
-mppib_finalize_kernel(const __grid_constant__ MppibParams p, int nu, const float* __restrict__ partials, int G,
-                float* __restrict__ U, float* __restrict__ action_out, float* __restrict__ stats) {
+mppib_finalize_kernel(const __grid_constant__ MppibParams p, int nu, const float* __restrict__ partials_in, int G,
+                float* __restrict__ U, float* __restrict__ action_out, float* __restrict__ stats, const __grid_constant__ PeerArgs peers) {
     extern __shared__ float un[];   // [T*nu] then [G] scales
-    const int T = p.T, NR = T * nu, P = 2 + NR;
+    const int T = p.T, NR = T * nu;
+    int P = 2 + NR;                 // row stride of the partials
+    const float* partials = partials_in;
+    uint32_t seq = 0;
+    if (partials_in == nullptr) {
+        // rows come from this rank's peer window: wait until every rank's row of exchange `seq` has landed
+        char* win = reinterpret_cast<char*>(peers.win[peers.rank]);
+        seq = *reinterpret_cast<const volatile uint32_t*>(win) + 1u;
+        if ((int)threadIdx.x < G) {
+            const uint32_t* flag = reinterpret_cast<const uint32_t*>(win + MPPIB_WIN_FLAGS_OFF) + (seq & 1u) * MPPIB_MAX_PEERS + threadIdx.x;
+            unsigned long long t0, now; uint32_t got;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (true) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(flag) : "memory");
+                if (got == seq) break;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (now - t0 > peers.timeout_ns) {
+                    printf("mppib_finalize: rank %d waited %.1f s for rank %d (exchange %u, flag %u): peer lost\n", peers.rank, (double)peers.timeout_ns * 1e-9, (int)threadIdx.x, seq, got);
+                    __trap();
+                }
+                __nanosleep(64);
+            }
+        }
+        __syncthreads();
+        partials = reinterpret_cast<const float*>(win + MPPIB_WIN_DATA_OFF) + (size_t)(seq & 1u) * G * peers.pcap;
+        P = peers.pcap;
+    }
     float* sg = un + NR;
     const float inv_lambda = 1.0f / p.lambda_;
     float b = INFINITY;
-    for (int gidx = 0; gidx < G; ++gidx) if (partials[(size_t)gidx * P + 1] > 0.f) b = fminf(b, partials[(size_t)gidx * P]);
+    for (int gidx = 0; gidx < G; ++gidx) if (__ldcg(&partials[(size_t)gidx * P + 1]) > 0.f) b = fminf(b, __ldcg(&partials[(size_t)gidx * P]));
     for (int gidx = threadIdx.x; gidx < G; gidx += blockDim.x) {
-        const float eg = partials[(size_t)gidx * P + 1];
-        sg[gidx] = eg > 0.f ? expf(-(partials[(size_t)gidx * P] - b) * inv_lambda) : 0.f;
+        const float eg = __ldcg(&partials[(size_t)gidx * P + 1]);
+        sg[gidx] = eg > 0.f ? expf(-(__ldcg(&partials[(size_t)gidx * P]) - b) * inv_lambda) : 0.f;
     }
     __syncthreads();
     float e = 0.f;
-    for (int gidx = 0; gidx < G; ++gidx) e += sg[gidx] * partials[(size_t)gidx * P + 1];
+    for (int gidx = 0; gidx < G; ++gidx) e += sg[gidx] * __ldcg(&partials[(size_t)gidx * P + 1]);
     for (int r = threadIdx.x; r < NR; r += blockDim.x) {
         float w = 0.f;
-        for (int gidx = 0; gidx < G; ++gidx) w += sg[gidx] * partials[(size_t)gidx * P + 2 + r];
+        for (int gidx = 0; gidx < G; ++gidx) w += sg[gidx] * __ldcg(&partials[(size_t)gidx * P + 2 + r]);
         const float wm = e > 0.f ? w / e : (p.mode == MPPIB_MODE_SIMPLE ? 0.f : U[r]);   // no valid sample: keep U
         un[r] = p.mode == MPPIB_MODE_SIMPLE ? U[r] + wm : (1.0f - p.step_size_mean) * U[r] + p.step_size_mean * wm;
     }
@@ -309,6 +350,7 @@ mppib_finalize_kernel(const __grid_constant__ MppibParams p, int nu, const float
         if (r < nu) action_out[r] = out;
     }
     if (threadIdx.x == 0 && stats) { stats[0] = b; stats[1] = e; }
+    if (threadIdx.x == 0 && partials_in == nullptr) *reinterpret_cast<volatile uint32_t*>(peers.win[peers.rank]) = seq;   // exchange `seq` consumed
 }
 
 __global__ void mppib_shift_kernel(const __grid_constant__ MppibParams p, int nu, float* __restrict__ U, uint32_t* __restrict__ plan_ctr) {
@@ -360,6 +402,14 @@ int make_map(CUtensorMap* tm, const float* base, int rows, int K, int box_rows, 
     return 0;
 }
 
+// K3 writes into the windows only when every peer is mapped (otherwise: single-GPU behaviour, world = 0)
+static PeerArgs reduce_peers(const MppibContext* c) {
+    PeerArgs a = peer_args(c);
+    for (int g = 0; g < a.world; ++g) if (!a.win[g]) { a.world = 0; break; }
+    if (a.world < 2) a.world = 0;
+    return a;
+}
+
 template <int W, int NS>
 int launch_reduce_t(MppibContext* c, const float* cost, const float* x, const float* U, float* partial, cudaStream_t s) {
     const int T = c->params.T, nu = c->model.nu, NR = T * nu, K = c->params.K;
@@ -381,7 +431,7 @@ int launch_reduce_t(MppibContext* c, const float* cost, const float* x, const fl
     int grid = ntiles < c->num_sms ? ntiles : c->num_sms;
     if (grid > MAX_GRID) grid = MAX_GRID;
     MPPIB_REQUIRE(grid <= c->reduce_max_ctas, "mppib_reduce: scratch too small");
-    mppib_reduce_kernel<W, NS><<<grid, NT, smem, s>>>(c->params, tm_x, tm_c, nu, xbox_rows, U, c->reduce_scratch, c->reduce_ticket, partial);
+    mppib_reduce_kernel<W, NS><<<grid, NT, smem, s>>>(c->params, tm_x, tm_c, nu, xbox_rows, U, c->reduce_scratch, c->reduce_ticket, partial, reduce_peers(c));
     MPPIB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -401,7 +451,7 @@ int launch_reduce(MppibContext* c, const float* cost, const float* x, const floa
 
 int launch_finalize(MppibContext* c, const float* partials, int G, float* U, float* action_out, float* stats, cudaStream_t s) {
     const int NR = c->params.T * c->model.nu;
-    mppib_finalize_kernel<<<1, 256, (NR + G) * sizeof(float), s>>>(c->params, c->model.nu, partials, G, U, action_out, stats);
+    mppib_finalize_kernel<<<1, 256, (NR + G) * sizeof(float), s>>>(c->params, c->model.nu, partials, G, U, action_out, stats, peer_args(c));
     MPPIB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

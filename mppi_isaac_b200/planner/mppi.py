@@ -22,6 +22,8 @@ from __future__ import annotations
 
 from typing import Callable, Optional
 
+import os
+
 import torch
 
 from ..model.blob import MODE_SIMPLE
@@ -103,8 +105,13 @@ class MPPIPlanner:
         self.use_library = str(cfg.sampling_method) == "halton"     # Halton-spline noise library, drawn once
         if getattr(cfg, "update_cov", False) or getattr(cfg, "update_lambda", False):
             raise NotImplementedError("update_cov / update_lambda are False in every shipped config and not provided")
-        sim.configure(mppi_cfg=cfg, horizon=self.T)      # (re)bakes Sigma / bounds / lambda into the kernel parameter block
         self.backend = sim.backend
+        self._peer_exchange = False
+        self._peer_capable = (self.world > 1 and getattr(self.backend, "name", "") == "cuda"
+                              and os.environ.get("MPPIB_EXCHANGE", "peer") == "peer")
+        if self._peer_capable:
+            self.close_peers()                           # a rebuilt planner re-opens windows sized for the new T * nu
+        sim.configure(mppi_cfg=cfg, horizon=self.T)      # (re)bakes Sigma / bounds / lambda into the kernel parameter block
         use_prior = bool(getattr(cfg, "use_priors", False)) and prior is not None
         self.use_priors = use_prior
         if rollout_mode == "auto":
@@ -114,8 +121,51 @@ class MPPIPlanner:
         self.rollout_mode = rollout_mode
         self.use_cuda_graph = bool(use_cuda_graph) and rollout_mode == "batched" and torch.device(self.device).type == "cuda"
         self._alloc()
+        if self._peer_capable:
+            self._open_peers()
 
     # ------------------------------------------------------------------------------------------
+    def _open_peers(self):
+        """Map every rank's exchange window (include/mppib.h mppib_peer_*): K3 then stores its shard row into all windows
+        over NVLink and K4 waits on arrival flags -- the all-gather between them disappears.  Collective; if any rank
+        cannot map a peer (no P2P path), every rank falls back to the NCCL all-gather."""
+        dist = torch.distributed
+        rank = dist.get_rank(self.pg)
+        ok, handle = 1, None
+        try:
+            handle = self.backend.peer_alloc(self.world, rank)
+        except RuntimeError as e:
+            ok, why = 0, str(e)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=self.pg)
+        if ok and all(h is not None for h in handles):
+            try:
+                for g, h in enumerate(handles):
+                    if g != rank:
+                        self.backend.peer_open(g, h)
+            except RuntimeError as e:
+                ok, why = 0, str(e)
+        else:
+            ok, why = 0, "a rank could not allocate its window"
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.pg)
+        self._peer_exchange = bool(int(flag.item()))
+        if not self._peer_exchange:
+            self.backend.peer_close()
+            if rank == 0:
+                print(f"[mppi_isaac_b200] peer-memory exchange unavailable ({why if not ok else 'another rank failed'}); using the NCCL all-gather")
+        dist.barrier(group=self.pg)
+
+    def close_peers(self):
+        """Collective: unmap the exchange windows (call before destroying the process group)."""
+        if getattr(self.backend, "name", "") != "cuda" or self.world <= 1:
+            return
+        if torch.distributed.is_initialized():
+            torch.cuda.synchronize(torch.device(self.device))
+            torch.distributed.barrier(group=self.pg)     # nobody is still storing into a window that is about to be freed
+        self.backend.peer_close()
+        self._peer_exchange = False
+
     def _alloc(self):
         dev, T, nu, K = self.device, self.T, self.nu, self.K
         f32 = dict(dtype=torch.float32, device=dev)
@@ -186,6 +236,8 @@ class MPPIPlanner:
     def _exchange(self):
         if self.world == 1:
             return self.partial.view(1, -1), 1
+        if self._peer_exchange:
+            return None, self.world                      # the rows are already in this rank's window (written by every K3)
         if torch.distributed.get_backend(self.pg) == "nccl":
             torch.distributed.all_gather_into_tensor(self.partials.view(-1), self.partial, group=self.pg)
         else:

@@ -7,6 +7,7 @@ Tolerances (float32 path):
 Full-size properties at BASELINE sizes (K = 10 000 / 65 536): shard-combine invariance, replica determinism,
 uniform-cost and dominant-sample limits."""
 import copy
+import os
 
 import numpy as np
 import pytest
@@ -428,3 +429,27 @@ def test_k3_shapes_and_alignment(oracle, setup, T):
     pg = partial.cpu().numpy()
     np.testing.assert_allclose(pg[:2], p_ref[:2], rtol=2e-5)
     np.testing.assert_allclose(pg[2:], p_ref[2:], rtol=0, atol=2e-5 * max(1.0, np.abs(p_ref[2:]).max()))
+
+
+@pytest.mark.gpu
+def test_peer_memory_exchange_matches_nccl_two_gpus():
+    """2 ranks (one per GPU): the exchange fused into K3/K4 over peer memory (mppib_peer_*) gives the same plan as the
+    NCCL all-gather path, eagerly and under CUDA-graph replay, and all ranks agree on the action."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    acts = {}
+    for mode in ("graph", "eager"):
+        for exch in ("peer", "nccl"):
+            env = dict(os.environ, MPPIB_EXCHANGE=exch, MPPIB_PEER_TIMEOUT_S="10")
+            out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                                  "--master-port", "29533", os.path.join(root, "tools", "dist_smoke.py"), mode],
+                                 capture_output=True, text=True, timeout=240, env=env, cwd=root)
+            assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+            line = [ln for ln in out.stdout.splitlines() if ln.startswith("ACTION ")][-1].split()
+            assert line[1] == exch, f"asked for the {exch} exchange, ran {line[1]}"
+            acts[(mode, exch)] = np.array([float(v) for v in line[2:]])
+        np.testing.assert_array_equal(acts[(mode, "peer")], acts[(mode, "nccl")])
+    np.testing.assert_array_equal(acts[("graph", "peer")], acts[("eager", "peer")])

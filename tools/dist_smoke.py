@@ -38,7 +38,7 @@ from mppi_isaac_b200.objectives import PandaReachObjective  # noqa: E402
 
 graph = len(sys.argv) > 1 and sys.argv[1] == "graph"
 planner = MPPIisaacPlanner(bench.panda_cfg(2000 * world, f"cuda:{local}"), PandaReachObjective(), use_cuda_graph=graph)
-say(f"planner built: K_local={planner.sim.num_envs} k_offset={planner.k_offset} graph={graph}")
+say(f"planner built: K_local={planner.sim.num_envs} k_offset={planner.k_offset} graph={graph} peer_exchange={planner.mppi._peer_exchange}")
 q0, goal = bench.synthetic_state()
 planner.sim.set_actor_position_by_name(goal, "goal")
 planner.sim.reset_robot_state(q0, np.zeros(7))
@@ -50,5 +50,7 @@ acts = [torch.zeros_like(a) for _ in range(world)]
 dist.all_gather(acts, a.contiguous())
 assert all(torch.equal(acts[0], t) for t in acts), "ranks disagree on the action"
 say("all ranks hold the same action")
+if rank == 0:
+    print("ACTION " + ("peer" if planner.mppi._peer_exchange else "nccl") + " " + " ".join(f"{float(v):.9e}" for v in a), flush=True)
 bench.shutdown_distributed(planner)
 say("done")
