@@ -15,11 +15,13 @@ namespace contact {
 
 enum : int { REF_STATIC = -1, REF_FREE0 = 64 };
 // free body slots
+// FB_MASS holds the INVERSE mass
 enum : int { FB_X = 0, FB_Q = 3, FB_V = 7, FB_W = 10, FB_MASS = 13, FB_HALF = 14, FB_IINV = 17, FB_R = 20, FB_IW = 29, FBN = 35 };
 // world shape slots
 enum : int { SH_R = 0, SH_C = 9, SH_HALF = 12, SH_MU = 15, SH_RAD = 16, SHN = 17 };
 // contact slots
-enum : int { CT_P = 0, CT_N = 3, CT_D = 6, CT_MU = 7, CT_LN = 8, CT_LT1 = 9, CT_LT2 = 10, CT_IDS = 11, CT_KN = 12, CT_KT1 = 13, CT_KT2 = 14, CTN = 15 };
+// CT_KN / CT_KT1 / CT_KT2 hold INVERSES: 1 / (k_n + gamma), 1 / k_t1, 1 / k_t2 (0 = row disabled); CT_T1 caches the first tangent
+enum : int { CT_P = 0, CT_N = 3, CT_D = 6, CT_MU = 7, CT_LN = 8, CT_LT1 = 9, CT_LT2 = 10, CT_IDS = 11, CT_KN = 12, CT_KT1 = 13, CT_KT2 = 14, CT_T1 = 15, CTN = 18 };
 
 struct Layout {
     int fb0, sh0, ct0, jv0, net0, total;   // offsets in slots
@@ -113,7 +115,7 @@ __device__ __forceinline__ void init(const MppibModel& m, const MppibParams& p, 
             if (m.shape_owner_kind[s] == MPPIB_OWNER_FREE && m.shape_owner[s] == f) { sg = mk(m.shape_size_sigma[s][0], m.shape_size_sigma[s][1], m.shape_size_sigma[s][2]); break; }
         const V3 half = mk(m.free_half[f][0] + 0.5f * sg.x * ns.x, m.free_half[f][1] + 0.5f * sg.y * ns.y, m.free_half[f][2] + 0.5f * sg.z * ns.z);
         const float m3 = mass / 3.0f;
-        XS(fb + FB_MASS) = mass;
+        XS(fb + FB_MASS) = 1.0f / mass;
         stx3(xs, fb + FB_HALF, lane, half);
         XS(fb + FB_IINV) = 1.0f / (m3 * (half.y * half.y + half.z * half.z));
         XS(fb + FB_IINV + 1) = 1.0f / (m3 * (half.x * half.x + half.z * half.z));
@@ -125,59 +127,72 @@ __device__ __forceinline__ void init(const MppibModel& m, const MppibParams& p, 
     for (int s = 0; s < 3 * MPPIB_MAX_SLOTS; ++s) XS(L.net0 + s) = 0.f;
 }
 
-// velocity of point pt per unit velocity of joint j:  S_j.f + S_j.n x pt  (S about the world origin)
-template <int NSLOT>
-__device__ __forceinline__ V3 joint_jac(const float* sm, int lane, int j, V3 pt) {
-    const V6 S = ld6(sm, j * NSLOT + F_S, lane);
-    return S.f + cross(S.n, pt);
-}
+// Articulation side of a contact.  The velocity of point pt per unit velocity of joint j is S_j.f + S_j.n x pt (S about the
+// world origin), so along a direction d it is  S_j.f . d + S_j.n . (pt x d):  one 6-vector dot per joint and no cross
+// product inside the chain walk.  jv0 + j: velocity correction of joint j, jv0 + nb + j: 1 / D_j, jv0 + 2 nb + j: predicted qd.
+template <int NSLOT, bool CHAIN>
+__device__ __forceinline__ int up(const MppibModel& m, int j) { return CHAIN ? j - 1 : m.parent[j]; }
 
-template <int NSLOT>
+template <int NSLOT, bool CHAIN>
 __device__ __forceinline__ V3 point_velocity(const MppibModel& m, const Layout& L, const float* sm, const float* xs, int lane, int ref, V3 pt) {
     if (ref == REF_STATIC) return mk(0, 0, 0);
     if (ref >= REF_FREE0) {
         const int fb = L.fb0 + (ref - REF_FREE0) * FBN;
         return ldx3(xs, fb + FB_V, lane) + cross(ldx3(xs, fb + FB_W, lane), pt - ldx3(xs, fb + FB_X, lane));
     }
-    V3 v = mk(0, 0, 0);
-    for (int j = ref; j >= 0; j = m.parent[j]) v = v + (XS(L.jv0 + 2 * m.nb + j) + XS(L.jv0 + j)) * joint_jac<NSLOT>(sm, lane, j, pt);
-    return v;
+    V3 w = mk(0, 0, 0), v = mk(0, 0, 0);       // spatial velocity of the link = sum over the chain of qd_j S_j
+    for (int j = ref; j >= 0; j = up<NSLOT, CHAIN>(m, j)) {
+        const float qd = XS(L.jv0 + 2 * m.nb + j) + XS(L.jv0 + j);
+        const V6 S = ld6(sm, j * NSLOT + F_S, lane);
+        w = w + qd * S.n; v = v + qd * S.f;
+    }
+    return v + cross(w, pt);
 }
 
-template <int NSLOT>
+template <int NSLOT, bool CHAIN>
 __device__ __forceinline__ float inv_mass(const MppibModel& m, const Layout& L, const float* sm, const float* xs, int lane, int refA, int refB, V3 pt, V3 dir) {
     float k = 0.f;
+    const V3 mom = cross(pt, dir);
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
         const int ref = e == 0 ? refA : refB;
         if (ref >= 0 && ref < REF_FREE0) {
-            for (int j = ref; j >= 0; j = m.parent[j]) { const float jd = dot(joint_jac<NSLOT>(sm, lane, j, pt), dir); k += jd * jd / XS(L.jv0 + m.nb + j); }
+            for (int j = ref; j >= 0; j = up<NSLOT, CHAIN>(m, j)) {
+                const V6 S = ld6(sm, j * NSLOT + F_S, lane);
+                const float jd = dot(S.f, dir) + dot(S.n, mom);
+                k += jd * jd * XS(L.jv0 + m.nb + j);
+            }
         } else if (ref >= REF_FREE0) {
             const int fb = L.fb0 + (ref - REF_FREE0) * FBN;
             const V3 r = pt - ldx3(xs, fb + FB_X, lane);
             const V3 rxn = cross(r, dir);
             const S3 Iw = {XS(fb + FB_IW), XS(fb + FB_IW + 1), XS(fb + FB_IW + 2), XS(fb + FB_IW + 3), XS(fb + FB_IW + 4), XS(fb + FB_IW + 5)};
-            k += 1.0f / XS(fb + FB_MASS) + dot(cross(mul(Iw, rxn), r), dir);
+            k += XS(fb + FB_MASS) + dot(cross(mul(Iw, rxn), r), dir);
         }
     }
     return k;
 }
 
-template <int NSLOT>
-__device__ __forceinline__ void apply_impulse(const MppibModel& m, const Layout& L, const float* sm, float* xs, int lane, int refA, int refB, V3 pt, V3 dir, float mag) {
+// impulse vector P at pt: +P on side A, -P on side B
+template <int NSLOT, bool CHAIN>
+__device__ __forceinline__ void apply_impulse(const MppibModel& m, const Layout& L, const float* sm, float* xs, int lane, int refA, int refB, V3 pt, V3 P) {
+    const V3 mom = cross(pt, P);
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
         const int ref = e == 0 ? refA : refB;
-        const float sgn = e == 0 ? mag : -mag;
+        const float sgn = e == 0 ? 1.0f : -1.0f;
         if (ref >= 0 && ref < REF_FREE0) {
-            for (int j = ref; j >= 0; j = m.parent[j]) XS(L.jv0 + j) += sgn * dot(joint_jac<NSLOT>(sm, lane, j, pt), dir) / XS(L.jv0 + m.nb + j);
+            for (int j = ref; j >= 0; j = up<NSLOT, CHAIN>(m, j)) {
+                const V6 S = ld6(sm, j * NSLOT + F_S, lane);
+                XS(L.jv0 + j) += sgn * (dot(S.f, P) + dot(S.n, mom)) * XS(L.jv0 + m.nb + j);
+            }
         } else if (ref >= REF_FREE0) {
             const int fb = L.fb0 + (ref - REF_FREE0) * FBN;
             const V3 r = pt - ldx3(xs, fb + FB_X, lane);
-            const float im = sgn / XS(fb + FB_MASS);
-            XS(fb + FB_V) += im * dir.x; XS(fb + FB_V + 1) += im * dir.y; XS(fb + FB_V + 2) += im * dir.z;
+            const float im = sgn * XS(fb + FB_MASS);
+            XS(fb + FB_V) += im * P.x; XS(fb + FB_V + 1) += im * P.y; XS(fb + FB_V + 2) += im * P.z;
             const S3 Iw = {XS(fb + FB_IW), XS(fb + FB_IW + 1), XS(fb + FB_IW + 2), XS(fb + FB_IW + 3), XS(fb + FB_IW + 4), XS(fb + FB_IW + 5)};
-            const V3 dw = mul(Iw, cross(r, dir));
+            const V3 dw = mul(Iw, cross(r, P));
             XS(fb + FB_W) += sgn * dw.x; XS(fb + FB_W + 1) += sgn * dw.y; XS(fb + FB_W + 2) += sgn * dw.z;
         }
     }
@@ -329,11 +344,12 @@ __device__ __forceinline__ int detect(const MppibModel& m, const Layout& L, floa
 }
 
 // Gauss-Seidel soft-constraint solve on the predicted velocities; fills dqv (joint velocity corrections) and the net forces
-template <int NSLOT>
+template <int NSLOT, bool CHAIN>
 __device__ __forceinline__ void solve(const MppibModel& m, const Layout& L, const float* sm, float* xs, int lane, int nc, float h) {
     const float kp = m.contact_kp, kd = m.contact_kd;
-    const float gamma = 1.0f / (h * (h * kp + kd)), beta = h * kp / (h * kp + kd);
-    // effective inverse masses along the contact frame are constant during the sweeps (poses are frozen within a substep)
+    const float gamma = 1.0f / (h * (h * kp + kd)), beta = h * kp / (h * kp + kd), ih = 1.0f / h;
+    // per contact, once: tangent frame, effective inverse masses along it (poses are frozen within a substep) -> stored as
+    // the reciprocals the sweeps multiply with, and the velocity bias of the normal row
 #pragma unroll 1
     for (int c = 0; c < nc; ++c) {
         const int cb = L.ct0 + c * CTN;
@@ -341,43 +357,48 @@ __device__ __forceinline__ void solve(const MppibModel& m, const Layout& L, cons
         const int refA = (ids & 0xFF) - 2, refB = ((ids >> 8) & 0xFF) - 2;
         const V3 pt = ldx3(xs, cb + CT_P, lane), n = ldx3(xs, cb + CT_N, lane);
         V3 t1, t2; tangents(n, t1, t2);
-        XS(cb + CT_KN) = inv_mass<NSLOT>(m, L, sm, xs, lane, refA, refB, pt, n);
-        XS(cb + CT_KT1) = inv_mass<NSLOT>(m, L, sm, xs, lane, refA, refB, pt, t1);
-        XS(cb + CT_KT2) = inv_mass<NSLOT>(m, L, sm, xs, lane, refA, refB, pt, t2);
+        const float kn = inv_mass<NSLOT, CHAIN>(m, L, sm, xs, lane, refA, refB, pt, n);
+        const float kt1 = inv_mass<NSLOT, CHAIN>(m, L, sm, xs, lane, refA, refB, pt, t1);
+        const float kt2 = inv_mass<NSLOT, CHAIN>(m, L, sm, xs, lane, refA, refB, pt, t2);
+        XS(cb + CT_KN) = kn > 0.f ? 1.0f / (kn + gamma) : 0.f;
+        XS(cb + CT_KT1) = kt1 > 0.f ? 1.0f / kt1 : 0.f;
+        XS(cb + CT_KT2) = kt2 > 0.f ? 1.0f / kt2 : 0.f;
+        stx3(xs, cb + CT_T1, lane, t1);
+        const float d = XS(cb + CT_D);
+        XS(cb + CT_D) = d > 0.f ? fminf(beta * d * ih, m.max_depen) : d * ih;      // from here on: the bias velocity
     }
 #pragma unroll 1
     for (int it = 0; it < m.contact_iters; ++it) {
 #pragma unroll 1
         for (int c = 0; c < nc; ++c) {
             const int cb = L.ct0 + c * CTN;
-            const float kn = XS(cb + CT_KN);
-            if (!(kn > 0.f)) continue;
+            const float ikn = XS(cb + CT_KN);
+            if (!(ikn > 0.f)) continue;
             const int ids = __float_as_int(XS(cb + CT_IDS));
             const int refA = (ids & 0xFF) - 2, refB = ((ids >> 8) & 0xFF) - 2;
-            const V3 pt = ldx3(xs, cb + CT_P, lane), n = ldx3(xs, cb + CT_N, lane);
-            const float d = XS(cb + CT_D), mu = XS(cb + CT_MU), kt1 = XS(cb + CT_KT1), kt2 = XS(cb + CT_KT2);
-            V3 t1, t2; tangents(n, t1, t2);
+            const V3 pt = ldx3(xs, cb + CT_P, lane), n = ldx3(xs, cb + CT_N, lane), t1 = ldx3(xs, cb + CT_T1, lane);
+            const V3 t2 = cross(n, t1);
+            const float bias = XS(cb + CT_D), mu = XS(cb + CT_MU), ikt1 = XS(cb + CT_KT1), ikt2 = XS(cb + CT_KT2);
             // one visit = normal row + two friction rows solved from the SAME relative velocity, then one impulse application
-            const V3 vr = point_velocity<NSLOT>(m, L, sm, xs, lane, refA, pt) - point_velocity<NSLOT>(m, L, sm, xs, lane, refB, pt);
-            const float bias = d > 0.f ? fminf(beta * d / h, m.max_depen) : d / h;
+            const V3 vr = point_velocity<NSLOT, CHAIN>(m, L, sm, xs, lane, refA, pt) - point_velocity<NSLOT, CHAIN>(m, L, sm, xs, lane, refB, pt);
             const float ln = XS(cb + CT_LN), lt1 = XS(cb + CT_LT1), lt2 = XS(cb + CT_LT2);
-            const float ln_new = fmaxf(0.f, ln + (-dot(vr, n) + bias - gamma * ln) / (kn + gamma));
+            const float ln_new = fmaxf(0.f, ln + (-dot(vr, n) + bias - gamma * ln) * ikn);
             const float lim = mu * ln_new;
-            const float lt1_new = kt1 > 0.f ? fminf(fmaxf(lt1 - dot(vr, t1) / kt1, -lim), lim) : lt1;
-            const float lt2_new = kt2 > 0.f ? fminf(fmaxf(lt2 - dot(vr, t2) / kt2, -lim), lim) : lt2;
+            const float lt1_new = ikt1 > 0.f ? fminf(fmaxf(lt1 - dot(vr, t1) * ikt1, -lim), lim) : lt1;
+            const float lt2_new = ikt2 > 0.f ? fminf(fmaxf(lt2 - dot(vr, t2) * ikt2, -lim), lim) : lt2;
             const V3 dP = (ln_new - ln) * n + (lt1_new - lt1) * t1 + (lt2_new - lt2) * t2;
             XS(cb + CT_LN) = ln_new; XS(cb + CT_LT1) = lt1_new; XS(cb + CT_LT2) = lt2_new;
-            apply_impulse<NSLOT>(m, L, sm, xs, lane, refA, refB, pt, dP, 1.0f);
+            apply_impulse<NSLOT, CHAIN>(m, L, sm, xs, lane, refA, refB, pt, dP);
         }
     }
     for (int s = 0; s < 3 * MPPIB_MAX_SLOTS; ++s) XS(L.net0 + s) = 0.f;
-    const float ih = 1.0f / h;
     for (int c = 0; c < nc; ++c) {
         const int cb = L.ct0 + c * CTN;
         const int ids = __float_as_int(XS(cb + CT_IDS));
         const int slotA = ((ids >> 16) & 0xFF) - 1, slotB = ((ids >> 24) & 0xFF) - 1;
-        const V3 n = ldx3(xs, cb + CT_N, lane);
-        V3 t1, t2; tangents(n, t1, t2);
+        if (slotA < 0 && slotB < 0) continue;
+        const V3 n = ldx3(xs, cb + CT_N, lane), t1 = ldx3(xs, cb + CT_T1, lane);
+        const V3 t2 = cross(n, t1);
         const V3 F = ih * (XS(cb + CT_LN) * n + XS(cb + CT_LT1) * t1 + XS(cb + CT_LT2) * t2);
         if (slotA >= 0) { XS(L.net0 + 3 * slotA) += F.x; XS(L.net0 + 3 * slotA + 1) += F.y; XS(L.net0 + 3 * slotA + 2) += F.z; }
         if (slotB >= 0) { XS(L.net0 + 3 * slotB) -= F.x; XS(L.net0 + 3 * slotB + 1) -= F.y; XS(L.net0 + 3 * slotB + 2) -= F.z; }

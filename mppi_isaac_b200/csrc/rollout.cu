@@ -457,7 +457,7 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
                     const V6 U = mul(IA, S);
                     const float Dj = dot6(S, U) + dimp;
                     const float invD = __frcp_rn(Dj);
-                    if (CONTACT) xs[(L.jv0 + nb + i) * 32 + lane] = fmaxf(Dj, 1e-6f);   // joint compliance of the contact solve
+                    if (CONTACT) xs[(L.jv0 + nb + i) * 32 + lane] = __frcp_rn(fmaxf(Dj, 1e-6f));   // joint compliance 1 / D_j of the contact solve
                     const float uu = tau - dot6(S, pA);
                     st6(sm, i * NSLOT + F_U, lane, U);
                     SM(i, F_INVD) = invD; SM(i, F_UU) = uu;
@@ -507,7 +507,7 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
                     xs[(fb + contact::FB_V) * 32 + lane] += h * m.gravity[0]; xs[(fb + contact::FB_V + 1) * 32 + lane] += h * m.gravity[1];
                     xs[(fb + contact::FB_V + 2) * 32 + lane] += h * m.gravity[2];
                 }
-                contact::solve<NSLOT>(m, L, sm, xs, lane, nc, h);
+                contact::solve<NSLOT, CHAIN>(m, L, sm, xs, lane, nc, h);
             }
             // ------------------------------------------------------------------ integrate
             for (int i = 0; i < nb; ++i) {
