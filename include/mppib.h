@@ -267,6 +267,14 @@ int32_t mppib_peer_alloc(MppibHandle h, int32_t world, int32_t rank, unsigned ch
 int32_t mppib_peer_open(MppibHandle h, int32_t peer, const unsigned char* ipc_handle_h);
 int32_t mppib_peer_close(MppibHandle h);
 
+/* Fused pose-reach cost term for Objectives (optional helper, no handle needed; the device is the one of the pointers /
+ * current context).  cost[i] (+)= w_pos |a[i,0:3] - b[i,0:3]| + w_ori |euler_ZYX(R(a[i,3:7]))[0:2]| for i < n, the
+ * quaternion read real-first as the reference's Objectives do (examples/panda/planner.py:22-40).  a and b are strided
+ * views: element (i, c) of a lives at a[i*a_si + c*a_sr] (the obs layout gives a_si = 1, a_sr = T*K; a broadcast goal has
+ * b_si = 0).  b may be NULL when w_pos == 0.                                                                          */
+int32_t mppib_cost_pose(int64_t n, const float* a, int64_t a_si, int64_t a_sr, const float* b, int64_t b_si,
+                        int64_t b_sr, float w_pos, float w_ori, float* cost, int32_t accumulate, void* stream);
+
 /* shift U by one step: U[t] <- U[t+1], U[T-1] <- u_init (mppi_torch command() prologue);
  * increments *plan_ctr (device, nullable) by one.                                            */
 int32_t mppib_shift(MppibHandle h, float* U, uint32_t* plan_ctr, void* stream);

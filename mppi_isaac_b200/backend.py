@@ -22,7 +22,7 @@ SYMBOLS = [
     "mppib_abi_version", "mppib_last_error", "mppib_create", "mppib_destroy", "mppib_set_params",
     "mppib_set_model", "mppib_state_size", "mppib_obs_size", "mppib_sample", "mppib_rollout",
     "mppib_reduce", "mppib_finalize", "mppib_shift", "mppib_noise_library", "mppib_sample_library",
-    "mppib_peer_alloc", "mppib_peer_open", "mppib_peer_close",
+    "mppib_peer_alloc", "mppib_peer_open", "mppib_peer_close", "mppib_cost_pose",
 ]
 
 

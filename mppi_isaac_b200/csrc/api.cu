@@ -231,4 +231,10 @@ int32_t mppib_shift(MppibHandle h, float* U, uint32_t* plan_ctr, void* stream) {
     return launch_shift(h, U, plan_ctr, (cudaStream_t)stream);
 }
 
+int32_t mppib_cost_pose(int64_t n, const float* a, int64_t a_si, int64_t a_sr, const float* b, int64_t b_si, int64_t b_sr, float w_pos, float w_ori,
+                        float* cost, int32_t accumulate, void* stream) {
+    MPPIB_REQUIRE(n >= 0 && a && cost && (b || w_pos == 0.f), "mppib_cost_pose: null argument");
+    return launch_cost_pose(n, a, a_si, a_sr, b, b_si, b_sr, w_pos, w_ori, cost, accumulate, (cudaStream_t)stream);
+}
+
 }  // extern "C"

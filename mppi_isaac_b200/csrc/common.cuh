@@ -74,6 +74,8 @@ int launch_rollout(MppibContext* c, const float* state0, const float* root0, flo
 int launch_reduce(MppibContext* c, const float* cost, const float* x, const float* U, float* partial, cudaStream_t s);
 int launch_finalize(MppibContext* c, const float* partials, int G, float* U, float* action_out, float* stats, cudaStream_t s);
 int launch_shift(MppibContext* c, float* U, uint32_t* plan_ctr, cudaStream_t s);
+int launch_cost_pose(long long n, const float* a, long long a_si, long long a_sr, const float* b, long long b_si, long long b_sr, float w_pos,
+                     float w_ori, float* cost, int accumulate, cudaStream_t s);
 
 static inline int obs_item_width(const MppibModel& m, int kind) {
     return kind == MPPIB_OBS_DOF_STATE ? 2 * m.nb : (kind == MPPIB_OBS_CONTACT ? 3 : 13);

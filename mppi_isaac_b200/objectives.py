@@ -15,31 +15,18 @@ Every term is row-wise over dim 0, so the functions work unchanged on the (K, .)
 """
 import torch
 
+from .ops import _zyx_first_two, pose_cost
 from .utils.conversions import matrix_to_euler_angles, quaternion_to_matrix, quaternion_to_yaw
-
-
-def _zyx_first_two(quat: torch.Tensor) -> torch.Tensor:
-    """|euler_ZYX(R(q))[:, 0:2]| for a (N,4) quaternion handed REAL-FIRST to the matrix formula (so the xyzw tensor of
-    the simulator is read as w=x, x=y, y=z, z=w: the reference's literal arithmetic, Appendix A #11).  Only the three
-    matrix entries the two angles need are formed -- same numbers as
-    ``matrix_to_euler_angles(quaternion_to_matrix(q), "ZYX")[:, 0:2]`` with a fraction of the element-wise kernels."""
-    r, i, j, k = quat[:, 0], quat[:, 1], quat[:, 2], quat[:, 3]
-    two_s = 2.0 / (quat * quat).sum(-1)
-    m00 = 1 - two_s * (j * j + k * k)
-    m10 = two_s * (i * j + k * r)
-    m20 = two_s * (i * k - j * r)
-    yaw = torch.atan2(m10, m00)
-    pitch = torch.asin(-m20)
-    return torch.sqrt(yaw * yaw + pitch * pitch)
 
 
 class PandaReachObjective:
     """w_goal * |p_ee - p_goal| + w_ori * |euler_ZYX(R(q_ee))[:2]| for the stick tip."""
 
-    def __init__(self, cfg=None, actor: str = "panda", link: str = "panda_ee_tip", goal: str = "goal", literal: bool = False):
+    def __init__(self, cfg=None, actor: str = "panda", link: str = "panda_ee_tip", goal: str = "goal", literal: bool = False, fused: bool = True):
         self.weights = {"robot_to_goal": 1.0, "robot_ori": 0.5}
         self.actor, self.link, self.goal = actor, link, goal
         self.literal = literal          # True: the reference's op-by-op formulation (full 3x3 matrix, stack, norm)
+        self.fused = fused              # True: both terms in one kernel (ops.pose_cost); False: torch ops, same arithmetic
 
     def reset(self):
         pass
@@ -47,6 +34,8 @@ class PandaReachObjective:
     def compute_cost(self, sim):
         ee = sim.get_actor_link_by_name(self.actor, self.link)
         goal = sim.get_actor_position_by_name(self.goal)
+        if self.fused and not self.literal:
+            return pose_cost(ee, goal, self.weights["robot_to_goal"], self.weights["robot_ori"])
         dist = torch.linalg.norm(ee[:, 0:3] - goal[:, 0:3], axis=1)
         if self.literal:
             # the reference hands the xyzw quaternion to a real-first API; reproduced literally (Appendix A #11)

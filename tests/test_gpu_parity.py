@@ -453,3 +453,35 @@ def test_peer_memory_exchange_matches_nccl_two_gpus():
             acts[(mode, exch)] = np.array([float(v) for v in line[2:]])
         np.testing.assert_array_equal(acts[(mode, "peer")], acts[(mode, "nccl")])
     np.testing.assert_array_equal(acts[("graph", "peer")], acts[("eager", "peer")])
+
+
+@pytest.mark.gpu
+def test_fused_pose_cost_matches_torch_ops():
+    """ops.pose_cost (one CUDA kernel) == the torch-op formulation of the reference's panda cost (examples/panda/planner.py:22-40)
+    on the obs layout (stride 1 along N), a stride-0 broadcast goal, a dense (N,13) tensor, and with accumulation; and the
+    fused Objective gives the same plan cost as the op-by-op one (literal=True: full matrix -> euler route)."""
+    from mppi_isaac_b200 import ops
+    from mppi_isaac_b200.objectives import PandaReachObjective
+    g = torch.Generator(device="cuda").manual_seed(11)
+    T, K = 5, 4000
+    rows = torch.randn((13, T, K), device="cuda", generator=g)
+    rows[3:7] /= rows[3:7].norm(dim=0, keepdim=True)
+    a = rows.view(13, T * K).t()                                   # (N,13) strides (1, N): the RolloutSim view
+    goal = torch.tensor([0.4, -0.1, 0.6], device="cuda").unsqueeze(0).expand(T * K, 3)
+    ref = ops.pose_cost_torch(a, goal, 1.0, 0.5)
+    out = ops.pose_cost(a, goal, 1.0, 0.5)
+    torch.testing.assert_close(out, ref, rtol=2e-6, atol=2e-6)
+    dense = a.contiguous()
+    per_row = torch.randn((T * K, 3), device="cuda", generator=g)
+    torch.testing.assert_close(ops.pose_cost(dense, per_row, 2.0, 0.0), ops.pose_cost_torch(dense, per_row, 2.0, 0.0), rtol=2e-6, atol=2e-6)
+    acc = ref.clone()
+    ops.pose_cost(a, None, 0.0, 2.0, out=acc, accumulate=True)
+    torch.testing.assert_close(acc, ref + ops.pose_cost_torch(a, None, 0.0, 2.0), rtol=2e-6, atol=2e-6)
+
+    class Sim:                                                      # the two getters the Objective uses
+        def get_actor_link_by_name(self, *_):
+            return a
+        def get_actor_position_by_name(self, *_):
+            return goal
+    fused, literal = PandaReachObjective(fused=True).compute_cost(Sim()), PandaReachObjective(literal=True).compute_cost(Sim())
+    torch.testing.assert_close(fused, literal, rtol=1e-4, atol=2e-5)
