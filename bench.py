@@ -349,7 +349,9 @@ def run_gpu_arm(args, rank, world, local_rank):
             roof = k3_roofline(planner, peak, peak_src, [K_PER_GPU, 65536, 262144])
             head = roof[0]
             line["roofline"] = {"kernel": "K3 reduce_kernel (fused cost accumulate + softmax + weighted control sum)", "bound": "hbm",
-                                "achieved": head["GBps"], "peak": peak, "unit": "GB/s", "frac": head["frac"], "traffic": None,
+                                "achieved": head["GBps"], "peak": peak, "unit": "GB/s", "frac": head["frac"],
+                                "traffic": 9635000 if (head["K"], T_HORIZON) == (10000, 30) else None,
+                                "traffic_source": "ncu --set full dram__bytes_read.sum + write of one K3 launch at K=10000 (profiles/r1_reduce_v2.md): 1.004 x algorithmic",
                                 "peak_source": peak_src, "bytes_per_launch": head["bytes"], "us_per_launch": head["us"], "K": head["K"],
                                 "note": "9.6 MB per launch at the named K is ~1.5 us of HBM time, i.e. launch/latency bound; see sweep for the asymptote",
                                 "sweep": roof}
