@@ -303,3 +303,58 @@ def test_fast_wire_codec_matches_torch_save_load():
         back = bytes_to_torch(enc(like, v))
         assert back.dtype == torch.float32 and back.shape == (7,) and np.array_equal(back.numpy(), v)
     assert enc._tpl[((7,), "cpu")] is not None
+
+
+def test_rpc_server_client_speak_the_zerorpc_wire_format():
+    """utils/rpc.py: ROUTER/DEALER framing, msgpack [header, name, args] events, OK / ERR answers on the request's channel,
+    heart-beats answered in kind -- the request/reply subset of zerorpc v3 the reference uses
+    (examples/panda/planner.py:46-48, world.py:21-22,35-50).  The planner methods carry torch.save bytes unchanged."""
+    import threading
+    import msgpack
+    import zmq
+    from mppi_isaac_b200.utils.rpc import RemoteError, RpcClient, RpcServer
+    from mppi_isaac_b200.utils.transport import bytes_to_torch, torch_to_bytes
+
+    class FakePlanner:
+        def compute_action_tensor(self, dof_bytes, root_bytes):
+            return torch_to_bytes(bytes_to_torch(dof_bytes)[0, 0:3] + bytes_to_torch(root_bytes).sum())
+        def update_weights(self, weights):
+            self.weights = weights
+            return None
+        def boom(self):
+            raise ValueError("bad thing")
+
+    planner = FakePlanner()
+    server = RpcServer(planner).bind("tcp://127.0.0.1:*")
+    endpoint = server.last_endpoint
+    th = threading.Thread(target=server.run, daemon=True)
+    th.start()
+    try:
+        cli = RpcClient(endpoint, timeout_s=10)
+        dof, root = torch.arange(14.0).reshape(1, 14), torch.ones(1, 2, 13)
+        out = bytes_to_torch(cli.compute_action_tensor(torch_to_bytes(dof), torch_to_bytes(root)))
+        assert torch.equal(out, dof[0, 0:3] + 26.0)
+        assert cli.update_weights({"robot_to_goal": 2.0, "robot_ori": 0.25}) is None and planner.weights["robot_ori"] == 0.25
+        with pytest.raises(RemoteError, match="ValueError: bad thing"):
+            cli.boom()
+        with pytest.raises(RemoteError, match="no such method"):
+            cli.not_there()
+        assert bytes_to_torch(cli.compute_action_tensor(torch_to_bytes(dof), torch_to_bytes(root))).shape == (3,)   # still serving
+        # raw frames, as a zerorpc client would put them on the wire
+        raw = zmq.Context.instance().socket(zmq.DEALER)
+        raw.setsockopt(zmq.LINGER, 0)
+        raw.connect(endpoint)
+        raw.send_multipart([b"", msgpack.packb([{"message_id": "abc", "v": 3}, "_zpc_hb", []], use_bin_type=True)])
+        assert raw.poll(5000)
+        frames = raw.recv_multipart()
+        header, name, args = msgpack.unpackb(frames[-1], raw=False)
+        assert frames[0] == b"" and name == "_zpc_hb" and header["response_to"] == "abc" and header["v"] == 3
+        raw.send_multipart([b"", msgpack.packb([{"message_id": "m2", "v": 3}, "update_weights", [{"a": 1.0}]], use_bin_type=True)])
+        assert raw.poll(5000)
+        header, name, args = msgpack.unpackb(raw.recv_multipart()[-1], raw=False)
+        assert name == "OK" and args == [None] and header["response_to"] == "m2" and "message_id" in header
+        raw.close()
+        cli.close()
+    finally:
+        server.stop()
+        th.join(timeout=5)
