@@ -363,6 +363,10 @@ def run_gpu_arm(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": k_s * T_HORIZON / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n_cpu} plans of K={k_s} of the K=10000 workload, CPU restatement (oracle/) on {cores} threads",
                                     "plan_hz_at_K10000_est": 1.0 / (dt * K_PER_GPU / k_s)}
+            # one host thread: how the reference configures PhysX (num_threads never set, isaacgym_wrapper.py:21-39)
+            dt1 = cpu_plan_rate(256, 3, 1, 1)
+            line["cpu_baseline"]["one_thread"] = {"value": 256 * T_HORIZON / dt1, "unit": UNIT, "sample": "3 plans of K=256 on 1 thread",
+                                                  "plan_hz_at_K10000_est": 1.0 / (dt1 * K_PER_GPU / 256)}
         print(json.dumps(line), flush=True)
     if world > 1:
         shutdown_distributed(planner)
