@@ -50,6 +50,6 @@ for name, cfgname, K, obj, q in CASES:
     except Exception as e:  # noqa: BLE001
         kt = {"rollout_us": float("nan"), "cost_objective_torch_us": float("nan"), "reduce_us_warm_l2": float("nan")}
     print(f"| {name} | {K} | {T} | {nu} | {ms:.3f} | {1e3 / ms:.0f} | {K * T * 1e3 / ms:.3e} | {kt['rollout_us']:.0f} | "
-          f"{kt['cost_objective_torch_us']:.0f} | {kt['reduce_us_warm_l2']:.1f} |", flush=True)
+          f"{kt['cost_objective_us']:.0f} | {kt['reduce_us_warm_l2']:.1f} |", flush=True)
     del planner
     torch.cuda.empty_cache()
