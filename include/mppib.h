@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MPPIB_ABI_VERSION 7
+#define MPPIB_ABI_VERSION 8
 
 #define MPPIB_MAX_BODIES 16   /* moving (1-DoF) bodies of the articulation            */
 #define MPPIB_MAX_LINKS  32   /* URDF links whose state can be observed               */
@@ -160,6 +160,8 @@ typedef struct MppibModel {
     float   contact_margin;                /* speculative-contact distance between boxes [m] (PhysX contact_offset 0.01) */
     int32_t contact_iters;                 /* Gauss-Seidel sweeps over the contact set per substep             */
     int32_t nactors;                       /* rows of the root-state buffer                                    */
+    int32_t max_contacts;                  /* contact points kept per rollout and substep: 1..MPPIB_MAX_CONTACTS (sized by the host so
+                                              that the rollout's working set fits the 227 KB of shared memory of an SM)         */
 } MppibModel;
 
 typedef struct MppibObsItem {

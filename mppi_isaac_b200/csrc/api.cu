@@ -26,6 +26,7 @@ static int validate(const MppibModel* m, const MppibParams* p) {
         if (m->shape_owner_kind[s] == MPPIB_OWNER_LINK) MPPIB_REQUIRE(m->shape_owner[s] >= -1 && m->shape_owner[s] < m->nb, "shape %d: body index out of range", s);
         if (m->shape_owner_kind[s] == MPPIB_OWNER_FREE) MPPIB_REQUIRE(m->shape_owner[s] >= 0 && m->shape_owner[s] < m->nfree, "shape %d: free body index out of range", s);
     }
+    MPPIB_REQUIRE((m->nshapes == 0 && m->nfree == 0) || (m->max_contacts >= 1 && m->max_contacts <= MPPIB_MAX_CONTACTS), "max_contacts %d out of range 1..%d", m->max_contacts, MPPIB_MAX_CONTACTS);
     for (int f = 0; f < m->nfree; ++f) MPPIB_REQUIRE(m->free_actor[f] >= 0 && m->free_actor[f] < m->nactors && m->free_mass[f] > 0.f, "free body %d invalid", f);
     for (int i = 0; i < m->nb; ++i) {
         MPPIB_REQUIRE(m->parent[i] >= -1 && m->parent[i] < i, "parent[%d]=%d is not topologically sorted", i, m->parent[i]);

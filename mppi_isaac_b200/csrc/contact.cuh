@@ -25,8 +25,8 @@ enum : int { CT_P = 0, CT_N = 3, CT_D = 6, CT_MU = 7, CT_LN = 8, CT_LT1 = 9, CT_
 
 struct Layout {
     int fb0, sh0, ct0, jv0, net0, total;   // offsets in slots
-    __host__ __device__ Layout(int nb, int nfree, int nshapes) {
-        fb0 = 0; sh0 = fb0 + nfree * FBN; ct0 = sh0 + nshapes * SHN; jv0 = ct0 + MPPIB_MAX_CONTACTS * CTN;
+    __host__ __device__ Layout(int nb, int nfree, int nshapes, int max_contacts) {
+        fb0 = 0; sh0 = fb0 + nfree * FBN; ct0 = sh0 + nshapes * SHN; jv0 = ct0 + max_contacts * CTN;
         net0 = jv0 + 3 * nb; total = net0 + 3 * MPPIB_MAX_SLOTS;
     }
 };
@@ -205,8 +205,8 @@ __device__ __forceinline__ int shape_ref(const MppibModel& m, int s) {
     return REF_STATIC;
 }
 
-__device__ __forceinline__ void add_contact(const Layout& L, float* xs, int lane, int& nc, int refA, int refB, int slotA, int slotB, V3 pt, V3 n, float d, float mu) {
-    if (nc >= MPPIB_MAX_CONTACTS) return;
+__device__ __forceinline__ void add_contact(const MppibModel& m, const Layout& L, float* xs, int lane, int& nc, int refA, int refB, int slotA, int slotB, V3 pt, V3 n, float d, float mu) {
+    if (nc >= m.max_contacts) return;
     const int cb = L.ct0 + nc * CTN;
     ++nc;
     stx3(xs, cb + CT_P, lane, pt); stx3(xs, cb + CT_N, lane, n);
@@ -248,8 +248,8 @@ __device__ __forceinline__ void points_in_box(const MppibModel& m, const Layout&
         const float xa = ax == 0 ? x.x : (ax == 1 ? x.y : x.z);
         const float sg = xa >= 0.f ? 1.f : -1.f;
         const V3 n = ax == 0 ? mk(sg * Rb.m00, sg * Rb.m10, sg * Rb.m20) : (ax == 1 ? mk(sg * Rb.m01, sg * Rb.m11, sg * Rb.m21) : mk(sg * Rb.m02, sg * Rb.m12, sg * Rb.m22));
-        if (!flip) add_contact(L, xs, lane, nc, refa, refb, slota, slotb, pt, n, pen, mu);
-        else add_contact(L, xs, lane, nc, refb, refa, slotb, slota, pt, mk(-n.x, -n.y, -n.z), pen, mu);
+        if (!flip) add_contact(m, L, xs, lane, nc, refa, refb, slota, slotb, pt, n, pen, mu);
+        else add_contact(m, L, xs, lane, nc, refb, refa, slotb, slota, pt, mk(-n.x, -n.y, -n.z), pen, mu);
     }
 }
 
@@ -321,7 +321,7 @@ __device__ __forceinline__ int detect(const MppibModel& m, const Layout& L, floa
             for (int idx = 0; idx < 8; ++idx) {
                 const int ix = (idx >> 2) * 2 - 1, iy = ((idx >> 1) & 1) * 2 - 1, iz = (idx & 1) * 2 - 1;
                 const V3 pt = mul(Ra, mk(ix * ha.x, iy * ha.y, iz * ha.z)) + ca;
-                if (pt.z < m.ground_margin) add_contact(L, xs, lane, nc, shape_ref(m, a), REF_STATIC, m.shape_slot[a], -1, pt, mk(0, 0, 1), -pt.z, mu);
+                if (pt.z < m.ground_margin) add_contact(m, L, xs, lane, nc, shape_ref(m, a), REF_STATIC, m.shape_slot[a], -1, pt, mk(0, 0, 1), -pt.z, mu);
             }
         }
         for (int b = 0; b < ns; ++b) {

@@ -142,18 +142,19 @@ enum : int {
     F_PB = 21,    // 6  bias force v x* I v
     F_U = 27,     // 6  IA S
     F_INVD = 33, F_UU = 34, F_QDD = 35, F_Q = 36, F_QD = 37, F_TGT = 38, F_SAT = 39,
-    // observation scratch: world rotation, origin, spatial velocity, quaternion of the body at the END of a model step.  It is
+    // observation scratch: quaternion, world rotation, origin, spatial velocity of the body at the END of a model step.  It is
     // filled by the first sweep 1 of the NEXT step (same state, same kinematics) so that no extra kinematics pass is needed
-    F_OR = 40, F_OO = 49, F_OV = 52, F_OQ = 58,
+    F_OQ = 40, F_OR = 44, F_OO = 53, F_OV = 56,
     NSLOT_CHAIN = 62,
-    // general trees (and contact scenes) only
-    F_R = 62,     // 9  world rotation of the body (parent lookup)
-    F_O = 71,     // 3
-    F_V = 74,     // 6  spatial velocity
-    F_IA = 80,    // 21 articulated inertia accumulator
-    F_PA = 101,   // 6  articulated bias accumulator
-    F_ACC = 107,  // 6  spatial acceleration
-    NSLOT_TREE = 113,
+    // general trees (and contact scenes) keep every body's world frame for the parent lookup / the shapes: the SAME slots as the
+    // observation scratch (when the observation is taken, the frame of the current sweep 1 IS the observed frame)
+    F_R = F_OR,   // 9  world rotation of the body
+    F_O = F_OO,   // 3
+    F_V = F_OV,   // 6  spatial velocity
+    F_IA = 62,    // 21 articulated inertia accumulator
+    F_PA = 83,    // 6  articulated bias accumulator
+    F_ACC = 89,   // 6  spatial acceleration
+    NSLOT_TREE = 95,
 };
 
 #define SM(i, f) sm[((i) * NSLOT + (f)) * 32 + lane]
@@ -241,7 +242,7 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
         SM(i, F_QD) = state0 ? state0[nb + i] : state[(size_t)(nb + i) * K + k];
     }
     float* xs = sm + (size_t)nb * NSLOT * 32;             // free bodies / shapes / contacts (CONTACT kernels only)
-    const contact::Layout L(nb, m.nfree, m.nshapes);
+    const contact::Layout L(nb, m.nfree, m.nshapes, m.max_contacts);
     if (CONTACT) contact::init(m, p, L, xs, lane, p.k_offset + (uint32_t)k, root0, state, state0 != nullptr, K, k);
     Frame base;
     const Quat bq = {m.base_quat[0], m.base_quat[1], m.base_quat[2], m.base_quat[3]};
@@ -380,7 +381,7 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
                             const Quat qz = {0.f, 0.f, sh, ch};
                             r = qmul(r, qz);
                         }
-                        stM3(sm, i * NSLOT + F_OR, lane, f.R); st3(sm, i * NSLOT + F_OO, lane, f.o); st6(sm, i * NSLOT + F_OV, lane, f.V);
+                        if (!STORE_FRAMES) { stM3(sm, i * NSLOT + F_OR, lane, f.R); st3(sm, i * NSLOT + F_OO, lane, f.o); st6(sm, i * NSLOT + F_OV, lane, f.V); }
                         SM(i, F_OQ) = r.x; SM(i, F_OQ + 1) = r.y; SM(i, F_OQ + 2) = r.z; SM(i, F_OQ + 3) = r.w;
                         qp = r;
                     }
@@ -537,7 +538,7 @@ template <bool CHAIN, bool CONTACT>
 int launch_t(MppibContext* c, const float* state0, const float* root0, float* state, const float* actions, int t0, int nsteps, float* obs, cudaStream_t s) {
     const int K = c->params.K;
     const int nslot = (CHAIN && !CONTACT) ? NSLOT_CHAIN : NSLOT_TREE;
-    const contact::Layout L(c->model.nb, c->model.nfree, c->model.nshapes);
+    const contact::Layout L(c->model.nb, c->model.nfree, c->model.nshapes, c->model.max_contacts);
     const size_t smem = sizeof(float) * 32 * ((size_t)c->model.nb * nslot + (CONTACT ? (size_t)L.total : 0) + 2 * (size_t)c->model.nu);
     MPPIB_REQUIRE(smem <= 226 * 1024, "mppib_rollout: %zu bytes of shared memory per CTA exceed the SM (too many bodies / shapes)", smem);
     static size_t smem_attr = 48 * 1024;

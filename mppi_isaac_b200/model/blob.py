@@ -18,7 +18,7 @@ import numpy as np
 
 from .urdf import RobotModel, compile_urdf, load_compiled, quat_xyzw_to_R, R_to_quat_xyzw
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_BODIES, MAX_LINKS, MAX_NU, MAX_OBS, MAX_FREE, MAX_SHAPES = 16, 32, 16, 64, 4, 24
 MAX_CONTACTS, MAX_SLOTS = 24, 8
 
@@ -54,7 +54,7 @@ class MppibModel(C.Structure):
         ("shape_quat", (f32 * 4) * MAX_SHAPES), ("shape_friction", f32 * MAX_SHAPES), ("shape_fric_pct", f32 * MAX_SHAPES),
         ("shape_size_sigma", (f32 * 3) * MAX_SHAPES),
         ("ncontact_slots", i32), ("ground_plane", i32), ("ground_friction", f32), ("contact_kp", f32), ("contact_kd", f32),
-        ("max_depen", f32), ("ground_margin", f32), ("contact_margin", f32), ("contact_iters", i32), ("nactors", i32),
+        ("max_depen", f32), ("ground_margin", f32), ("contact_margin", f32), ("contact_iters", i32), ("nactors", i32), ("max_contacts", i32),
     ]
 
 
@@ -212,6 +212,9 @@ def build_scene(actor_cfgs: list, gravity=(0.0, 0.0, -9.8), assets_dirs=None, su
                                          (nw * kd * (L / 2) ** 2 / r**2, mu * mtot * g * L / 2))):
             m.kd[j], m.effort[j], m.damping[j] = gain, lim, 0.0
         wheels = [i for i, n in enumerate(robot.dof_names) if n in (rcfg.left_wheel_joints or []) + (rcfg.right_wheel_joints or [])]
+        if not wheels:
+            raise NotImplementedError(f"differential-drive robot '{rcfg.name}' names no left_wheel_joints / right_wheel_joints: the command map of "
+                                      "isaacgym_wrapper.py:510-522 cannot be built (the reference's jackal.yaml has this gap too)")
         axis = np.asarray(robot.tree_R[wheels[0]])[:, 2]                     # wheel axis in the root-link frame
         fwd = np.cross(axis, [0.0, 0.0, 1.0])                                # a wheel turning +omega about `axis` rolls the base along axis x z
         m.planar_base = 1
@@ -305,6 +308,18 @@ def build_scene(actor_cfgs: list, gravity=(0.0, 0.0, -9.8), assets_dirs=None, su
             m.free_slot[sh["owner"]] = m.shape_slot[si]
     m.nfree, m.nshapes, m.ncontact_slots = nfree, len(shapes), len(contact_slot)
     m.nactors = len(actor_cfgs)
+    # contact capacity: as many points as the rollout kernel's shared-memory working set allows (csrc/rollout.cu, contact.cuh:
+    # 95 slots per body + 35 per free body + 17 per shape + 18 per contact + 3 per joint + 24 net-force + 2 nu action slots,
+    # 128 B per slot for a 32-rollout CTA, 226 KB usable), at most MAX_CONTACTS
+    if nfree or shapes:
+        fixed = 95 * m.nb + 35 * nfree + 17 * len(shapes) + 3 * m.nb + 3 * MAX_SLOTS + 2 * m.nu
+        cap = min(MAX_CONTACTS, (226 * 1024 // 128 - fixed) // 18)
+        if cap < 12:
+            raise NotImplementedError(f"scene too large for one SM's shared memory: {m.nb} bodies, {len(shapes)} collision boxes leave room for "
+                                      f"{cap} contact points per rollout (12 needed)")
+        m.max_contacts = cap
+    else:
+        m.max_contacts = MAX_CONTACTS
     m.ground_plane, m.ground_friction = 1, 1.0                        # isaacgym_utils.py:61-68
     m.contact_kp, m.contact_kd, m.contact_iters = contact_kp, contact_kd, contact_iters
     # speculative contacts: a body may not close a gap faster than gap / h (keeps resting contacts alive at large h)

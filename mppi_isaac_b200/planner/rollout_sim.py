@@ -96,6 +96,8 @@ class RolloutSim:
         self._act_host = None
         if self._visualize_link_present:
             rcfg = self.env_cfg[sc.robot_actor]
+            if rcfg.visualize_link not in sc.robot.link_names:
+                raise ValueError(f"visualize_link '{rcfg.visualize_link}' is not a link of {rcfg.urdf_file}: {sc.robot.link_names}")
             self._viz_link = sc.robot.link_names.index(rcfg.visualize_link)
             self.robot_rigid_body_viz_idx = sc.body_offset[sc.robot_actor] + self._viz_link
         self._mode = "step"        # "step" | "batched"

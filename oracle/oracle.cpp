@@ -371,7 +371,7 @@ struct ContactWorld {
         }
     }
     void add_contact(int refA, int refB, int slotA, int slotB, const S* pt, const S* n, S d, S mu, int penalty) {
-        if (nc >= MPPIB_MAX_CONTACTS) return;
+        if (nc >= m->max_contacts) return;
         Contact<S>& c = ct[nc++];
         c.refA = refA; c.refB = refB; c.slotA = slotA; c.slotB = slotB; c.penalty = penalty; c.d = d; c.mu = mu; c.ln = c.lt1 = c.lt2 = 0;
         for (int i = 0; i < 3; ++i) { c.p[i] = pt[i]; c.n[i] = n[i]; }

@@ -145,3 +145,24 @@ def point_cfg(K=128, T=12, device="cpu", **mppi_kw):
     for k, v in mppi_kw.items():
         setattr(cfg.mppi, k, v)
     return cfg
+
+
+def robot_setup(actor, link, K=64, T=10, u_lim=0.2, sigma=0.1, extra_actors=("goal",), substeps=2, dt=0.05, **kw):
+    """Any single-robot scene of the shipped conf/ (albert, omnipanda, panda_effort, ...): link + DOF observations, contact-free unless
+    `extra_actors` brings colliding boxes."""
+    actors = load_actor_cfgs([actor] + list(extra_actors))
+    for a in actors:
+        a.noise_sigma_size, a.noise_percentage_mass, a.noise_percentage_friction = None, 0.0, 0.0
+    sc = build_scene(actors, substep=dt / substeps)
+    obs = [(OBS_LINK_STATE, sc.robot.link_names.index(link)), (OBS_DOF_STATE, 0)]
+    if sc.model.nfree:
+        obs.append((OBS_FREE_STATE, 0))
+    mc = MPPIConfig(num_samples=K, horizon=T, mppi_mode="simple", sampling_method="random", noise_sigma=(sigma * np.eye(sc.nu)).tolist(),
+                    u_min=[-u_lim], u_max=[u_lim], lambda_=0.05, sample_null_action=True, **kw)
+    p = make_params(mc, IsaacGymConfig(dt=dt, substeps=substeps), sc.nu, K, obs)
+    dof0 = sc.dof_state0
+    nd, nv = sc.ndof, sc.virtual_dofs
+    state0 = np.zeros(2 * nd, np.float32)
+    state0[nv:nd] = dof0[0::2]
+    state0[nd + nv:] = dof0[1::2]
+    return sc, p, state0

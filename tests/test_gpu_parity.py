@@ -520,3 +520,28 @@ def test_k2_drive_saturation_resolve_path(oracle, setup, K):
     be_free.rollout(dev(state0), state2, dev(actions), 0, T, None)
     diff = np.abs(state2.cpu().numpy()[:nb] - s[:nb]).max(axis=0)
     assert diff[K // 4:].max() > 1e-2 and diff[: K // 4].max() < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("actor,link,u_lim", [("albert", "mmrobot_link7", 0.4), ("omnipanda", "panda_ee_tip", 0.3), ("panda_effort", "panda_link7", 8.0),
+                                               ("panda", "panda_link7", 0.2)])
+def test_k2_rollout_parity_further_robots(oracle, actor, link, u_lim):
+    """the remaining robots of the reference's example set run through the same kernel and match the oracle --
+    albert (differential-drive base reduced to the plane + 7-DoF arm, 12 bodies, tree), omnipanda (x / y / yaw base joints + arm +
+    gripper, 12 DOF), the panda in EFFORT mode (commands are torques, isaacgym_wrapper.py:492-496), the plain panda."""
+    from scenes import robot_setup
+    K, T = 256, 12
+    sc, p, state0 = robot_setup(actor, link, K=K, T=T, u_lim=u_lim)
+    be = gpu_backend(sc, p)
+    rng = np.random.default_rng(8)
+    actions = rng.uniform(-u_lim, u_lim, (T, sc.nu, K)).astype(np.float32)
+    obs, state = torch.zeros((be.obs_size(), T, K), device=DEV), torch.zeros((be.state_size(), K), device=DEV)
+    root0 = dev(sc.root_state0.astype(np.float32))
+    be.rollout(dev(state0), state, dev(actions), 0, T, obs, root0=root0)
+    st_ref, obs_ref = oracle.rollout(sc.model, p, state0, actions, use_double=True, nthreads=8, root0=sc.root_state0.astype(np.float32))
+    s, o = state.cpu().numpy(), obs.cpu().numpy()
+    nd = sc.ndof
+    assert np.abs(s[:nd] - st_ref[:nd]).max() <= 1e-4
+    assert np.abs(s[nd:2 * nd] - st_ref[nd:2 * nd]).max() <= 5e-3
+    assert np.abs(o[0:3] - obs_ref[0:3]).max() <= 1e-4
+    assert np.abs(s[:nd] - state0[:nd, None]).max() > 1e-2            # something actually moved

@@ -358,3 +358,27 @@ def test_rpc_server_client_speak_the_zerorpc_wire_format():
     finally:
         server.stop()
         th.join(timeout=5)
+
+
+@pytest.mark.parametrize("task,objective,q", [
+    ("config_albert_b200", lambda: PandaReachObjective(actor="albert", link="mmrobot_link7"), [0, 0, 0, 0, -0.94, 0, -2.8, 0, 1.8675, 0]),
+    ("config_panda_effort_b200", lambda: PandaReachObjective(actor="panda", link="panda_link7"), [0, -0.94, 0, -2.8, 0, 1.8675, 0]),
+    ("config_omnipanda_pick_b200", lambda: PandaPickObjective(actor="omnipanda", link="panda_hand"), [0, 0, 0, 0, -0.94, 0, -2.8, 0, 1.8675, 0, 0.02, 0.02]),
+])
+def test_further_example_robots_plan_through_the_api(task, objective, q):
+    """albert (differential-drive base + arm), the panda in effort mode and omnipanda picking from a table build
+    from the shipped conf/ + compiled models and plan through the drop-in API (checker backend on the CPU)."""
+    import copy
+    from mppi_isaac_b200 import load_isaacgym_config
+    cfg = copy.deepcopy(load_isaacgym_config(task))
+    cfg.mppi.num_samples, cfg.mppi.device = 48, "cpu"
+    p = MPPIisaacPlanner(cfg, objective(), backend=OracleBackend(nthreads=8))
+    sc = p.sim.scene
+    assert cfg.nx == 2 * (sc.ndof - sc.virtual_dofs)                                          # nx of the reference's task files (real DOFs)
+    a0 = p.compute_action(q, [0.0] * len(q))
+    a1 = p.compute_action(q, [0.0] * len(q))
+    assert a0.shape == (sc.nu,) and torch.isfinite(a0).all() and torch.isfinite(a1).all()
+    lo, hi = torch.tensor(p.mppi.backend.params.u_min[:sc.nu]), torch.tensor(p.mppi.backend.params.u_max[:sc.nu])
+    assert bool(((a1 >= lo - 1e-6) & (a1 <= hi + 1e-6)).all())
+    if sc.model.nshapes:
+        assert 12 <= sc.model.max_contacts <= 24                                               # sized to the SM's shared memory

@@ -18,8 +18,9 @@ ROBOTS = [
     "panda_isaac/robots/franka_panda.urdf",
     "panda_isaac/robots/franka_panda_stick.urdf",
     "panda_isaac/robots/franka_panda_gripper.urdf",
+    "omni_panda/omniPandaWithGripper.urdf",
 ]
-FLOATING = ["boxer/boxer.urdf"]          # differential-drive bases: compiled with the planar virtual-joint root
+FLOATING = ["boxer/boxer.urdf", "albert/albert.urdf"]          # differential-drive bases: compiled with the planar virtual-joint root
 
 
 def main():
