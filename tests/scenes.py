@@ -160,9 +160,6 @@ def robot_setup(actor, link, K=64, T=10, u_lim=0.2, sigma=0.1, extra_actors=("go
     mc = MPPIConfig(num_samples=K, horizon=T, mppi_mode="simple", sampling_method="random", noise_sigma=(sigma * np.eye(sc.nu)).tolist(),
                     u_min=[-u_lim], u_max=[u_lim], lambda_=0.05, sample_null_action=True, **kw)
     p = make_params(mc, IsaacGymConfig(dt=dt, substeps=substeps), sc.nu, K, obs)
-    dof0 = sc.dof_state0
-    nd, nv = sc.ndof, sc.virtual_dofs
-    state0 = np.zeros(2 * nd, np.float32)
-    state0[nv:nd] = dof0[0::2]
-    state0[nd + nv:] = dof0[1::2]
+    dof0 = sc.dof_state0                                  # interleaved (q, qd) of ALL joints, virtual base joints included
+    state0 = np.concatenate([dof0[0::2], dof0[1::2]]).astype(np.float32)
     return sc, p, state0

@@ -523,7 +523,7 @@ def test_k2_drive_saturation_resolve_path(oracle, setup, K):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("actor,link,u_lim", [("albert", "mmrobot_link7", 0.4), ("omnipanda", "panda_ee_tip", 0.3), ("panda_effort", "panda_link7", 8.0),
+@pytest.mark.parametrize("actor,link,u_lim", [("albert", "mmrobot_link7", 0.4), ("omnipanda", "panda_hand", 0.3), ("panda_effort", "panda_link7", 8.0),
                                                ("panda", "panda_link7", 0.2)])
 def test_k2_rollout_parity_further_robots(oracle, actor, link, u_lim):
     """the remaining robots of the reference's example set run through the same kernel and match the oracle --
