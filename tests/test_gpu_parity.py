@@ -312,16 +312,24 @@ def test_contact_randomisation_and_shard_offset_on_device(oracle):
     assert torch.equal(obs2, obs[:, :, 32:])                                           # global sample index keys the draws
 
 
-@pytest.mark.parametrize("task", ["push", "pick"])
+@pytest.mark.parametrize("task", ["push", "pick", "omnipick"])
 def test_contact_plan_through_planner_api(task):
-    """First plan from the same world state, GPU (CUDA graph) vs checker backend, configs C4 / C5 at test size."""
+    """First plan from the same world state, GPU (CUDA graph) vs checker backend, configs C4 / C5 at test size, and the omnipanda
+    pick scene (12 bodies + 14 boxes: contact capacity 17, sized to the SM's shared memory)."""
     from mppi_isaac_b200 import MPPIisaacPlanner
     from mppi_isaac_b200.objectives import PandaPickObjective, PushObjective
     from oracle.backend import OracleBackend
     if task == "push":
         mk, obj, q = (lambda d: push_cfg(K=512, T=10, device=d)), PushObjective, [0.0, 0.0, 0.0]
-    else:
+    elif task == "pick":
         mk, obj, q = (lambda d: pick_cfg(K=256, T=12, device=d)), PandaPickObjective, [0.0, -0.94, 0.0, -2.8, 0.0, 1.8675, 0.0, 0.02, 0.02]
+    else:
+        from mppi_isaac_b200 import load_isaacgym_config
+        def mk(d):
+            cfg = copy.deepcopy(load_isaacgym_config("config_omnipanda_pick_b200"))
+            cfg.mppi.num_samples, cfg.mppi.device, cfg.mppi.sampling_method, cfg.mppi.mppi_mode = 256, d, "random", "simple"
+            return cfg
+        obj, q = (lambda: PandaPickObjective(actor="omnipanda", link="panda_hand")), [0.0, 0.0, 0.0, 0.0, -0.94, 0.0, -2.8, 0.0, 1.8675, 0.0, 0.02, 0.02]
     gpu = MPPIisaacPlanner(mk(DEV), obj(), use_cuda_graph=True)
     cpu = MPPIisaacPlanner(mk("cpu"), obj(), backend=OracleBackend(nthreads=8))
     ag, ac = gpu.compute_action(q, [0.0] * len(q)), cpu.compute_action(q, [0.0] * len(q))
@@ -331,6 +339,8 @@ def test_contact_plan_through_planner_api(task):
     for _ in range(3):
         ag = gpu.compute_action(q, [0.0] * len(q))
     assert gpu.mppi._graph is not None and torch.isfinite(ag).all()
+    if task == "omnipick":
+        assert gpu.sim.scene.model.max_contacts == 17
     blk = "block" if task == "push" else "panda_pick_block"
     zg, zc = gpu.sim.get_actor_position_by_name(blk)[:, 2], cpu.sim.get_actor_position_by_name(blk)[:, 2]
     assert abs(float(zg.mean()) - float(zc.mean())) <= 5e-3
