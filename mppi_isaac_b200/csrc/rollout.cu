@@ -34,6 +34,9 @@
 #ifndef ROLL_UNROLL_S1
 #define ROLL_UNROLL_S1 1      // unroll factor of sweep 1 (kinematics / inertia: bodies are independent apart from the frame recursion)
 #endif
+#ifndef ROLL_S1_PIPE
+#define ROLL_S1_PIPE 0        // software-pipelined sweep 1 for serial chains (kinematics of body i+1 with the dynamics terms of body i)
+#endif
 #ifndef ROLL_UNROLL_S3
 #define ROLL_UNROLL_S3 2      // unroll factor of sweep 3 (accelerations)
 #endif
@@ -220,6 +223,45 @@ __device__ __forceinline__ void body_kinematics(const MppibModel& m, int i, floa
     out.V.f = par.V.f + qd * S.f;
 }
 
+// sweep-1 dynamics of body i in its world frame f: rotational inertia about the world origin, first moment, bias force
+// V x* (I V) and velocity-product acceleration c = V x (S qd)  ->  slots F_S, F_C, F_A, F_HW, F_PB
+template <int NSLOT>
+__device__ __forceinline__ void s1_dynamics(const MppibModel& m, float* sm, int lane, int i, const Frame& f, const V6& S, float qdi) {
+    const float mass = m.mass[i];
+    // centre of mass (world), first moment, inertia about the world origin:
+    //   R I_o R^T + m[(|cw|^2 - |cb|^2) 1 - (cw cw^T - cb cb^T)],  cb = R c_body, cw = o + cb
+    V3 cb = mk(0, 0, 0);
+    if (mass > 0.f) cb = __frcp_rn(mass) * mul(f.R, mk(m.mcom[i][0], m.mcom[i][1], m.mcom[i][2]));
+    const V3 cw = f.o + cb;
+    const V3 hw = mass * cw;
+    const S3 Io = {m.inertia[i][0], m.inertia[i][1], m.inertia[i][2], m.inertia[i][3], m.inertia[i][4], m.inertia[i][5]};
+    const V3 r0 = mk(f.R.m00, f.R.m01, f.R.m02), r1 = mk(f.R.m10, f.R.m11, f.R.m12), r2 = mk(f.R.m20, f.R.m21, f.R.m22);
+    const V3 t0v = mul(Io, r0), t1v = mul(Io, r1), t2v = mul(Io, r2);
+    S3 A;
+    A.xx = dot(r0, t0v); A.yy = dot(r1, t1v); A.zz = dot(r2, t2v);
+    A.xy = dot(r0, t1v); A.xz = dot(r0, t2v); A.yz = dot(r1, t2v);
+    const float d2 = mass * (dot(cw, cw) - dot(cb, cb));
+    A.xx += d2 - mass * (cw.x * cw.x - cb.x * cb.x); A.yy += d2 - mass * (cw.y * cw.y - cb.y * cb.y);
+    A.zz += d2 - mass * (cw.z * cw.z - cb.z * cb.z);
+    A.xy -= mass * (cw.x * cw.y - cb.x * cb.y); A.xz -= mass * (cw.x * cw.z - cb.x * cb.z);
+    A.yz -= mass * (cw.y * cw.z - cb.y * cb.z);
+    // bias force V x* (I V) and velocity-product acceleration c = V x (S qd)
+    const V3 w = f.V.n, v = f.V.f;
+    const V3 nn = mul(A, w) + cross(hw, v);
+    const V3 ff = mass * v - cross(hw, w);
+    V6 pb, c;
+    pb.n = cross(w, nn) + cross(v, ff);
+    pb.f = cross(w, ff);
+    const V3 sw = qdi * S.n, sv = qdi * S.f;
+    c.n = cross(w, sw);
+    c.f = cross(w, sv) + cross(v, sw);
+    st6(sm, i * NSLOT + F_S, lane, S);
+    st6(sm, i * NSLOT + F_C, lane, c);
+    stS3(sm, i * NSLOT + F_A, lane, A);
+    st3(sm, i * NSLOT + F_HW, lane, hw);
+    st6(sm, i * NSLOT + F_PB, lane, pb);
+}
+
 #include "contact.cuh"
 
 template <bool CHAIN, bool CONTACT>
@@ -361,6 +403,43 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
             {
                 const bool obs_now = sub == 0 && pending >= 0;   // this sweep's kinematics ARE the observation of the previous step
                 Frame par = base; Quat qp = bq;
+#if ROLL_S1_PIPE
+                if (CHAIN && !CONTACT) {
+                    // software-pipelined: the kinematics of body i+1 (the frame recursion) and the inertia / bias terms of body i are
+                    // independent and sit in ONE basic block, so the scheduler can interleave them (the last iteration recomputes
+                    // the kinematics of body nb-1, discarded)
+                    auto head = [&](int j, const Frame& pf, Frame& f, V6& S, float& qdj) {
+                        const float qj = SM(j, F_Q);
+                        qdj = SM(j, F_QD);
+                        body_kinematics(m, j, qj, qdj, pf, f, S);
+                        return qj;
+                    };
+                    auto obs_head = [&](int j, float qj, const Frame& f) {
+                        const Quat qt = {m.tree_quat[j][0], m.tree_quat[j][1], m.tree_quat[j][2], m.tree_quat[j][3]};
+                        Quat r = qmul(qp, qt);
+                        if (m.jtype[j] == MPPIB_JOINT_REVOLUTE) {
+                            float sh, ch; sincos_cw(0.5f * qj, &sh, &ch);
+                            const Quat qz = {0.f, 0.f, sh, ch};
+                            r = qmul(r, qz);
+                        }
+                        stM3(sm, j * NSLOT + F_OR, lane, f.R); st3(sm, j * NSLOT + F_OO, lane, f.o); st6(sm, j * NSLOT + F_OV, lane, f.V);
+                        SM(j, F_OQ) = r.x; SM(j, F_OQ + 1) = r.y; SM(j, F_OQ + 2) = r.z; SM(j, F_OQ + 3) = r.w;
+                        qp = r;
+                    };
+                    Frame fc; V6 Sc; float qdc;
+                    { const float q0 = head(0, base, fc, Sc, qdc); if (obs_now) obs_head(0, q0, fc); }
+#pragma unroll 1
+                    for (int i = 0; i < nb; ++i) {
+                        const int j = i + 1 < nb ? i + 1 : nb - 1;
+                        Frame fn; V6 Sn; float qdn;
+                        const float qj = head(j, fc, fn, Sn, qdn);
+                        s1_dynamics<NSLOT>(m, sm, lane, i, fc, Sc, qdc);
+                        SM(i, F_SAT) = 0.f;
+                        if (obs_now && i + 1 < nb) obs_head(j, qj, fn);
+                        fc = fn; Sc = Sn; qdc = qdn;
+                    }
+                } else
+#endif
                 MPPIB_UNROLL(ROLL_UNROLL_S1)
                 for (int i = 0; i < nb; ++i) {
                     if (!CHAIN) {
@@ -385,39 +464,7 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
                         SM(i, F_OQ) = r.x; SM(i, F_OQ + 1) = r.y; SM(i, F_OQ + 2) = r.z; SM(i, F_OQ + 3) = r.w;
                         qp = r;
                     }
-                    const float mass = m.mass[i];
-                    // centre of mass (world), first moment, inertia about the world origin:
-                    //   R I_o R^T + m[(|cw|^2 - |cb|^2) 1 - (cw cw^T - cb cb^T)],  cb = R c_body, cw = o + cb
-                    V3 cb = mk(0, 0, 0);
-                    if (mass > 0.f) cb = __frcp_rn(mass) * mul(f.R, mk(m.mcom[i][0], m.mcom[i][1], m.mcom[i][2]));
-                    const V3 cw = f.o + cb;
-                    const V3 hw = mass * cw;
-                    const S3 Io = {m.inertia[i][0], m.inertia[i][1], m.inertia[i][2], m.inertia[i][3], m.inertia[i][4], m.inertia[i][5]};
-                    const V3 r0 = mk(f.R.m00, f.R.m01, f.R.m02), r1 = mk(f.R.m10, f.R.m11, f.R.m12), r2 = mk(f.R.m20, f.R.m21, f.R.m22);
-                    const V3 t0v = mul(Io, r0), t1v = mul(Io, r1), t2v = mul(Io, r2);
-                    S3 A;
-                    A.xx = dot(r0, t0v); A.yy = dot(r1, t1v); A.zz = dot(r2, t2v);
-                    A.xy = dot(r0, t1v); A.xz = dot(r0, t2v); A.yz = dot(r1, t2v);
-                    const float d2 = mass * (dot(cw, cw) - dot(cb, cb));
-                    A.xx += d2 - mass * (cw.x * cw.x - cb.x * cb.x); A.yy += d2 - mass * (cw.y * cw.y - cb.y * cb.y);
-                    A.zz += d2 - mass * (cw.z * cw.z - cb.z * cb.z);
-                    A.xy -= mass * (cw.x * cw.y - cb.x * cb.y); A.xz -= mass * (cw.x * cw.z - cb.x * cb.z);
-                    A.yz -= mass * (cw.y * cw.z - cb.y * cb.z);
-                    // bias force V x* (I V) and velocity-product acceleration c = V x (S qd)
-                    const V3 w = f.V.n, v = f.V.f;
-                    const V3 nn = mul(A, w) + cross(hw, v);
-                    const V3 ff = mass * v - cross(hw, w);
-                    V6 pb, c;
-                    pb.n = cross(w, nn) + cross(v, ff);
-                    pb.f = cross(w, ff);
-                    const V3 sw = qdi * S.n, sv = qdi * S.f;
-                    c.n = cross(w, sw);
-                    c.f = cross(w, sv) + cross(v, sw);
-                    st6(sm, i * NSLOT + F_S, lane, S);
-                    st6(sm, i * NSLOT + F_C, lane, c);
-                    stS3(sm, i * NSLOT + F_A, lane, A);
-                    st3(sm, i * NSLOT + F_HW, lane, hw);
-                    st6(sm, i * NSLOT + F_PB, lane, pb);
+                    s1_dynamics<NSLOT>(m, sm, lane, i, f, S, qdi);
                     SM(i, F_SAT) = 0.f;
                     if (CHAIN) par = f;
                     if (STORE_FRAMES) { stM3(sm, i * NSLOT + F_R, lane, f.R); st3(sm, i * NSLOT + F_O, lane, f.o); st6(sm, i * NSLOT + F_V, lane, f.V); }

@@ -12,12 +12,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "tune_build")
 VARIANTS = {
     "base": [],
-    "s1u2": ["-DROLL_UNROLL_S1=2"],
-    "s1u4": ["-DROLL_UNROLL_S1=4"],
-    "s3u2": ["-DROLL_UNROLL_S3=2"],
-    "s1u2_s3u2": ["-DROLL_UNROLL_S1=2", "-DROLL_UNROLL_S3=2"],
-    "fastsincos": ["-DROLL_FAST_SINCOS=1"],
-    "all": ["-DROLL_UNROLL_S1=2", "-DROLL_UNROLL_S3=2", "-DROLL_FAST_SINCOS=1"],
+    "s1pipe": ["-DROLL_S1_PIPE=1"],
+    "s1pipe_s3u1": ["-DROLL_S1_PIPE=1", "-DROLL_UNROLL_S3=1"],
+    "s3u4": ["-DROLL_UNROLL_S3=4"],
 }
 
 if sys.argv[1] == "build":
@@ -26,7 +23,7 @@ if sys.argv[1] == "build":
     for name, flags in VARIANTS.items():
         so = os.path.join(OUT, f"libmppib_{name}.so")
         cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
-               "-diag-suppress", "177", *flags, "-o", so] + [os.path.join(csrc, f) for f in ("api.cu", "sample.cu", "rollout.cu", "reduce.cu")]
+               "-diag-suppress", "177", *flags, "-o", so] + [os.path.join(csrc, f) for f in ("api.cu", "sample.cu", "rollout.cu", "reduce.cu", "cost.cu")]
         subprocess.check_call(cmd)
         print("built", so)
 elif sys.argv[1] == "run":
