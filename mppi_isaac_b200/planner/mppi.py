@@ -182,8 +182,6 @@ class MPPIPlanner:
         self.partial = torch.zeros((P,), **f32)
         self.partials = torch.zeros((self.world, P), **f32)
         self._action = torch.zeros((nu,), **f32)
-        # host mirror of the action: the D2H copy is the last node of the (captured) plan, so the caller only waits for the stream
-        self._action_host = torch.zeros((nu,), dtype=torch.float32, pin_memory=True) if torch.device(dev).type == "cuda" else None
         self.stats = torch.zeros((2,), **f32)                # (beta, eta)
         self.plan_ctr = torch.zeros((1,), dtype=torch.int32, device=dev)
         self._prior_rows = torch.zeros((T, nu), **f32) if self.use_priors else None
@@ -222,13 +220,6 @@ class MPPIPlanner:
         """(K, T, nu) view, the layout mppi_torch exposes."""
         return self.actions.permute(2, 0, 1)
 
-    def action_on_host(self):
-        """float32 numpy view of the first action after the last plan (waits for the plan's stream; no extra copy on CUDA)."""
-        if self._action_host is None:
-            return self._action.detach().cpu().numpy()
-        torch.cuda.current_stream(torch.device(self.device)).synchronize()
-        return self._action_host.numpy()
-
     def invalidate_graph(self):
         self._graph = None
         self._graph_failed = False
@@ -264,8 +255,6 @@ class MPPIPlanner:
         be.reduce(cost, x, self.U, self.partial)
         partials, G = self._exchange()
         be.finalize(partials, G, self.U, self._action, self.stats)
-        if self._action_host is not None:
-            self._action_host.copy_(self._action, non_blocking=True)
 
     def _plan_stepwise(self, state):
         be, sim, T = self.backend, self.sim, self.T
@@ -292,8 +281,6 @@ class MPPIPlanner:
         be.reduce(self.cost, x, self.U, self.partial)
         partials, G = self._exchange()
         be.finalize(partials, G, self.U, self._action, self.stats)
-        if self._action_host is not None:
-            self._action_host.copy_(self._action, non_blocking=True)
 
     def _try_capture(self):
         dev = torch.device(self.device)
