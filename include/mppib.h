@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MPPIB_ABI_VERSION 8
+#define MPPIB_ABI_VERSION 9
 
 #define MPPIB_MAX_BODIES 16   /* moving (1-DoF) bodies of the articulation            */
 #define MPPIB_MAX_LINKS  32   /* URDF links whose state can be observed               */
@@ -276,6 +276,11 @@ int32_t mppib_peer_close(MppibHandle h);
  * b_si = 0).  b may be NULL when w_pos == 0.                                                                          */
 int32_t mppib_cost_pose(int64_t n, const float* a, int64_t a_si, int64_t a_sr, const float* b, int64_t b_si,
                         int64_t b_sr, float w_pos, float w_ori, float* cost, int32_t accumulate, void* stream);
+
+/* Optional host mirror of the action: when set, mppib_finalize also stores action_out[0..nu) to `mirror` -- a pointer into
+ * PINNED host memory (device-addressable under unified addressing), so the caller of the reference's compute_action* only
+ * waits for the stream instead of issuing a device->host copy.  NULL switches it off.                                      */
+int32_t mppib_set_action_mirror(MppibHandle h, float* mirror);
 
 /* shift U by one step: U[t] <- U[t+1], U[T-1] <- u_init (mppi_torch command() prologue);
  * increments *plan_ctr (device, nullable) by one.                                            */

@@ -22,7 +22,7 @@ SYMBOLS = [
     "mppib_abi_version", "mppib_last_error", "mppib_create", "mppib_destroy", "mppib_set_params",
     "mppib_set_model", "mppib_state_size", "mppib_obs_size", "mppib_sample", "mppib_rollout",
     "mppib_reduce", "mppib_finalize", "mppib_shift", "mppib_noise_library", "mppib_sample_library",
-    "mppib_peer_alloc", "mppib_peer_open", "mppib_peer_close", "mppib_cost_pose",
+    "mppib_peer_alloc", "mppib_peer_open", "mppib_peer_close", "mppib_cost_pose", "mppib_set_action_mirror",
 ]
 
 
@@ -149,6 +149,11 @@ class CudaBackend:
     def peer_close(self):
         if self.handle:
             self.lib.mppib_peer_close(self.handle)
+
+    def set_action_mirror(self, pinned_host_tensor):
+        """K4 also stores the action into this PINNED host tensor (None switches it off)."""
+        self._mirror_keepalive = pinned_host_tensor
+        self._check(self.lib.mppib_set_action_mirror(self.handle, _ptr(pinned_host_tensor)), "mppib_set_action_mirror")
 
     def reduce(self, cost, x, U, partial):
         self.launches += 1

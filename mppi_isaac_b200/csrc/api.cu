@@ -227,6 +227,12 @@ int32_t mppib_finalize(MppibHandle h, const float* partials, int32_t G, float* U
     return launch_finalize(h, partials, G, U, action_out, stats, (cudaStream_t)stream);
 }
 
+int32_t mppib_set_action_mirror(MppibHandle h, float* mirror) {
+    MPPIB_REQUIRE(h != nullptr, "null handle");
+    h->action_mirror = mirror;
+    return 0;
+}
+
 int32_t mppib_shift(MppibHandle h, float* U, uint32_t* plan_ctr, void* stream) {
     MPPIB_REQUIRE(h && U, "mppib_shift: null argument");
     return launch_shift(h, U, plan_ctr, (cudaStream_t)stream);

@@ -44,6 +44,7 @@ struct MppibContext {
     int peer_world, peer_rank, peer_pcap;      // pcap: floats per row (>= 2 + T*nu, multiple of 4)
     void* peer_win[MPPIB_MAX_PEERS];           // window base of every rank (own entry = local allocation)
     unsigned long long peer_timeout_ns;
+    float* action_mirror;                      // pinned host mirror of the action written by K4 (nullable)
 };
 
 // device view of the peer windows, passed by value to K3 / K4

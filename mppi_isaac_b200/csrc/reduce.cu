@@ -278,7 +278,8 @@ __constant__ float c_sg_edge[4][9] = {{763.f, 441.f, 189.f, 7.f, -105.f, -147.f,
 // K4: combine G shard partials, U update, optional Savitzky-Golay (window 9, order 2, 'interp' edges), action out.
 __global__ void __launch_bounds__(256)
 mppib_finalize_kernel(const __grid_constant__ MppibParams p, int nu, const float* __restrict__ partials_in, int G,
-                float* __restrict__ U, float* __restrict__ action_out, float* __restrict__ stats, const __grid_constant__ PeerArgs peers) {
+                float* __restrict__ U, float* __restrict__ action_out, float* __restrict__ stats, const __grid_constant__ PeerArgs peers,
+                float* __restrict__ action_mirror) {
     extern __shared__ float un[];   // [T*nu] then [G] scales
     const int T = p.T, NR = T * nu;
     int P = 2 + NR;                 // row stride of the partials
@@ -347,7 +348,7 @@ mppib_finalize_kernel(const __grid_constant__ MppibParams p, int nu, const float
             out = fminf(fmaxf(s, p.u_min[j]), p.u_max[j]);   // smoothing may overshoot the bounds at the edges
         }
         U[r] = out;
-        if (r < nu) action_out[r] = out;
+        if (r < nu) { action_out[r] = out; if (action_mirror) action_mirror[r] = out; }
     }
     if (threadIdx.x == 0 && stats) { stats[0] = b; stats[1] = e; }
     if (threadIdx.x == 0 && partials_in == nullptr) *reinterpret_cast<volatile uint32_t*>(peers.win[peers.rank]) = seq;   // exchange `seq` consumed
@@ -451,7 +452,7 @@ int launch_reduce(MppibContext* c, const float* cost, const float* x, const floa
 
 int launch_finalize(MppibContext* c, const float* partials, int G, float* U, float* action_out, float* stats, cudaStream_t s) {
     const int NR = c->params.T * c->model.nu;
-    mppib_finalize_kernel<<<1, 256, (NR + G) * sizeof(float), s>>>(c->params, c->model.nu, partials, G, U, action_out, stats, peer_args(c));
+    mppib_finalize_kernel<<<1, 256, (NR + G) * sizeof(float), s>>>(c->params, c->model.nu, partials, G, U, action_out, stats, peer_args(c), c->action_mirror);
     MPPIB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

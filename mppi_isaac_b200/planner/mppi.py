@@ -182,6 +182,12 @@ class MPPIPlanner:
         self.partial = torch.zeros((P,), **f32)
         self.partials = torch.zeros((self.world, P), **f32)
         self._action = torch.zeros((nu,), **f32)
+        # host mirror of the action: K4 stores it straight into pinned host memory (include/mppib.h mppib_set_action_mirror), the
+        # caller of compute_action* then only waits for the stream -- no device->host copy call
+        self._action_host = None
+        if torch.device(dev).type == "cuda" and hasattr(self.backend, "set_action_mirror"):
+            self._action_host = torch.zeros((nu,), dtype=torch.float32, pin_memory=True)
+            self.backend.set_action_mirror(self._action_host)
         self.stats = torch.zeros((2,), **f32)                # (beta, eta)
         self.plan_ctr = torch.zeros((1,), dtype=torch.int32, device=dev)
         self._prior_rows = torch.zeros((T, nu), **f32) if self.use_priors else None
@@ -219,6 +225,13 @@ class MPPIPlanner:
     def perturbed_action(self):
         """(K, T, nu) view, the layout mppi_torch exposes."""
         return self.actions.permute(2, 0, 1)
+
+    def action_on_host(self):
+        """float32 numpy view of the first action of the last plan, after waiting for the plan's stream."""
+        if self._action_host is None:
+            return self._action.detach().cpu().numpy()
+        torch.cuda.current_stream(self._action.device).synchronize()
+        return self._action_host.numpy()
 
     def invalidate_graph(self):
         self._graph = None

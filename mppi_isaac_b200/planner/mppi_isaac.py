@@ -103,8 +103,10 @@ class MPPIisaacPlanner(object):
         if obst_tensor is not None and len(obst_tensor) > 0:
             self.sim.update_root_state_tensor_by_obstacles_tensor(obst_tensor)
         self.sim.save_root_state()
-        actions = self.mppi.command(self.state_place_holder).cpu()
-        return actions
+        actions = self.mppi.command(self.state_place_holder)
+        if self.mppi.u_per_command == 1 and actions.is_cuda:
+            return torch.from_numpy(self.mppi.action_on_host().copy())       # K4 already stored it into pinned host memory
+        return actions.cpu()
 
     def reset_rollout_sim(self, dof_state_tensor, root_state_tensor, rigid_body_state_tensor=None):
         self.sim.visualize_link_buffer = []
@@ -131,7 +133,8 @@ class MPPIisaacPlanner(object):
         action = self.mppi.command(self.state_place_holder)
         # same bytes as torch_to_bytes(action) (a pickled tensor on the planner's device): one D2H copy into pinned
         # memory, then payload + CRC patched into the cached archive (transport.FastEncoder)
-        return self._enc(action, self.sim.read_action(action))
+        host = self.mppi.action_on_host() if self.mppi.u_per_command == 1 else self.sim.read_action(action)
+        return self._enc(action, host)
 
     def add_to_env(self, env_cfg_additions):
         self.sim.add_to_envs(env_cfg_additions)
