@@ -416,15 +416,15 @@ int launch_reduce_t(MppibContext* c, const float* cost, const float* x, const fl
     const int T = c->params.T, nu = c->model.nu, NR = T * nu, K = c->params.K;
     const size_t smem = reduce_smem_bytes<W, NS>(T, nu);
     MPPIB_REQUIRE(smem <= 226 * 1024, "mppib_reduce: ring of %zu bytes exceeds shared memory", smem);
-    static size_t smem_attr = 0;
-    if (smem > smem_attr) {
+    static size_t smem_attr[64] = {0};              // per device: the attribute belongs to the function on ONE device
+    size_t& attr = smem_attr[c->device & 63];
+    if (smem > attr) {
         MPPIB_CHECK_CUDA(cudaFuncSetAttribute(mppib_reduce_kernel<W, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_attr = smem;
+        attr = smem;
     }
-    // box rows <= 256 per TMA instruction: split T*nu rows evenly
-    const int nbox = (NR + 255) / 256;
-    const int xbox_rows = (NR + nbox - 1) / nbox;
-    MPPIB_REQUIRE(NR % xbox_rows == 0, "mppib_reduce: T*nu = %d cannot be split into equal TMA boxes", NR);
+    // a TMA box has at most 256 rows: split the T*nu rows into equal boxes (largest divisor of T*nu that fits)
+    int xbox_rows = NR < 256 ? NR : 256;
+    while (NR % xbox_rows != 0) --xbox_rows;
     CUtensorMap tm_x, tm_c;
     if (int rc = make_map(&tm_x, x, NR, K, xbox_rows, W)) return rc;
     if (int rc = make_map(&tm_c, cost, T, K, T, W)) return rc;

@@ -588,10 +588,11 @@ int launch_t(MppibContext* c, const float* state0, const float* root0, float* st
     const contact::Layout L(c->model.nb, c->model.nfree, c->model.nshapes, c->model.max_contacts);
     const size_t smem = sizeof(float) * 32 * ((size_t)c->model.nb * nslot + (CONTACT ? (size_t)L.total : 0) + 2 * (size_t)c->model.nu);
     MPPIB_REQUIRE(smem <= 226 * 1024, "mppib_rollout: %zu bytes of shared memory per CTA exceed the SM (too many bodies / shapes)", smem);
-    static size_t smem_attr = 48 * 1024;
-    if (smem > smem_attr) {
+    static size_t smem_attr[64] = {0};              // per device: the attribute belongs to the function on ONE device
+    size_t& attr = smem_attr[c->device & 63];
+    if (smem > 48 * 1024 && smem > attr) {
         MPPIB_CHECK_CUDA(cudaFuncSetAttribute(mppib_rollout_kernel<CHAIN, CONTACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_attr = smem;
+        attr = smem;
     }
     dim3 grid((K + 31) / 32), block(32);
     mppib_rollout_kernel<CHAIN, CONTACT><<<grid, block, smem, s>>>(c->model, c->params, state0, root0, state, actions, t0, nsteps, obs);

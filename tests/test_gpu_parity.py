@@ -420,9 +420,9 @@ def test_halton_spline_plan_through_planner_api():
     assert gpu.mppi._graph is not None
 
 
-@pytest.mark.parametrize("setup,T", [(point_setup, 12), (point_setup, 25), (point_setup, 9), (gripper_setup, 30), (gripper_setup, 11)])
+@pytest.mark.parametrize("setup,T", [(point_setup, 12), (point_setup, 25), (point_setup, 9), (gripper_setup, 30), (gripper_setup, 11), (gripper_setup, 29)])
 def test_k3_shapes_and_alignment(oracle, setup, T):
-    """K3 across (T, nu) shapes: T*nu = 27..270 rows, odd row counts, two TMA boxes for T*nu > 256."""
+    """K3 across (T, nu) shapes: T*nu = 27..270 rows, odd row counts, two TMA boxes for T*nu > 256 (270 = 2 x 135) and three for 261 = 3 x 87."""
     K = 1000
     sc, p, _ = setup(K=K, T=T) if setup is not gripper_setup else setup(K=K, T=T, filter_u=False)
     p.filter_u = 0
