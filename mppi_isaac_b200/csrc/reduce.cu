@@ -430,6 +430,7 @@ int launch_reduce_t(MppibContext* c, const float* cost, const float* x, const fl
     if (int rc = make_map(&tm_c, cost, T, K, T, W)) return rc;
     const int ntiles = (K + W - 1) / W;
     int grid = ntiles < c->num_sms ? ntiles : c->num_sms;
+    if (const char* e = getenv("MPPIB_K3_GRID")) { const int g = atoi(e); if (g >= 1 && g < grid) grid = g; }   // tuning knob (tools/tune_reduce.py)
     if (grid > MAX_GRID) grid = MAX_GRID;
     MPPIB_REQUIRE(grid <= c->reduce_max_ctas, "mppib_reduce: scratch too small");
     mppib_reduce_kernel<W, NS><<<grid, NT, smem, s>>>(c->params, tm_x, tm_c, nu, xbox_rows, U, c->reduce_scratch, c->reduce_ticket, partial, reduce_peers(c));
@@ -443,8 +444,9 @@ int launch_reduce(MppibContext* c, const float* cost, const float* x, const floa
     const int T = c->params.T, nu = c->model.nu;
     MPPIB_REQUIRE(T * nu <= RPT * NT, "mppib_reduce: T*nu = %d exceeds %d", T * nu, RPT * NT);
     MPPIB_REQUIRE(T <= 256, "mppib_reduce: T = %d exceeds the 256-row TMA box", T);
-    // wide tiles once every SM has several of them; narrow tiles keep all SMs busy at small K
-    const bool wide = c->params.K >= 64 * c->num_sms * 3 && reduce_smem_bytes<64, 3>(T, nu) <= 226 * 1024;
+    // wide tiles once every SM has one; narrow tiles keep all SMs busy at small K
+    bool wide = c->params.K >= 64 * c->num_sms && reduce_smem_bytes<64, 3>(T, nu) <= 226 * 1024;   // tools/tune_reduce.py: 12.5 -> 11.7 us at K = 10 000
+    if (const char* e = getenv("MPPIB_K3_WIDE")) wide = atoi(e) != 0 && reduce_smem_bytes<64, 3>(T, nu) <= 226 * 1024;   // tuning knob
     if (wide) return launch_reduce_t<64, 3>(c, cost, x, U, partial, s);
     if (reduce_smem_bytes<32, 4>(T, nu) <= 226 * 1024) return launch_reduce_t<32, 4>(c, cost, x, U, partial, s);
     return launch_reduce_t<32, 2>(c, cost, x, U, partial, s);
