@@ -329,7 +329,7 @@ def run_gpu_arm(args, rank, world, local_rank):
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        launches_per_plan = 6     # shift, sample, rollout, fused pose cost (Objective), reduce, finalize -- all kernels of libmppib.so
+        launches_per_plan = (5 if world == 1 else 6)   # shift, sample, rollout, fused pose cost (Objective), reduce(+finalize fused at 1 GPU) [, finalize]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_s * 1e3 / args.steps, "plan_hz": args.steps / total_s, "higher_is_better": True,

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MPPIB_ABI_VERSION 9
+#define MPPIB_ABI_VERSION 10
 
 #define MPPIB_MAX_BODIES 16   /* moving (1-DoF) bodies of the articulation            */
 #define MPPIB_MAX_LINKS  32   /* URDF links whose state can be observed               */
@@ -242,6 +242,12 @@ int32_t mppib_rollout(MppibHandle h, const float* state0, const float* root0, fl
  * Single pass over HBM; the last CTA to finish folds the per-CTA partials.                  */
 int32_t mppib_reduce(MppibHandle h, const float* cost, const float* x, const float* U,
                      float* partial, void* stream);
+
+/* K3 + K4 in ONE launch for single-GPU plans (G = 1): the last CTA of the reduction, which holds the shard row, also updates
+ * U in place (+ savgol, clamp), writes action_out[nu] and stats[2] -- same results as mppib_reduce followed by
+ * mppib_finalize(partial, 1, ...), one kernel launch and one graph node less per plan.                                     */
+int32_t mppib_reduce_finalize(MppibHandle h, const float* cost, const float* x, float* U, float* partial,
+                              float* action_out, float* stats, void* stream);
 
 /* K4: combine G shard partials, update U in place, optional savgol, write action_out[nu]
  * (= first row of U), and weights statistics stats[2] = (beta, eta).  partials == NULL with an

@@ -22,7 +22,7 @@ SYMBOLS = [
     "mppib_abi_version", "mppib_last_error", "mppib_create", "mppib_destroy", "mppib_set_params",
     "mppib_set_model", "mppib_state_size", "mppib_obs_size", "mppib_sample", "mppib_rollout",
     "mppib_reduce", "mppib_finalize", "mppib_shift", "mppib_noise_library", "mppib_sample_library",
-    "mppib_peer_alloc", "mppib_peer_open", "mppib_peer_close", "mppib_cost_pose", "mppib_set_action_mirror",
+    "mppib_peer_alloc", "mppib_peer_open", "mppib_peer_close", "mppib_cost_pose", "mppib_set_action_mirror", "mppib_reduce_finalize",
 ]
 
 
@@ -158,6 +158,12 @@ class CudaBackend:
     def reduce(self, cost, x, U, partial):
         self.launches += 1
         self._check(self.lib.mppib_reduce(self.handle, _ptr(cost), _ptr(x), _ptr(U), _ptr(partial), self._stream()), "mppib_reduce")
+
+    def reduce_finalize(self, cost, x, U, partial, action_out, stats):
+        """K3 + K4 in one launch (single-GPU plans)."""
+        self.launches += 1
+        self._check(self.lib.mppib_reduce_finalize(self.handle, _ptr(cost), _ptr(x), _ptr(U), _ptr(partial), _ptr(action_out), _ptr(stats), self._stream()),
+                    "mppib_reduce_finalize")
 
     def finalize(self, partials, G, U, action_out, stats):
         self.launches += 1

@@ -215,7 +215,13 @@ int32_t mppib_rollout(MppibHandle h, const float* state0, const float* root0, fl
 int32_t mppib_reduce(MppibHandle h, const float* cost, const float* x, const float* U, float* partial, void* stream) {
     MPPIB_REQUIRE(h && cost && x && U && partial, "mppib_reduce: null argument");
     MPPIB_REQUIRE(((uintptr_t)cost & 15) == 0 && ((uintptr_t)x & 15) == 0, "mppib_reduce: cost/x must be 16-byte aligned");
-    return launch_reduce(h, cost, x, U, partial, (cudaStream_t)stream);
+    return launch_reduce(h, cost, x, U, partial, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int32_t mppib_reduce_finalize(MppibHandle h, const float* cost, const float* x, float* U, float* partial, float* action_out, float* stats, void* stream) {
+    MPPIB_REQUIRE(h && cost && x && U && partial && action_out, "mppib_reduce_finalize: null argument");
+    MPPIB_REQUIRE(h->peer_world <= 1, "mppib_reduce_finalize is the single-GPU plan tail; with an open peer window use mppib_reduce + mppib_finalize");
+    return launch_reduce(h, cost, x, U, partial, U, action_out, stats, (cudaStream_t)stream);
 }
 
 int32_t mppib_finalize(MppibHandle h, const float* partials, int32_t G, float* U, float* action_out, float* stats, void* stream) {

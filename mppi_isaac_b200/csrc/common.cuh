@@ -72,7 +72,8 @@ int launch_sample_library(MppibContext* c, uint32_t k_offset, uint32_t k_total, 
                           float* actions, float* noise, cudaStream_t s);
 int launch_rollout(MppibContext* c, const float* state0, const float* root0, float* state, const float* actions, int t0, int nsteps,
                    float* obs, cudaStream_t s);
-int launch_reduce(MppibContext* c, const float* cost, const float* x, const float* U, float* partial, cudaStream_t s);
+int launch_reduce(MppibContext* c, const float* cost, const float* x, const float* U, float* partial, float* fin_U, float* fin_action,
+                  float* fin_stats, cudaStream_t s);
 int launch_finalize(MppibContext* c, const float* partials, int G, float* U, float* action_out, float* stats, cudaStream_t s);
 int launch_shift(MppibContext* c, float* U, uint32_t* plan_ctr, cudaStream_t s);
 int launch_cost_pose(long long n, const float* a, long long a_si, long long a_sr, const float* b, long long b_si, long long b_sr, float w_pos,

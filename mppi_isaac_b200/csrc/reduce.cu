@@ -59,11 +59,68 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
                  ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(col), "r"(row), "r"(smem_u32(bar)) : "memory");
 }
 
+__constant__ float c_sg_mid[9] = {-21.f, 14.f, 39.f, 54.f, 59.f, 54.f, 39.f, 14.f, -21.f};
+__constant__ float c_sg_edge[4][9] = {{763.f, 441.f, 189.f, 7.f, -105.f, -147.f, -119.f, -21.f, 147.f},
+                                      {441.f, 322.f, 220.5f, 136.5f, 70.f, 21.f, -10.5f, -24.5f, -21.f},
+                                      {189.f, 220.5f, 232.f, 223.5f, 195.f, 146.5f, 78.f, -10.5f, -119.f},
+                                      {7.f, 136.5f, 223.5f, 268.f, 270.f, 229.5f, 146.5f, 21.f, -147.f}};
+
+// combine G rows (beta_g, eta_g, W_g) of stride P, update U (+ Savitzky-Golay, clamp), first action, statistics; one CTA of 256
+// threads, `un` = [T*nu + G] floats of shared memory
+__device__ __forceinline__ void finalize_rows(const MppibParams& p, int nu, const float* __restrict__ partials, int G, int P, float* __restrict__ U,
+                                              float* __restrict__ action_out, float* __restrict__ stats, float* __restrict__ action_mirror, float* un) {
+    const int T = p.T, NR = T * nu;
+    float* sg = un + NR;
+    const float inv_lambda = 1.0f / p.lambda_;
+    float b = INFINITY;
+    for (int gidx = 0; gidx < G; ++gidx) if (__ldcg(&partials[(size_t)gidx * P + 1]) > 0.f) b = fminf(b, __ldcg(&partials[(size_t)gidx * P]));
+    for (int gidx = threadIdx.x; gidx < G; gidx += blockDim.x) {
+        const float eg = __ldcg(&partials[(size_t)gidx * P + 1]);
+        sg[gidx] = eg > 0.f ? expf(-(__ldcg(&partials[(size_t)gidx * P]) - b) * inv_lambda) : 0.f;
+    }
+    __syncthreads();
+    float e = 0.f;
+    for (int gidx = 0; gidx < G; ++gidx) e += sg[gidx] * __ldcg(&partials[(size_t)gidx * P + 1]);
+    for (int r = threadIdx.x; r < NR; r += blockDim.x) {
+        float w = 0.f;
+        for (int gidx = 0; gidx < G; ++gidx) w += sg[gidx] * __ldcg(&partials[(size_t)gidx * P + 2 + r]);
+        const float wm = e > 0.f ? w / e : (p.mode == MPPIB_MODE_SIMPLE ? 0.f : U[r]);   // no valid sample: keep U
+        un[r] = p.mode == MPPIB_MODE_SIMPLE ? U[r] + wm : (1.0f - p.step_size_mean) * U[r] + p.step_size_mean * wm;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < NR; r += blockDim.x) {
+        float out = un[r];
+        if (p.filter_u) {
+            const int t = r / nu, j = r % nu;
+            float s = 0.f;
+            if (t < 4) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) s += c_sg_edge[t][i] * un[i * nu + j];
+                s *= (1.0f / 1155.0f);
+            } else if (t >= T - 4) {
+                const int ee = T - 1 - t;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) s += c_sg_edge[ee][i] * un[(T - 1 - i) * nu + j];
+                s *= (1.0f / 1155.0f);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) s += c_sg_mid[i] * un[(t - 4 + i) * nu + j];
+                s *= (1.0f / 231.0f);
+            }
+            out = fminf(fmaxf(s, p.u_min[j]), p.u_max[j]);   // smoothing may overshoot the bounds at the edges
+        }
+        U[r] = out;
+        if (r < nu) { action_out[r] = out; if (action_mirror) action_mirror[r] = out; }
+    }
+    if (threadIdx.x == 0 && stats) { stats[0] = b; stats[1] = e; }
+}
+
 template <int W, int NS>
 __global__ void __launch_bounds__(NT, 1)
 mppib_reduce_kernel(const __grid_constant__ MppibParams p, const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_c,
               int nu, int xbox_rows, const float* __restrict__ U, float* __restrict__ scratch, unsigned int* __restrict__ ticket,
-              float* __restrict__ partial, const __grid_constant__ PeerArgs peers) {
+              float* __restrict__ partial, const __grid_constant__ PeerArgs peers, float* __restrict__ fin_U, float* __restrict__ fin_action,
+              float* __restrict__ fin_stats, float* __restrict__ fin_mirror) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int KPL = W / 32;   // samples per lane
     const int K = p.K, T = p.T, NR = T * nu;
@@ -266,14 +323,15 @@ mppib_reduce_kernel(const __grid_constant__ MppibParams p, const __grid_constant
             }
         }
         if (tid == 0) *ticket = 0u;
+        if (fin_U != nullptr) {
+            // single-GPU plans: this CTA is the last one alive and holds the shard row -> do K4's work here (U update, savgol,
+            // first action) instead of launching another kernel.  Every CTA read U in its prologue, long before this point.
+            __threadfence();
+            __syncthreads();
+            finalize_rows(p, nu, partial, 1, P, fin_U, fin_action, fin_stats, fin_mirror, tiles);
+        }
     }
 }
-
-__constant__ float c_sg_mid[9] = {-21.f, 14.f, 39.f, 54.f, 59.f, 54.f, 39.f, 14.f, -21.f};
-__constant__ float c_sg_edge[4][9] = {{763.f, 441.f, 189.f, 7.f, -105.f, -147.f, -119.f, -21.f, 147.f},
-                                      {441.f, 322.f, 220.5f, 136.5f, 70.f, 21.f, -10.5f, -24.5f, -21.f},
-                                      {189.f, 220.5f, 232.f, 223.5f, 195.f, 146.5f, 78.f, -10.5f, -119.f},
-                                      {7.f, 136.5f, 223.5f, 268.f, 270.f, 229.5f, 146.5f, 21.f, -147.f}};
 
 // K4: combine G shard partials, U update, optional Savitzky-Golay (window 9, order 2, 'interp' edges), action out.
 __global__ void __launch_bounds__(256)
@@ -308,49 +366,7 @@ mppib_finalize_kernel(const __grid_constant__ MppibParams p, int nu, const float
         partials = reinterpret_cast<const float*>(win + MPPIB_WIN_DATA_OFF) + (size_t)(seq & 1u) * G * peers.pcap;
         P = peers.pcap;
     }
-    float* sg = un + NR;
-    const float inv_lambda = 1.0f / p.lambda_;
-    float b = INFINITY;
-    for (int gidx = 0; gidx < G; ++gidx) if (__ldcg(&partials[(size_t)gidx * P + 1]) > 0.f) b = fminf(b, __ldcg(&partials[(size_t)gidx * P]));
-    for (int gidx = threadIdx.x; gidx < G; gidx += blockDim.x) {
-        const float eg = __ldcg(&partials[(size_t)gidx * P + 1]);
-        sg[gidx] = eg > 0.f ? expf(-(__ldcg(&partials[(size_t)gidx * P]) - b) * inv_lambda) : 0.f;
-    }
-    __syncthreads();
-    float e = 0.f;
-    for (int gidx = 0; gidx < G; ++gidx) e += sg[gidx] * __ldcg(&partials[(size_t)gidx * P + 1]);
-    for (int r = threadIdx.x; r < NR; r += blockDim.x) {
-        float w = 0.f;
-        for (int gidx = 0; gidx < G; ++gidx) w += sg[gidx] * __ldcg(&partials[(size_t)gidx * P + 2 + r]);
-        const float wm = e > 0.f ? w / e : (p.mode == MPPIB_MODE_SIMPLE ? 0.f : U[r]);   // no valid sample: keep U
-        un[r] = p.mode == MPPIB_MODE_SIMPLE ? U[r] + wm : (1.0f - p.step_size_mean) * U[r] + p.step_size_mean * wm;
-    }
-    __syncthreads();
-    for (int r = threadIdx.x; r < NR; r += blockDim.x) {
-        float out = un[r];
-        if (p.filter_u) {
-            const int t = r / nu, j = r % nu;
-            float s = 0.f;
-            if (t < 4) {
-#pragma unroll
-                for (int i = 0; i < 9; ++i) s += c_sg_edge[t][i] * un[i * nu + j];
-                s *= (1.0f / 1155.0f);
-            } else if (t >= T - 4) {
-                const int ee = T - 1 - t;
-#pragma unroll
-                for (int i = 0; i < 9; ++i) s += c_sg_edge[ee][i] * un[(T - 1 - i) * nu + j];
-                s *= (1.0f / 1155.0f);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 9; ++i) s += c_sg_mid[i] * un[(t - 4 + i) * nu + j];
-                s *= (1.0f / 231.0f);
-            }
-            out = fminf(fmaxf(s, p.u_min[j]), p.u_max[j]);   // smoothing may overshoot the bounds at the edges
-        }
-        U[r] = out;
-        if (r < nu) { action_out[r] = out; if (action_mirror) action_mirror[r] = out; }
-    }
-    if (threadIdx.x == 0 && stats) { stats[0] = b; stats[1] = e; }
+    finalize_rows(p, nu, partials, G, P, U, action_out, stats, action_mirror, un);
     if (threadIdx.x == 0 && partials_in == nullptr) *reinterpret_cast<volatile uint32_t*>(peers.win[peers.rank]) = seq;   // exchange `seq` consumed
 }
 
@@ -412,7 +428,8 @@ static PeerArgs reduce_peers(const MppibContext* c) {
 }
 
 template <int W, int NS>
-int launch_reduce_t(MppibContext* c, const float* cost, const float* x, const float* U, float* partial, cudaStream_t s) {
+int launch_reduce_t(MppibContext* c, const float* cost, const float* x, const float* U, float* partial, float* fin_U, float* fin_action,
+                    float* fin_stats, cudaStream_t s) {
     const int T = c->params.T, nu = c->model.nu, NR = T * nu, K = c->params.K;
     const size_t smem = reduce_smem_bytes<W, NS>(T, nu);
     MPPIB_REQUIRE(smem <= 226 * 1024, "mppib_reduce: ring of %zu bytes exceeds shared memory", smem);
@@ -433,23 +450,25 @@ int launch_reduce_t(MppibContext* c, const float* cost, const float* x, const fl
     if (const char* e = getenv("MPPIB_K3_GRID")) { const int g = atoi(e); if (g >= 1 && g < grid) grid = g; }   // tuning knob (tools/tune_reduce.py)
     if (grid > MAX_GRID) grid = MAX_GRID;
     MPPIB_REQUIRE(grid <= c->reduce_max_ctas, "mppib_reduce: scratch too small");
-    mppib_reduce_kernel<W, NS><<<grid, NT, smem, s>>>(c->params, tm_x, tm_c, nu, xbox_rows, U, c->reduce_scratch, c->reduce_ticket, partial, reduce_peers(c));
+    mppib_reduce_kernel<W, NS><<<grid, NT, smem, s>>>(c->params, tm_x, tm_c, nu, xbox_rows, U, c->reduce_scratch, c->reduce_ticket, partial, reduce_peers(c), fin_U, fin_action,
+                                                       fin_stats, fin_U ? c->action_mirror : nullptr);
     MPPIB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 }  // namespace
 
-int launch_reduce(MppibContext* c, const float* cost, const float* x, const float* U, float* partial, cudaStream_t s) {
+int launch_reduce(MppibContext* c, const float* cost, const float* x, const float* U, float* partial, float* fin_U, float* fin_action,
+                  float* fin_stats, cudaStream_t s) {
     const int T = c->params.T, nu = c->model.nu;
     MPPIB_REQUIRE(T * nu <= RPT * NT, "mppib_reduce: T*nu = %d exceeds %d", T * nu, RPT * NT);
     MPPIB_REQUIRE(T <= 256, "mppib_reduce: T = %d exceeds the 256-row TMA box", T);
     // wide tiles once every SM has one; narrow tiles keep all SMs busy at small K
     bool wide = c->params.K >= 64 * c->num_sms && reduce_smem_bytes<64, 3>(T, nu) <= 226 * 1024;   // tools/tune_reduce.py: 12.5 -> 11.7 us at K = 10 000
     if (const char* e = getenv("MPPIB_K3_WIDE")) wide = atoi(e) != 0 && reduce_smem_bytes<64, 3>(T, nu) <= 226 * 1024;   // tuning knob
-    if (wide) return launch_reduce_t<64, 3>(c, cost, x, U, partial, s);
-    if (reduce_smem_bytes<32, 4>(T, nu) <= 226 * 1024) return launch_reduce_t<32, 4>(c, cost, x, U, partial, s);
-    return launch_reduce_t<32, 2>(c, cost, x, U, partial, s);
+    if (wide) return launch_reduce_t<64, 3>(c, cost, x, U, partial, fin_U, fin_action, fin_stats, s);
+    if (reduce_smem_bytes<32, 4>(T, nu) <= 226 * 1024) return launch_reduce_t<32, 4>(c, cost, x, U, partial, fin_U, fin_action, fin_stats, s);
+    return launch_reduce_t<32, 2>(c, cost, x, U, partial, fin_U, fin_action, fin_stats, s);
 }
 
 int launch_finalize(MppibContext* c, const float* partials, int G, float* U, float* action_out, float* stats, cudaStream_t s) {

@@ -265,6 +265,9 @@ class MPPIPlanner:
         self.sim.rollout_all(self.actions)
         cost = self._cost_batched()
         x = self.noise if be.params.mode == MODE_SIMPLE else self.actions
+        if self.world == 1 and hasattr(be, "reduce_finalize"):
+            be.reduce_finalize(cost, x, self.U, self.partial, self._action, self.stats)      # K3 + K4 in one launch
+            return
         be.reduce(cost, x, self.U, self.partial)
         partials, G = self._exchange()
         be.finalize(partials, G, self.U, self._action, self.stats)

@@ -555,3 +555,27 @@ def test_k2_rollout_parity_further_robots(oracle, actor, link, u_lim):
     assert np.abs(s[nd:2 * nd] - st_ref[nd:2 * nd]).max() <= 5e-3
     assert np.abs(o[0:3] - obs_ref[0:3]).max() <= 1e-4
     assert np.abs(s[:nd] - state0[:nd, None]).max() > 1e-2            # something actually moved
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,filt", [("simple", True), ("halton-spline", False), ("simple", False)])
+def test_fused_reduce_finalize_equals_two_launches(mode, filt):
+    """mppib_reduce_finalize (K4 done by the last CTA of K3) == mppib_reduce + mppib_finalize, bit for bit."""
+    K, T = 4100, 30
+    sc, p, _ = panda_setup(K=K, T=T, mode=mode, filter_u=filt)
+    be = gpu_backend(sc, p)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn((T, sc.nu, K), device=DEV, generator=g) * 0.2
+    cost = torch.rand((T, K), device=DEV, generator=g) * 5
+    cost[3, 17] = float("nan")                                           # a rejected sample goes through both paths
+    U0 = torch.randn((T, sc.nu), device=DEV, generator=g) * 0.05
+    Ua, Ub = U0.clone(), U0.clone()
+    pa, pb = torch.zeros(2 + T * sc.nu, device=DEV), torch.zeros(2 + T * sc.nu, device=DEV)
+    aa, ab = torch.zeros(sc.nu, device=DEV), torch.zeros(sc.nu, device=DEV)
+    sa, sb = torch.zeros(2, device=DEV), torch.zeros(2, device=DEV)
+    be.reduce(cost, x, Ua, pa)
+    be.finalize(pa.view(1, -1), 1, Ua, aa, sa)
+    be.reduce_finalize(cost, x, Ub, pb, ab, sb)
+    torch.cuda.synchronize()
+    assert torch.equal(pa, pb) and torch.equal(Ua, Ub) and torch.equal(aa, ab) and torch.equal(sa, sb)
+    assert not torch.equal(Ua, U0)
