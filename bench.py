@@ -215,6 +215,8 @@ def time_kernels(planner, reps=20):
     out["reduce_us_warm_l2"] = t(lambda: be.reduce(cost, x, m.U, m.partial))
     u_tmp = m.U.clone()
     out["finalize_us"] = t(lambda: be.finalize(m.partial.view(1, -1), 1, u_tmp, m._action, m.stats))
+    if m.world == 1:        # what a single-GPU plan actually launches: K3 with K4 done by its last CTA
+        out["reduce_finalize_fused_us_warm_l2"] = t(lambda: be.reduce_finalize(cost, x, u_tmp, m.partial, m._action, m.stats))
     return out
 
 
