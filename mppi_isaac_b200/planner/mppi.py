@@ -137,7 +137,8 @@ class MPPIPlanner:
         except RuntimeError as e:
             ok, why = 0, str(e)
         handles = [None] * self.world
-        dist.all_gather_object(handles, handle, group=self.pg)
+        with torch.cuda.device(torch.device(self.device)):     # object collectives stage through the CURRENT device
+            dist.all_gather_object(handles, handle, group=self.pg)
         if ok and all(h is not None for h in handles):
             try:
                 for g, h in enumerate(handles):
