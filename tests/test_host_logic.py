@@ -382,3 +382,35 @@ def test_further_example_robots_plan_through_the_api(task, objective, q):
     assert bool(((a1 >= lo - 1e-6) & (a1 <= hi + 1e-6)).all())
     if sc.model.nshapes:
         assert 12 <= sc.model.max_contacts <= 24                                               # sized to the SM's shared memory
+
+
+def test_examples_panda_planner_and_world_close_the_loop_over_rpc():
+    """examples/panda: the planner process' object behind RpcServer, the world process' one-env RolloutSim driving it through
+    RpcClient with torch.save bytes (the reference's planner.py / world.py split, examples/panda/planner.py:43-48, world.py:35-50)."""
+    import os
+    import sys
+    import threading
+    ex = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "panda")
+    sys.path.insert(0, ex)
+    try:
+        import planner as ex_planner
+        import world as ex_world
+    finally:
+        sys.path.remove(ex)
+    from mppi_isaac_b200.utils.rpc import RpcClient, RpcServer
+    pl = ex_planner.build_planner(samples=96, device="cpu", backend=OracleBackend(nthreads=8))
+    cfg, sim = ex_world.build_world(device="cpu", backend=OracleBackend(nthreads=1))
+    server = RpcServer(pl).bind("tcp://127.0.0.1:*")
+    th = threading.Thread(target=server.run, daemon=True)
+    th.start()
+    try:
+        client = RpcClient(server.last_endpoint, timeout_s=60)
+        d0 = ex_world.goal_distance(sim)
+        for _ in range(8):
+            a = ex_world.control_step(sim, client)
+        assert a.shape == (7,) and torch.isfinite(a).all()
+        assert ex_world.goal_distance(sim) < d0 - 0.01 and server.calls == 8
+        client.close()
+    finally:
+        server.stop()
+        th.join(timeout=5)
