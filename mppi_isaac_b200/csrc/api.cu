@@ -33,7 +33,7 @@ static int validate(const MppibModel* m, const MppibParams* p) {
         MPPIB_REQUIRE(m->cmd_i0[i] >= 0 && m->cmd_i0[i] < m->nu && m->cmd_i1[i] >= 0 && m->cmd_i1[i] < m->nu, "cmd map of dof %d out of range", i);
     }
     MPPIB_REQUIRE(!m->planar_base || (m->nb >= 3 && m->nu >= 2), "planar_base needs three virtual joints and a (v, omega) command");
-    MPPIB_REQUIRE(p->K >= 4 && p->K % 4 == 0, "K=%d must be a positive multiple of 4 (128-bit loads)", p->K);
+    MPPIB_REQUIRE(p->K >= 1, "K=%d must be positive", p->K);     // K % 4 == 0 is a requirement of the reduction only (checked there)
     MPPIB_REQUIRE(p->T >= 1 && p->substeps >= 1 && p->dt > 0.f, "bad T/substeps/dt");
     MPPIB_REQUIRE(p->lambda_ > 0.f, "lambda must be positive");
     MPPIB_REQUIRE(!(p->filter_u && p->T < 9), "filter_u needs T >= 9");

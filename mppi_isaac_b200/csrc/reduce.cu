@@ -461,6 +461,7 @@ int launch_reduce_t(MppibContext* c, const float* cost, const float* x, const fl
 int launch_reduce(MppibContext* c, const float* cost, const float* x, const float* U, float* partial, float* fin_U, float* fin_action,
                   float* fin_stats, cudaStream_t s) {
     const int T = c->params.T, nu = c->model.nu;
+    MPPIB_REQUIRE(c->params.K >= 4 && c->params.K % 4 == 0, "mppib_reduce: K=%d must be a positive multiple of 4 (16-byte rows for TMA / 128-bit loads)", c->params.K);
     MPPIB_REQUIRE(T * nu <= RPT * NT, "mppib_reduce: T*nu = %d exceeds %d", T * nu, RPT * NT);
     MPPIB_REQUIRE(T <= 256, "mppib_reduce: T = %d exceeds the 256-row TMA box", T);
     // wide tiles once every SM has one; narrow tiles keep all SMs busy at small K
