@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MPPIB_ABI_VERSION 10
+#define MPPIB_ABI_VERSION 11
 
 #define MPPIB_MAX_BODIES 16   /* moving (1-DoF) bodies of the articulation            */
 #define MPPIB_MAX_LINKS  32   /* URDF links whose state can be observed               */
@@ -282,6 +282,10 @@ int32_t mppib_peer_close(MppibHandle h);
  * b_si = 0).  b may be NULL when w_pos == 0.                                                                          */
 int32_t mppib_cost_pose(int64_t n, const float* a, int64_t a_si, int64_t a_sr, const float* b, int64_t b_si,
                         int64_t b_sr, float w_pos, float w_ori, float* cost, int32_t accumulate, void* stream);
+
+/* Shared-memory bytes one 32-rollout CTA of mppib_rollout needs for this model (host-side arithmetic, no device access):
+ * lets the model compiler size `max_contacts` to what fits an SM (226 KB usable) before a handle exists.                     */
+int64_t mppib_rollout_smem_bytes(const MppibModel* model_h);
 
 /* Optional host mirror of the action: when set, mppib_finalize also stores action_out[0..nu) to `mirror` -- a pointer into
  * PINNED host memory (device-addressable under unified addressing), so the caller of the reference's compute_action* only

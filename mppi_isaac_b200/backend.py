@@ -22,7 +22,7 @@ SYMBOLS = [
     "mppib_abi_version", "mppib_last_error", "mppib_create", "mppib_destroy", "mppib_set_params",
     "mppib_set_model", "mppib_state_size", "mppib_obs_size", "mppib_sample", "mppib_rollout",
     "mppib_reduce", "mppib_finalize", "mppib_shift", "mppib_noise_library", "mppib_sample_library",
-    "mppib_peer_alloc", "mppib_peer_open", "mppib_peer_close", "mppib_cost_pose", "mppib_set_action_mirror", "mppib_reduce_finalize",
+    "mppib_peer_alloc", "mppib_peer_open", "mppib_peer_close", "mppib_cost_pose", "mppib_set_action_mirror", "mppib_reduce_finalize", "mppib_rollout_smem_bytes",
 ]
 
 
@@ -43,7 +43,7 @@ def load_library():
     lib.mppib_last_error.restype = C.c_char_p
     for name in SYMBOLS:
         if name != "mppib_last_error":
-            getattr(lib, name).restype = C.c_int32
+            getattr(lib, name).restype = C.c_int64 if name == "mppib_rollout_smem_bytes" else C.c_int32
     if lib.mppib_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libmppib.so ABI {lib.mppib_abi_version()} != python binding {ABI_VERSION}; rebuild")
     _lib = lib

@@ -233,6 +233,11 @@ int32_t mppib_finalize(MppibHandle h, const float* partials, int32_t G, float* U
     return launch_finalize(h, partials, G, U, action_out, stats, (cudaStream_t)stream);
 }
 
+int64_t mppib_rollout_smem_bytes(const MppibModel* model_h) {
+    if (!model_h) return -1;
+    return (int64_t)rollout_smem_bytes(*model_h);
+}
+
 int32_t mppib_set_action_mirror(MppibHandle h, float* mirror) {
     MPPIB_REQUIRE(h != nullptr, "null handle");
     h->action_mirror = mirror;

@@ -76,6 +76,7 @@ int launch_reduce(MppibContext* c, const float* cost, const float* x, const floa
                   float* fin_stats, cudaStream_t s);
 int launch_finalize(MppibContext* c, const float* partials, int G, float* U, float* action_out, float* stats, cudaStream_t s);
 int launch_shift(MppibContext* c, float* U, uint32_t* plan_ctr, cudaStream_t s);
+long long rollout_smem_bytes(const MppibModel& m);
 int launch_cost_pose(long long n, const float* a, long long a_si, long long a_sr, const float* b, long long b_si, long long b_sr, float w_pos,
                      float w_ori, float* cost, int accumulate, cudaStream_t s);
 

@@ -581,12 +581,20 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
     }
 }
 
+static bool is_chain(const MppibModel& m) {
+    for (int i = 0; i < m.nb; ++i) if (m.parent[i] != i - 1) return false;
+    return true;
+}
+static size_t smem_bytes_for(const MppibModel& m, bool chain, bool contact) {
+    const int nslot = (chain && !contact) ? NSLOT_CHAIN : NSLOT_TREE;
+    const contact::Layout L(m.nb, m.nfree, m.nshapes, m.max_contacts);
+    return sizeof(float) * 32 * ((size_t)m.nb * nslot + (contact ? (size_t)L.total : 0) + 2 * (size_t)m.nu);
+}
+
 template <bool CHAIN, bool CONTACT>
 int launch_t(MppibContext* c, const float* state0, const float* root0, float* state, const float* actions, int t0, int nsteps, float* obs, cudaStream_t s) {
     const int K = c->params.K;
-    const int nslot = (CHAIN && !CONTACT) ? NSLOT_CHAIN : NSLOT_TREE;
-    const contact::Layout L(c->model.nb, c->model.nfree, c->model.nshapes, c->model.max_contacts);
-    const size_t smem = sizeof(float) * 32 * ((size_t)c->model.nb * nslot + (CONTACT ? (size_t)L.total : 0) + 2 * (size_t)c->model.nu);
+    const size_t smem = smem_bytes_for(c->model, CHAIN, CONTACT);
     MPPIB_REQUIRE(smem <= 226 * 1024, "mppib_rollout: %zu bytes of shared memory per CTA exceed the SM (too many bodies / shapes)", smem);
     static size_t smem_attr[64] = {0};              // per device: the attribute belongs to the function on ONE device
     size_t& attr = smem_attr[c->device & 63];
@@ -605,8 +613,7 @@ int launch_t(MppibContext* c, const float* state0, const float* root0, float* st
 int launch_rollout(MppibContext* c, const float* state0, const float* root0, float* state, const float* actions, int t0, int nsteps,
                    float* obs, cudaStream_t s) {
     const MppibModel& m = c->model;
-    bool chain = true;
-    for (int i = 0; i < m.nb; ++i) if (m.parent[i] != i - 1) chain = false;
+    const bool chain = is_chain(m);
     const bool contact = m.nfree > 0 || m.nshapes > 0;
     if (contact) {
         MPPIB_REQUIRE(root0 != nullptr, "mppib_rollout: root0 is required for scenes with free bodies / collision boxes");
@@ -616,3 +623,5 @@ int launch_rollout(MppibContext* c, const float* state0, const float* root0, flo
     if (chain) return launch_t<true, false>(c, state0, root0, state, actions, t0, nsteps, obs, s);
     return launch_t<false, false>(c, state0, root0, state, actions, t0, nsteps, obs, s);
 }
+
+long long rollout_smem_bytes(const MppibModel& m) { return (long long)smem_bytes_for(m, is_chain(m), m.nfree > 0 || m.nshapes > 0); }

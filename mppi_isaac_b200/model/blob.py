@@ -18,7 +18,7 @@ import numpy as np
 
 from .urdf import RobotModel, compile_urdf, load_compiled, quat_xyzw_to_R, R_to_quat_xyzw
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 MAX_BODIES, MAX_LINKS, MAX_NU, MAX_OBS, MAX_FREE, MAX_SHAPES = 16, 32, 16, 64, 4, 24
 MAX_CONTACTS, MAX_SLOTS = 24, 8
 
@@ -308,16 +308,21 @@ def build_scene(actor_cfgs: list, gravity=(0.0, 0.0, -9.8), assets_dirs=None, su
             m.free_slot[sh["owner"]] = m.shape_slot[si]
     m.nfree, m.nshapes, m.ncontact_slots = nfree, len(shapes), len(contact_slot)
     m.nactors = len(actor_cfgs)
-    # contact capacity: as many points as the rollout kernel's shared-memory working set allows (csrc/rollout.cu, contact.cuh:
-    # 95 slots per body + 35 per free body + 17 per shape + 18 per contact + 3 per joint + 24 net-force + 2 nu action slots,
-    # 128 B per slot for a 32-rollout CTA, 226 KB usable), at most MAX_CONTACTS
+    # contact capacity: as many points as the rollout kernel's shared-memory working set allows -- the library reports the bytes
+    # one 32-rollout CTA needs for a model (mppib_rollout_smem_bytes, include/mppib.h); 226 KB of an SM are usable
     if nfree or shapes:
-        fixed = 95 * m.nb + 35 * nfree + 17 * len(shapes) + 3 * m.nb + 3 * MAX_SLOTS + 2 * m.nu
-        cap = min(MAX_CONTACTS, (226 * 1024 // 128 - fixed) // 18)
+        import ctypes as C
+        from ..backend import load_library
+        lib = load_library()
+        cap = MAX_CONTACTS
+        while cap >= 1:
+            m.max_contacts = cap
+            if lib.mppib_rollout_smem_bytes(C.byref(m)) <= 226 * 1024:
+                break
+            cap -= 1
         if cap < 12:
             raise NotImplementedError(f"scene too large for one SM's shared memory: {m.nb} bodies, {len(shapes)} collision boxes leave room for "
                                       f"{cap} contact points per rollout (12 needed)")
-        m.max_contacts = cap
     else:
         m.max_contacts = MAX_CONTACTS
     m.ground_plane, m.ground_friction = 1, 1.0                        # isaacgym_utils.py:61-68
