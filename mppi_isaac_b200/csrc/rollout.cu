@@ -37,6 +37,9 @@
 #ifndef ROLL_S1_PIPE
 #define ROLL_S1_PIPE 0        // software-pipelined sweep 1 for serial chains (kinematics of body i+1 with the dynamics terms of body i)
 #endif
+#ifndef ROLL_UNROLL_S2
+#define ROLL_UNROLL_S2 1      // unroll factor of sweep 2 (articulated inertias)
+#endif
 #ifndef ROLL_UNROLL_S3
 #define ROLL_UNROLL_S3 2      // unroll factor of sweep 3 (accelerations)
 #endif
@@ -483,7 +486,7 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
                 }
                 SpI Ic; V6 pc;   // contribution of the child (serial chains)
                 bool have_child = false;
-#pragma unroll 1
+                MPPIB_UNROLL(ROLL_UNROLL_S2)
                 for (int i = nb - 1; i >= 0; --i) {
                     const V6 S = ld6(sm, i * NSLOT + F_S, lane);
                     SpI IA; V6 pA;

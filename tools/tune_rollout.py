@@ -12,9 +12,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "tune_build")
 VARIANTS = {
     "base": [],
+    "s2u2": ["-DROLL_UNROLL_S2=2"],
+    "s2u2_s3u3": ["-DROLL_UNROLL_S2=2", "-DROLL_UNROLL_S3=3"],
+    "s3u3": ["-DROLL_UNROLL_S3=3"],
+    "maxreg128": ["-maxrregcount=128"],
     "s1pipe": ["-DROLL_S1_PIPE=1"],
-    "s1pipe_s3u1": ["-DROLL_S1_PIPE=1", "-DROLL_UNROLL_S3=1"],
-    "s3u4": ["-DROLL_UNROLL_S3=4"],
 }
 
 if sys.argv[1] == "build":
