@@ -170,7 +170,8 @@ typedef struct MppibObsItem {
 } MppibObsItem;
 
 typedef struct MppibParams {
-    int32_t K;                 /* samples on THIS device                                   */
+    int32_t K;                 /* samples on THIS device; mppib_reduce needs K % 4 == 0 (16-byte rows),
+                                  sampling / rollout accept any K >= 1 (a one-env world simulator)        */
     int32_t T;                 /* horizon                                                  */
     int32_t substeps;          /* isaacgym_wrapper.py:24                                   */
     float   dt;                /* model step; substep h = dt/substeps                      */
