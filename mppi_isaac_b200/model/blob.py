@@ -260,11 +260,17 @@ def build_scene(actor_cfgs: list, gravity=(0.0, 0.0, -9.8), assets_dirs=None, su
     for ai, a in enumerate(actor_cfgs):
         if ai == ra or not a.collision:
             continue
-        if a.type == "sphere":
-            raise NotImplementedError(f"colliding sphere actor '{a.name}' is not supported on this path (boxes only)")
-        if a.type != "box":
+        if a.type not in ("box", "sphere"):
             raise NotImplementedError(f"actor asset of type {a.type} is not yet implemented!")      # isaacgym_utils.py:54-56
-        half = 0.5 * np.asarray(a.size, float)[:3]
+        if a.type == "sphere":
+            # spheres collide through their bounding box, like every non-box robot collision geometry on this path;
+            # size[0] is the radius (isaacgym_utils.py:42-52).  Only FIXED spheres: the obstacles of compute_action(obst=...),
+            # whose pose is re-read from the root state at the start of every plan and held over the horizon.
+            if not a.fixed:
+                raise NotImplementedError(f"free sphere actor '{a.name}': only fixed sphere obstacles are supported (as bounding boxes)")
+            half = np.full(3, float(a.size[0]))
+        else:
+            half = 0.5 * np.asarray(a.size, float)[:3]
         sigma = np.asarray(a.noise_sigma_size if a.noise_sigma_size is not None else [0, 0, 0], float)[:3]
         sh = dict(kind=OWNER_STATIC, owner=-1, actor=ai, half=half, pos=np.zeros(3), quat=np.array([0, 0, 0, 1.0]),
                   friction=float(a.friction), fric_pct=float(a.noise_percentage_friction), sigma=sigma, body=body_offset[ai])

@@ -414,3 +414,31 @@ def test_examples_panda_planner_and_world_close_the_loop_over_rpc():
     finally:
         server.stop()
         th.join(timeout=5)
+
+
+def test_compute_action_with_sphere_obstacles():
+    """compute_action(q, qdot, obst={...}) (mppi_isaac.py:71-85, isaacgym_wrapper.py:695-746): obstacles become fixed actors named
+    sphere<i>; on this path they collide through their bounding boxes and are held at their pose over the horizon."""
+    p = make(point_cfg(K=64, T=12), PointReachObjective(), observe="all")
+    obst = {"o0": {"position": [0.75, 0.0, 0.1], "velocity": [0.0, 0.0, 0.0], "size": [0.2]}}
+    a0 = p.compute_action([0.1, 0.0, 0.0], [0.0, 0.0, 0.0], obst=obst)         # first call: actor added, rollout model rebuilt
+    a1 = p.compute_action([0.1, 0.0, 0.0], [0.0, 0.0, 0.0], obst=obst)
+    assert [a.name for a in p.sim.env_cfg][-1] == "sphere0" and p.sim.scene.model.nshapes >= 2
+    assert torch.isfinite(a0).all() and torch.isfinite(a1).all()
+    np.testing.assert_allclose(p.sim.get_actor_position_by_name("sphere0")[0].numpy(), [0.75, 0.0, 0.1], atol=1e-6)
+    # the obstacle is solid: driving the point robot along +x for 2 s stops at the box face instead of reaching x = 0.1 + 1.5 * 2
+    s = p.sim
+    s.reset_robot_state([0.1, 0.0, 0.0], [0.0, 0.0, 0.0])
+    s.begin_step_mode()
+    u = torch.zeros(64, 3); u[:, 0] = 1.5
+    for _ in range(40):
+        p.dynamics(None, u)
+    x = float(s._dof_state[0, 0])
+    assert 0.2 < x < 0.75 - 0.2 + 0.05, x
+    moved = obst | {"o0": {"position": [0.75, 2.0, 0.1], "velocity": [0.0, 0.0, 0.0], "size": [0.2]}}
+    p.compute_action([0.1, 0.0, 0.0], [0.0, 0.0, 0.0], obst=moved)             # same actor, new pose: no rebuild, free path now
+    s.reset_robot_state([0.1, 0.0, 0.0], [0.0, 0.0, 0.0])
+    s.begin_step_mode()
+    for _ in range(40):
+        p.dynamics(None, u)
+    assert float(s._dof_state[0, 0]) > 1.5
