@@ -347,6 +347,25 @@ def run_gpu_arm(args, rank, world, local_rank):
             "clocks": clocks,
         }
         if world == 1:
+            # transparency: the same plan with the Objective written as plain torch ops (~28 element-wise launches instead of the
+            # one fused ops.pose_cost launch) -- what an unmodified user Objective costs
+            planner.objective.fused = False
+            planner.mppi.invalidate_graph()
+            for _ in range(3):
+                planner.mppi.command()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 30))]
+            for a, b in ev:
+                flush.zero_()
+                a.record()
+                planner.mppi.command()
+                b.record()
+            torch.cuda.synchronize()
+            ms_torch_obj = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+            line["objective_as_torch_ops"] = {"ms_per_step": ms_torch_obj, "plan_hz": 1e3 / ms_torch_obj,
+                                              "value": k_total * T_HORIZON / (ms_torch_obj * 1e-3), "unit": UNIT}
+            planner.objective.fused = True
+            planner.mppi.invalidate_graph()
+            planner.mppi.command()
             kt = time_kernels(planner)
             roof = k3_roofline(planner, peak, peak_src, [K_PER_GPU, 65536, 262144])
             head = roof[0]
