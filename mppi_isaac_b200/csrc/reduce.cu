@@ -21,7 +21,7 @@ namespace {
 
 constexpr int NT = 256;         // threads per CTA
 constexpr int RPT = 2;          // rows of W per thread (T*nu <= 512)
-constexpr int MAX_GRID = 256;   // persistent CTAs (<= scratch rows)
+constexpr int MAX_GRID = 512;   // persistent CTAs (<= scratch rows)
 
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
@@ -115,8 +115,8 @@ __device__ __forceinline__ void finalize_rows(const MppibParams& p, int nu, cons
     if (threadIdx.x == 0 && stats) { stats[0] = b; stats[1] = e; }
 }
 
-template <int W, int NS>
-__global__ void __launch_bounds__(NT, 1)
+template <int W, int NS, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 mppib_reduce_kernel(const __grid_constant__ MppibParams p, const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_c,
               int nu, int xbox_rows, const float* __restrict__ U, float* __restrict__ scratch, unsigned int* __restrict__ ticket,
               float* __restrict__ partial, const __grid_constant__ PeerArgs peers, float* __restrict__ fin_U, float* __restrict__ fin_action,
@@ -272,13 +272,15 @@ mppib_reduce_kernel(const __grid_constant__ MppibParams p, const __grid_constant
     float* fold = tiles + MAX_GRID;      // [4][PP]
     {
         float b = (tid < G) ? __ldcg(scratch + (size_t)tid * ((((P + 3) >> 2) << 2))) : INFINITY;
-        float bm = warp_min(b);
+        const float b2 = (tid + NT < G) ? __ldcg(scratch + (size_t)(tid + NT) * ((((P + 3) >> 2) << 2))) : INFINITY;   // CTAs 256..511
+        float bm = warp_min(fminf(b, b2));
         if (lane == 0) misc[warp] = bm;
         __syncthreads();
         float bb = INFINITY;
 #pragma unroll
         for (int w8 = 0; w8 < 8; ++w8) bb = fminf(bb, misc[w8]);
         if (tid < G) sc[tid] = (b == INFINITY) ? 0.f : expf(-(b - bb) * inv_lambda);
+        if (tid + NT < G) sc[tid + NT] = (b2 == INFINITY) ? 0.f : expf(-(b2 - bb) * inv_lambda);
         __syncthreads();
         // parallel fold with deep memory-level parallelism: P4 = ceil(P/4) float4 columns x 4 CTA groups of 64 threads;
         // thread (cg, e4) sums CTAs c = cg, cg+4, ... with 8 independent 128-bit L2 loads in flight
@@ -427,7 +429,7 @@ static PeerArgs reduce_peers(const MppibContext* c) {
     return a;
 }
 
-template <int W, int NS>
+template <int W, int NS, int MINB = 1>
 int launch_reduce_t(MppibContext* c, const float* cost, const float* x, const float* U, float* partial, float* fin_U, float* fin_action,
                     float* fin_stats, cudaStream_t s) {
     const int T = c->params.T, nu = c->model.nu, NR = T * nu, K = c->params.K;
@@ -436,7 +438,7 @@ int launch_reduce_t(MppibContext* c, const float* cost, const float* x, const fl
     static size_t smem_attr[64] = {0};              // per device: the attribute belongs to the function on ONE device
     size_t& attr = smem_attr[c->device & 63];
     if (smem > attr) {
-        MPPIB_CHECK_CUDA(cudaFuncSetAttribute(mppib_reduce_kernel<W, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MPPIB_CHECK_CUDA(cudaFuncSetAttribute(mppib_reduce_kernel<W, NS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
     // a TMA box has at most 256 rows: split the T*nu rows into equal boxes (largest divisor of T*nu that fits)
@@ -447,10 +449,10 @@ int launch_reduce_t(MppibContext* c, const float* cost, const float* x, const fl
     if (int rc = make_map(&tm_c, cost, T, K, T, W)) return rc;
     const int ntiles = (K + W - 1) / W;
     int grid = ntiles < c->num_sms ? ntiles : c->num_sms;
-    if (const char* e = getenv("MPPIB_K3_GRID")) { const int g = atoi(e); if (g >= 1 && g < grid) grid = g; }   // tuning knob (tools/tune_reduce.py)
+    if (const char* e = getenv("MPPIB_K3_GRID")) { const int g = atoi(e); if (g >= 1 && g <= ntiles) grid = g; }   // tuning knob (tools/tune_reduce.py)
     if (grid > MAX_GRID) grid = MAX_GRID;
     MPPIB_REQUIRE(grid <= c->reduce_max_ctas, "mppib_reduce: scratch too small");
-    mppib_reduce_kernel<W, NS><<<grid, NT, smem, s>>>(c->params, tm_x, tm_c, nu, xbox_rows, U, c->reduce_scratch, c->reduce_ticket, partial, reduce_peers(c), fin_U, fin_action,
+    mppib_reduce_kernel<W, NS, MINB><<<grid, NT, smem, s>>>(c->params, tm_x, tm_c, nu, xbox_rows, U, c->reduce_scratch, c->reduce_ticket, partial, reduce_peers(c), fin_U, fin_action,
                                                        fin_stats, fin_U ? c->action_mirror : nullptr);
     MPPIB_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -467,6 +469,12 @@ int launch_reduce(MppibContext* c, const float* cost, const float* x, const floa
     // wide tiles once every SM has one; narrow tiles keep all SMs busy at small K
     bool wide = c->params.K >= 64 * c->num_sms && reduce_smem_bytes<64, 3>(T, nu) <= 226 * 1024;   // tools/tune_reduce.py: 12.5 -> 11.7 us at K = 10 000
     if (const char* e = getenv("MPPIB_K3_WIDE")) wide = atoi(e) != 0 && reduce_smem_bytes<64, 3>(T, nu) <= 226 * 1024;   // tuning knob
+    if (const char* e = getenv("MPPIB_K3_VARIANT")) {          // tuning knob: "64x3" | "64x1" | "32x4" | "32x2"
+        if (!strcmp(e, "64x1")) return launch_reduce_t<64, 1, 2>(c, cost, x, U, partial, fin_U, fin_action, fin_stats, s);
+        if (!strcmp(e, "32x2")) return launch_reduce_t<32, 2, 2>(c, cost, x, U, partial, fin_U, fin_action, fin_stats, s);
+        if (!strcmp(e, "32x4")) return launch_reduce_t<32, 4>(c, cost, x, U, partial, fin_U, fin_action, fin_stats, s);
+        if (!strcmp(e, "64x3")) return launch_reduce_t<64, 3>(c, cost, x, U, partial, fin_U, fin_action, fin_stats, s);
+    }
     if (wide) return launch_reduce_t<64, 3>(c, cost, x, U, partial, fin_U, fin_action, fin_stats, s);
     if (reduce_smem_bytes<32, 4>(T, nu) <= 226 * 1024) return launch_reduce_t<32, 4>(c, cost, x, U, partial, fin_U, fin_action, fin_stats, s);
     return launch_reduce_t<32, 2>(c, cost, x, U, partial, fin_U, fin_action, fin_stats, s);

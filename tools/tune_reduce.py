@@ -13,15 +13,13 @@ code = ("import sys; sys.path.insert(0, %r); import bench, torch, numpy as np\n"
         "r = bench.k3_roofline(p, 6486.5, 'x', %r)\n"
         "print('RES', ' '.join('%%d:%%.2f' %% (e['K'], e['us']) for e in r))\n") % (ROOT, Ks)
 res = {}
-for grid in ("", "37", "74", "111"):
-    for wide in ("", "1"):
-        env = dict(os.environ)
-        if grid:
-            env["MPPIB_K3_GRID"] = grid
-        if wide:
-            env["MPPIB_K3_WIDE"] = wide
-        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
-        line = [l for l in out.stdout.splitlines() if l.startswith("RES")]
-        res[f"grid={grid or 'sms'} wide={wide or 'auto'}"] = line[0][4:] if line else out.stderr[-200:]
-        print(f"grid={grid or 'sms':4s} wide={wide or 'auto':4s}  {res[f'grid={grid or chr(115)+chr(109)+chr(115)} wide={wide or chr(97)+chr(117)+chr(116)+chr(111)}']}", flush=True)
+CASES = [{}, {"MPPIB_K3_VARIANT": "32x2", "MPPIB_K3_GRID": "296"}, {"MPPIB_K3_VARIANT": "64x1", "MPPIB_K3_GRID": "296"},
+         {"MPPIB_K3_VARIANT": "32x4"}, {"MPPIB_K3_VARIANT": "32x2", "MPPIB_K3_GRID": "148"}, {"MPPIB_K3_VARIANT": "32x2", "MPPIB_K3_GRID": "444"}]
+for case in CASES:
+    env = dict(os.environ, **case)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    line = [l for l in out.stdout.splitlines() if l.startswith("RES")]
+    key = " ".join(f"{k[9:]}={v}" for k, v in case.items()) or "default"
+    res[key] = line[0][4:] if line else out.stderr[-300:]
+    print(f"{key:32s} {res[key]}", flush=True)
 print(json.dumps(res))
