@@ -1,5 +1,6 @@
 // api.cu -- the C ABI of include/mppib.h (handle lifetime + thin launch wrappers).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -88,6 +89,8 @@ int32_t mppib_create(const MppibModel* model_h, const MppibParams* params_h, int
     c->model = *model_h;
     c->params = *params_h;
     c->num_sms = prop.multiProcessorCount;
+    c->k2_lanes = 1;
+    if (const char* e = getenv("MPPIB_K2_LANES")) c->k2_lanes = atoi(e) != 0;   // read once per handle, not per launch
     derive(c);
     if (int rc = alloc_scratch(c)) { delete c; return rc; }
     *out = c;

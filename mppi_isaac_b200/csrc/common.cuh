@@ -45,6 +45,7 @@ struct MppibContext {
     void* peer_win[MPPIB_MAX_PEERS];           // window base of every rank (own entry = local allocation)
     unsigned long long peer_timeout_ns;
     float* action_mirror;                      // pinned host mirror of the action written by K4 (nullable)
+    int k2_lanes;                              // K2 mapping for eligible scenes: 1 = one body per lane (default), 0 = one thread per rollout
 };
 
 // device view of the peer windows, passed by value to K3 / K4
@@ -77,6 +78,10 @@ int launch_reduce(MppibContext* c, const float* cost, const float* x, const floa
 int launch_finalize(MppibContext* c, const float* partials, int G, float* U, float* action_out, float* stats, cudaStream_t s);
 int launch_shift(MppibContext* c, float* U, uint32_t* plan_ctr, cudaStream_t s);
 long long rollout_smem_bytes(const MppibModel& m);
+// K2, lanes-per-rollout mapping for serial chains without contacts (rollout_lanes.cu)
+bool rollout_lanes_eligible(const MppibModel& m);
+int launch_rollout_lanes(MppibContext* c, const float* state0, float* state, const float* actions, int t0, int nsteps, float* obs,
+                         cudaStream_t s);
 int launch_cost_pose(long long n, const float* a, long long a_si, long long a_sr, const float* b, long long b_si, long long b_sr, float w_pos,
                      float w_ori, float* cost, int accumulate, cudaStream_t s);
 
