@@ -72,6 +72,7 @@ class CudaBackend:
         self.handle = C.c_void_p(0)
         self.model = None
         self.params = None
+        self._mirror_keepalive = None
         self.launches = 0   # kernels launched through this handle (bench.py's gpu_launches)
 
     # -- lifetime -------------------------------------------------------------------------------
@@ -84,6 +85,8 @@ class CudaBackend:
             self.destroy()
         self.model, self.params = model, params
         self._check(self.lib.mppib_create(C.byref(model), C.byref(params), C.c_int32(self.device.index), C.byref(self.handle)), "mppib_create")
+        if self._mirror_keepalive is not None:           # a re-created handle keeps writing the action to the same pinned mirror
+            self.set_action_mirror(self._mirror_keepalive)
 
     def destroy(self):
         if self.handle:

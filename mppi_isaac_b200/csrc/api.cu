@@ -79,7 +79,8 @@ int32_t mppib_create(const MppibModel* model_h, const MppibParams* params_h, int
     int ndev = 0;
     MPPIB_CHECK_CUDA(cudaGetDeviceCount(&ndev));
     MPPIB_REQUIRE(device >= 0 && device < ndev, "device %d not present (%d CUDA devices)", device, ndev);
-    MPPIB_CHECK_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);                   // the caller's current device is restored on return
+    MPPIB_CHECK_CUDA(guard.err);
     cudaDeviceProp prop;
     MPPIB_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
     MPPIB_REQUIRE(prop.major == 10, "this library is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
@@ -102,7 +103,7 @@ int32_t mppib_peer_close(MppibHandle h) {
     bool any = false;
     for (int g = 0; g < MPPIB_MAX_PEERS; ++g) any = any || h->peer_win[g] != nullptr;
     if (!any) { h->peer_world = 0; return 0; }
-    cudaSetDevice(h->device);
+    MPPIB_ON_DEVICE(h);
     cudaDeviceSynchronize();
     for (int g = 0; g < MPPIB_MAX_PEERS; ++g) {
         if (!h->peer_win[g]) continue;
@@ -118,7 +119,7 @@ int32_t mppib_peer_alloc(MppibHandle h, int32_t world, int32_t rank, unsigned ch
     MPPIB_REQUIRE(world >= 2 && world <= MPPIB_MAX_PEERS && rank >= 0 && rank < world, "mppib_peer_alloc: world %d / rank %d out of range (max %d ranks)", world, rank, MPPIB_MAX_PEERS);
     static_assert(sizeof(cudaIpcMemHandle_t) == MPPIB_IPC_HANDLE_BYTES, "IPC handle size");
     mppib_peer_close(h);
-    MPPIB_CHECK_CUDA(cudaSetDevice(h->device));
+    MPPIB_ON_DEVICE(h);
     const int P = 2 + h->params.T * h->model.nu;
     const int pcap = ((P + 3) >> 2) << 2;
     void* win = nullptr;
@@ -142,7 +143,7 @@ int32_t mppib_peer_open(MppibHandle h, int32_t peer, const unsigned char* ipc_ha
     MPPIB_REQUIRE(h->peer_world >= 2, "mppib_peer_open: call mppib_peer_alloc first");
     MPPIB_REQUIRE(peer >= 0 && peer < h->peer_world && peer != h->peer_rank, "mppib_peer_open: peer %d out of range", peer);
     MPPIB_REQUIRE(h->peer_win[peer] == nullptr, "mppib_peer_open: peer %d is already open", peer);
-    MPPIB_CHECK_CUDA(cudaSetDevice(h->device));
+    MPPIB_ON_DEVICE(h);
     cudaIpcMemHandle_t hd;
     memcpy(&hd, ipc_handle_h, sizeof(hd));
     void* win = nullptr;
@@ -153,7 +154,7 @@ int32_t mppib_peer_open(MppibHandle h, int32_t peer, const unsigned char* ipc_ha
 
 int32_t mppib_destroy(MppibHandle h) {
     if (!h) return 0;
-    cudaSetDevice(h->device);
+    MPPIB_ON_DEVICE(h);
     mppib_peer_close(h);
     if (h->reduce_scratch) cudaFree(h->reduce_scratch);
     if (h->reduce_ticket) cudaFree(h->reduce_ticket);
@@ -168,7 +169,7 @@ int32_t mppib_set_params(MppibHandle h, const MppibParams* params_h) {
     MPPIB_REQUIRE(h->peer_world <= 1 || 2 + params_h->T * h->model.nu <= h->peer_pcap, "mppib_set_params: T*nu outgrows the open peer window; close and re-open the peers");
     h->params = *params_h;
     derive(h);
-    if (resize) { MPPIB_CHECK_CUDA(cudaSetDevice(h->device)); return alloc_scratch(h); }
+    if (resize) { MPPIB_ON_DEVICE(h); return alloc_scratch(h); }
     return 0;
 }
 
@@ -179,7 +180,7 @@ int32_t mppib_set_model(MppibHandle h, const MppibModel* model_h) {
     MPPIB_REQUIRE(h->peer_world <= 1 || 2 + h->params.T * model_h->nu <= h->peer_pcap, "mppib_set_model: T*nu outgrows the open peer window; close and re-open the peers");
     h->model = *model_h;
     derive(h);
-    if (resize) { MPPIB_CHECK_CUDA(cudaSetDevice(h->device)); return alloc_scratch(h); }
+    if (resize) { MPPIB_ON_DEVICE(h); return alloc_scratch(h); }
     return 0;
 }
 
@@ -190,6 +191,7 @@ int32_t mppib_sample(MppibHandle h, uint64_t seed, uint64_t plan_idx, const uint
                      const float* prior_row, float* actions, float* noise, void* stream) {
     MPPIB_REQUIRE(h && U && actions, "mppib_sample: null argument");
     MPPIB_REQUIRE((uint64_t)k_offset + (uint64_t)h->params.K <= (uint64_t)k_total, "mppib_sample: shard [%u,+%d) exceeds k_total %u", k_offset, h->params.K, k_total);
+    MPPIB_ON_DEVICE(h);
     return launch_sample(h, seed, plan_idx, plan_ctr, k_offset, k_total, U, prior_row, actions, noise, (cudaStream_t)stream);
 }
 
@@ -197,6 +199,7 @@ int32_t mppib_noise_library(MppibHandle h, uint32_t k_offset, uint32_t k_total, 
                             float* Z, void* stream) {
     MPPIB_REQUIRE(h && halton_tab && B && Z, "mppib_noise_library: null argument");
     MPPIB_REQUIRE((uint64_t)k_offset + (uint64_t)h->params.K <= (uint64_t)k_total, "mppib_noise_library: shard exceeds k_total");
+    MPPIB_ON_DEVICE(h);
     return launch_noise_library(h, k_offset, k_total, halton_tab, B, n_knots, Z, (cudaStream_t)stream);
 }
 
@@ -204,6 +207,7 @@ int32_t mppib_sample_library(MppibHandle h, uint32_t k_offset, uint32_t k_total,
                              float* actions, float* noise, void* stream) {
     MPPIB_REQUIRE(h && U && Z && actions, "mppib_sample_library: null argument");
     MPPIB_REQUIRE((uint64_t)k_offset + (uint64_t)h->params.K <= (uint64_t)k_total, "mppib_sample_library: shard exceeds k_total");
+    MPPIB_ON_DEVICE(h);
     return launch_sample_library(h, k_offset, k_total, U, prior_row, Z, actions, noise, (cudaStream_t)stream);
 }
 
@@ -212,18 +216,21 @@ int32_t mppib_rollout(MppibHandle h, const float* state0, const float* root0, fl
     MPPIB_REQUIRE(h && actions, "mppib_rollout: null argument");
     MPPIB_REQUIRE(state0 || state, "mppib_rollout: need state0 (broadcast) or state (continue)");
     MPPIB_REQUIRE(t0 >= 0 && nsteps >= 0 && t0 + (nsteps > 0 ? nsteps : 1) <= h->params.T, "mppib_rollout: steps [%d,%d) outside horizon %d", t0, t0 + nsteps, h->params.T);
+    MPPIB_ON_DEVICE(h);
     return launch_rollout(h, state0, root0, state, actions, t0, nsteps, obs, (cudaStream_t)stream);
 }
 
 int32_t mppib_reduce(MppibHandle h, const float* cost, const float* x, const float* U, float* partial, void* stream) {
     MPPIB_REQUIRE(h && cost && x && U && partial, "mppib_reduce: null argument");
     MPPIB_REQUIRE(((uintptr_t)cost & 15) == 0 && ((uintptr_t)x & 15) == 0, "mppib_reduce: cost/x must be 16-byte aligned");
+    MPPIB_ON_DEVICE(h);
     return launch_reduce(h, cost, x, U, partial, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int32_t mppib_reduce_finalize(MppibHandle h, const float* cost, const float* x, float* U, float* partial, float* action_out, float* stats, void* stream) {
     MPPIB_REQUIRE(h && cost && x && U && partial && action_out, "mppib_reduce_finalize: null argument");
     MPPIB_REQUIRE(h->peer_world <= 1, "mppib_reduce_finalize is the single-GPU plan tail; with an open peer window use mppib_reduce + mppib_finalize");
+    MPPIB_ON_DEVICE(h);
     return launch_reduce(h, cost, x, U, partial, U, action_out, stats, (cudaStream_t)stream);
 }
 
@@ -233,6 +240,7 @@ int32_t mppib_finalize(MppibHandle h, const float* partials, int32_t G, float* U
         MPPIB_REQUIRE(h->peer_world >= 2 && G == h->peer_world, "mppib_finalize: partials == NULL needs an open peer window and G == world (G=%d, world=%d)", G, h->peer_world);
         for (int g = 0; g < h->peer_world; ++g) MPPIB_REQUIRE(h->peer_win[g] != nullptr, "mppib_finalize: peer %d is not open", g);
     }
+    MPPIB_ON_DEVICE(h);
     return launch_finalize(h, partials, G, U, action_out, stats, (cudaStream_t)stream);
 }
 
@@ -249,6 +257,7 @@ int32_t mppib_set_action_mirror(MppibHandle h, float* mirror) {
 
 int32_t mppib_shift(MppibHandle h, float* U, uint32_t* plan_ctr, void* stream) {
     MPPIB_REQUIRE(h && U, "mppib_shift: null argument");
+    MPPIB_ON_DEVICE(h);
     return launch_shift(h, U, plan_ctr, (cudaStream_t)stream);
 }
 

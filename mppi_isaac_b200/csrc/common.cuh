@@ -48,6 +48,24 @@ struct MppibContext {
     int k2_lanes;                              // K2 mapping for eligible scenes: 1 = one body per lane (default), 0 = one thread per rollout
 };
 
+// Every C-ABI entry that touches the device runs on the handle's device, whatever the calling thread's current device is (an
+// RPC server thread, a caller that switched devices), and leaves the caller's current device as it found it.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) { err = cudaSetDevice(device); switched = err == cudaSuccess; }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define MPPIB_ON_DEVICE(h)                                                                   \
+    DeviceGuard _guard((h)->device);                                                        \
+    MPPIB_CHECK_CUDA(_guard.err)
+
 // device view of the peer windows, passed by value to K3 / K4
 struct PeerArgs {
     int world, rank, pcap;

@@ -119,7 +119,8 @@ __device__ __forceinline__ void kinematics(const BodyConst& bc, int i, float q, 
     prefix_add<G>(kn.V.n, i); prefix_add<G>(kn.V.f, i);
 }
 
-template <int G>
+// G lanes per rollout (power of two), NB >= nb the compile-time number of joint-space rows (loops over bodies are fully unrolled)
+template <int G, int NB>
 __global__ void __launch_bounds__(32, LANES_MIN_CTAS)
 mppib_rollout_lanes_kernel(const __grid_constant__ MppibModel m, const __grid_constant__ MppibParams p,
                            const float* __restrict__ state0, float* __restrict__ state, const float* __restrict__ actions,
@@ -286,19 +287,18 @@ mppib_rollout_lanes_kernel(const __grid_constant__ MppibModel m, const __grid_co
             F.f = bc.mc * kn.S.f - cross(hc, kn.S.n);
             const float bias = dot6(kn.S, fb);
             // ---- joint-space inertia: lane j owns column j (rows i <= j are the valid ones)
-            float mcol[G];
+            float mcol[NB];
 #pragma unroll
-            for (int r = 0; r < G; ++r) {
-                mcol[r] = 0.f;
-                if (r < nb) {
-                    V6 Sr;
-                    Sr.n.x = shfl_at<G>(kn.S.n.x, r); Sr.n.y = shfl_at<G>(kn.S.n.y, r); Sr.n.z = shfl_at<G>(kn.S.n.z, r);
-                    Sr.f.x = shfl_at<G>(kn.S.f.x, r); Sr.f.y = shfl_at<G>(kn.S.f.y, r); Sr.f.z = shfl_at<G>(kn.S.f.z, r);
-                    mcol[r] = dot6(Sr, F);
-                }
+            for (int r = 0; r < NB; ++r) {
+                V6 Sr;
+                Sr.n.x = shfl_at<G>(kn.S.n.x, r); Sr.n.y = shfl_at<G>(kn.S.n.y, r); Sr.n.z = shfl_at<G>(kn.S.n.z, r);
+                Sr.f.x = shfl_at<G>(kn.S.f.x, r); Sr.f.y = shfl_at<G>(kn.S.f.y, r); Sr.f.z = shfl_at<G>(kn.S.f.z, r);
+                mcol[r] = dot6(Sr, F);
             }
             // ---- solve (M + diag(dimp)) qdd = tau - bias ; joint force and implicit diagonal: the velocity drive kd (q* - qd) and
-            // the joint damping b qd act on the NEW velocity
+            // the joint damping b qd act on the NEW velocity.  LDL^T, right looking, with the forward substitution folded into
+            // the pivot loop: at pivot kk every lane j > kk knows l_jk (its row of L), lane kk collects column kk of L in lcol[]
+            // for the backward substitution.  Bodies i >= nb are an identity block (no mass, unit diagonal): no guards needed.
             float sat = 0.f, qdd = 0.f;
 #pragma unroll 1
             for (int solve = 0; solve < 2; ++solve) {
@@ -306,44 +306,34 @@ mppib_rollout_lanes_kernel(const __grid_constant__ MppibModel m, const __grid_co
                 if (sat != 0.f) { tau = sat * bc.effort - bc.damp * qd; dimp = bc.dimp_sat; }
                 else if (vel_mode) { tau = bc.kd * (tgt - qd) - bc.damp * qd; dimp = bc.dimp_drive; }
                 else { tau = fminf(fmaxf(tgt, -bc.effort), bc.effort) - (bc.kd + bc.damp) * qd; dimp = bc.dimp_drive; }
-                float col[G], lcol[G];
+                float col[NB], lcol[NB];
 #pragma unroll
-                for (int r = 0; r < G; ++r) { col[r] = (r == i) ? mcol[r] + dimp : mcol[r]; lcol[r] = 0.f; }
+                for (int r = 0; r < NB; ++r) { col[r] = mcol[r]; lcol[r] = 0.f; }
                 float invd = 1.f;
-                // LDL^T, right looking: after step kk lane j > kk holds l_jk in col[kk], lane kk holds column kk of L in lcol[]
-#pragma unroll
-                for (int kk = 0; kk < G; ++kk) {
-                    if (kk < nb) {
-                        const float dk = shfl_at<G>(col[kk], kk);
-                        const float inv = rcp_approx(dk);
-                        const float lk = col[kk] * inv;
-                        if (i == kk) invd = inv;
-#pragma unroll
-                        for (int r = kk + 1; r < G; ++r) {
-                            if (r < nb) {
-                                const float lr = shfl_at<G>(lk, r);
-                                col[r] = fmaf(-lr, col[kk], col[r]);
-                                if (i == kk) lcol[r] = lr;
-                            }
-                        }
-                        if (i > kk) col[kk] = lk;
-                    }
-                }
                 float y = tau - bias;
 #pragma unroll
-                for (int kk = 0; kk < G - 1; ++kk) {
-                    if (kk + 1 < nb) {
-                        const float yk = shfl_at<G>(y, kk);
-                        if (i > kk) y = fmaf(-col[kk], yk, y);
+                for (int kk = 0; kk < NB; ++kk) {
+                    const float dk = shfl_at<G>(col[kk] + dimp, kk);      // only lane kk's sum (its diagonal + implicit term) is read
+                    const float inv = rcp_approx(dk);
+                    const bool own = i == kk;
+                    if (own) invd = inv;
+                    const float lk = col[kk] * inv;                       // l_jk on lanes j > kk
+                    if (kk + 1 < NB) {
+                        const float yk = shfl_at<G>(y, kk);               // y_kk is final
+                        if (i > kk) y = fmaf(-lk, yk, y);
+                    }
+#pragma unroll
+                    for (int r = kk + 1; r < NB; ++r) {
+                        const float lr = shfl_at<G>(lk, r);
+                        col[r] = fmaf(-lr, col[kk], col[r]);
+                        if (own) lcol[r] = lr;
                     }
                 }
                 y *= invd;
 #pragma unroll
-                for (int jj = G - 1; jj >= 1; --jj) {
-                    if (jj < nb) {
-                        const float xj = shfl_at<G>(y, jj);
-                        if (i < jj) y = fmaf(-lcol[jj], xj, y);
-                    }
+                for (int jj = NB - 1; jj >= 1; --jj) {
+                    const float xj = shfl_at<G>(y, jj);
+                    if (i < jj) y = fmaf(-lcol[jj], xj, y);
                 }
                 qdd = bval ? y : 0.f;
                 bool newly = false;
@@ -377,12 +367,12 @@ mppib_rollout_lanes_kernel(const __grid_constant__ MppibModel m, const __grid_co
     }
 }
 
-template <int G>
+template <int G, int NB>
 int launch_lanes_t(MppibContext* c, const float* state0, float* state, const float* actions, int t0, int nsteps, float* obs, cudaStream_t s) {
     const int K = c->params.K;
     constexpr int RPW = 32 / G;
     const int warps = (K + RPW - 1) / RPW;
-    mppib_rollout_lanes_kernel<G><<<warps, 32, 0, s>>>(c->model, c->params, state0, state, actions, t0, nsteps, obs);
+    mppib_rollout_lanes_kernel<G, NB><<<warps, 32, 0, s>>>(c->model, c->params, state0, state, actions, t0, nsteps, obs);
     MPPIB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -397,6 +387,9 @@ bool rollout_lanes_eligible(const MppibModel& m) {
 }
 
 int launch_rollout_lanes(MppibContext* c, const float* state0, float* state, const float* actions, int t0, int nsteps, float* obs, cudaStream_t s) {
-    if (c->model.nb <= 4) return launch_lanes_t<4>(c, state0, state, actions, t0, nsteps, obs, s);
-    return launch_lanes_t<8>(c, state0, state, actions, t0, nsteps, obs, s);
+    const int nb = c->model.nb;
+    if (nb <= 3) return launch_lanes_t<4, 3>(c, state0, state, actions, t0, nsteps, obs, s);
+    if (nb <= 4) return launch_lanes_t<4, 4>(c, state0, state, actions, t0, nsteps, obs, s);
+    if (nb <= 7) return launch_lanes_t<8, 7>(c, state0, state, actions, t0, nsteps, obs, s);
+    return launch_lanes_t<8, 8>(c, state0, state, actions, t0, nsteps, obs, s);
 }

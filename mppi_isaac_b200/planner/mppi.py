@@ -194,6 +194,7 @@ class MPPIPlanner:
         self._prior_rows = torch.zeros((T, nu), **f32) if self.use_priors else None
         self._graph = None
         self._graph_failed = False
+        self._graph_epoch = -1
         self._plans = 0
         if self.use_library:
             self._build_library()
@@ -316,6 +317,7 @@ class MPPIPlanner:
             self.U.copy_(u_keep)
             self.plan_ctr.copy_(ctr_keep)
             self._graph = g
+            self._graph_epoch = getattr(self.sim, "model_epoch", 0)
         except Exception as e:  # capture is an optimisation; the eager path is the same kernels
             self._graph = None
             self._graph_failed = True
@@ -326,6 +328,10 @@ class MPPIPlanner:
     def command(self, state=None):
         """One MPPI plan; returns the first action(s) of the updated control sequence (device tensor)."""
         if self.rollout_mode == "batched":
+            # the captured graph bakes in the model block (a by-value kernel parameter: base pose, obstacle poses) and the sim's
+            # buffers: any sim-side change of either (setters, set_model, a rebuilt sim) invalidates it
+            if self._graph is not None and self._graph_epoch != getattr(self.sim, "model_epoch", 0):
+                self.invalidate_graph()
             if self.use_cuda_graph and self._graph is None and not self._graph_failed:
                 self._try_capture()
             if self._graph is not None:

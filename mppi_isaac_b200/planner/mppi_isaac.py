@@ -68,8 +68,17 @@ class MPPIisaacPlanner(object):
         # place holder handed to mppi, the real state is the rollout simulator itself (mppi_isaac.py:51-52)
         self.state_place_holder = torch.zeros((self.k_local, self.cfg.nx))
 
-    def _build_mppi(self):
-        self.mppi = MPPIPlanner(
+    def _build_mppi(self, keep_U: bool = False):
+        old = getattr(self, "mppi", None) if keep_U else None
+        self._last_root_bytes = None           # whatever was uploaded belonged to the previous handle / buffers
+        self._sim_build = self.sim.build_epoch
+        self.mppi = self._make_mppi()
+        self._sim_build = self.sim.build_epoch         # MPPIPlanner.__init__ re-configures the sim (one more handle)
+        if old is not None and old.U.shape == self.mppi.U.shape:
+            self.mppi.U.copy_(old.U)           # the warm start survives a rebuilt simulator, as in the reference (mppi is not rebuilt there)
+
+    def _make_mppi(self):
+        return MPPIPlanner(
             self.cfg.mppi,
             self.cfg.nx,
             dynamics=self.dynamics,
@@ -100,6 +109,13 @@ class MPPIisaacPlanner(object):
         self.sim.reset_robot_state(q, qdot)
         if obst:
             self.sim.update_root_state_tensor_by_obstacles(obst)
+            if self.sim.build_epoch != self._sim_build:
+                # an obstacle was added / resized: the simulator was rebuilt (stop_sim / start_sim as isaacgym_wrapper.py:743-746),
+                # i.e. a new kernel handle, new buffers and scene-default joint states.  Re-trace, re-bind the planner to the new
+                # handle (action mirror, captured graph) and re-apply the robot state the caller has just handed over.
+                self.sim.trace(lambda s: self.objective.compute_cost(s))
+                self._build_mppi(keep_U=True)
+                self.sim.reset_robot_state(q, qdot)
         if obst_tensor is not None and len(obst_tensor) > 0:
             self.sim.update_root_state_tensor_by_obstacles_tensor(obst_tensor)
         self.sim.save_root_state()
@@ -139,7 +155,7 @@ class MPPIisaacPlanner(object):
     def add_to_env(self, env_cfg_additions):
         self.sim.add_to_envs(env_cfg_additions)
         self.sim.trace(lambda s: self.objective.compute_cost(s))
-        self._build_mppi()
+        self._build_mppi(keep_U=True)
 
     def get_rollouts(self):
         if not self.sim._visualize_link_present:

@@ -67,6 +67,10 @@ class RolloutSim:
         self._backend = backend
         self._recording = False
         self.saved_root_state = None
+        # what a captured CUDA graph bakes in: `model_epoch` counts changes of the kernel constant block (MppibModel is a
+        # by-value kernel parameter) and of the K-indexed buffers; `build_epoch` counts re-creations of the kernel handle
+        self.model_epoch = 0
+        self.build_epoch = 0
         self.start_sim()
 
     # ------------------------------------------------------------------------------------------
@@ -136,6 +140,8 @@ class RolloutSim:
             from ..backend import CudaBackend
             self._backend = CudaBackend(dev)
         self._backend.create(sc.model, self.params)
+        self.model_epoch += 1
+        self.build_epoch += 1
         assert self._backend.obs_size() == self._R
         NS = self._backend.state_size()
         self._state = torch.zeros((NS, K), dtype=torch.float32, device=dev)            # (NS,K) step-protocol state
@@ -395,7 +401,7 @@ class RolloutSim:
             self._state_stale = True
             if m.base_pos[2] != float(row[2]):
                 m.base_pos[2] = float(row[2])
-                self._backend.set_model(m)
+                self._set_model(m)
                 return True
             return False
         changed = False
@@ -406,8 +412,13 @@ class RolloutSim:
             if m.base_quat[i] != float(row[3 + i]):
                 m.base_quat[i] = float(row[3 + i]); changed = True
         if changed:
-            self._backend.set_model(m)
+            self._set_model(m)
         return changed
+
+    def _set_model(self, m):
+        """Push the model block to the handle; planners compare `model_epoch` before replaying a captured graph."""
+        self._backend.set_model(m)
+        self.model_epoch += 1
 
     def _base_from_root(self, root_row):
         """(x, y, yaw, vx, vy, wz) of a planar base from a 13-float root state (host tensor / array)."""
@@ -637,10 +648,17 @@ class RolloutSim:
             self._root0[j] = torch.tensor([*obst["position"], 0, 0, 0, 1, *obst["velocity"], 0, 0, 0], dtype=torch.float32, device=self.device)
         if env_cfg_changed:
             keep = self._root0.clone()
+            for i, a in enumerate(self.env_cfg):
+                a.handle = i
             self.stop_sim()
-            self.start_sim()
+            self.start_sim()           # new kernel handle, new buffers (build_epoch / model_epoch tell the planner)
             n = min(keep.shape[0], self._root0.shape[0])
             self._root0[:n] = keep[:n]
+            for i, obst in enumerate(list(obstacles.values())):     # rows of the obstacles that were just created
+                j = [a.name for a in self.env_cfg].index(f"sphere{i}")
+                self._root0[j] = torch.tensor([*obst["position"], 0, 0, 0, 1, *obst["velocity"], 0, 0, 0], dtype=torch.float32, device=self.device)
+            self._stage[2 * self.scene.ndof:].copy_(self._root0.reshape(-1).cpu())
+        return env_cfg_changed
 
     def update_root_state_tensor_by_obstacles_tensor(self, obst_tensor):
         for o_tensor in obst_tensor:
