@@ -1,28 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- plan-loop Hz / rollout-steps per second of the MPPI rollout hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c2|c3|c4|c5] [--scaling strong|weak]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is ONE MPPI plan of the BASELINE headline workload (panda 7-DoF reach, K = 10 000 samples per GPU,
-T = 30, dt 0.05 / 2 substeps): shift U -> K1 sample/clamp -> K2 articulated rollout -> Objective cost ->
-K3 fused cost/softmax/weighted sum -> [NCCL all-gather of the shard partials] -> K4 update.
-Samples are sharded over the ranks (weak scaling: every GPU owns K = 10 000 samples, K_total = N * 10 000).
+A "step" is ONE MPPI plan of a BASELINE configuration: shift U -> K1 sample/clamp -> K2 articulated rollout -> Objective cost ->
+K3 fused cost/softmax/weighted sum -> [exchange of the shard partials] -> K4 update.
+
+  --config   c2 (default) = the headline, panda 7-DoF reach K = 10 000, T = 30 (BASELINE C2*); c3 = boxer_push K = 4 000, T = 20;
+             c4 = heijn_push K = 16 000, T = 25 (BASELINE: 4 GPUs); c5 = panda_pick K = 65 536, T = 30 (BASELINE: 8 GPUs)
+  --scaling  strong (default; BASELINE.md section 4: the configuration's K is the GLOBAL sample count, sharded over the N ranks) or
+             weak (every GPU owns the configuration's K).  With N > 1 the strong run also reports a short weak run under "weak".
 
 Printed JSON (rank 0, one line):
-  value      rollout-steps/s (= K_total * T * plans/s), inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e        the same metric through MPPIisaacPlanner.compute_action_tensor(dof_bytes, root_bytes) with host buffers
-  roofline   K3 (fused cost-softmax-weighted-sum) achieved HBM GB/s vs the measured peak (MEASURED_PEAKS.json)
-  cpu_baseline  the CPU restatement of the reference pipeline (oracle/) timed on this box's host cores (N=1 only)
---impl reference times that CPU restatement as the reference arm (the reference's own engines, IsaacGym/PhysX and
-mppi_torch, are closed / un-vendored and cannot run here: BASELINE.md section 2).
+  value         rollout-steps/s (= K_total * T * plans/s), inputs resident in HBM, CUDA events per plan, max over ranks
+  e2e           the same metric through MPPIisaacPlanner.compute_action_tensor(dof_bytes, root_bytes) with host buffers; every other
+                call carries a NEW root-state message (moving goal), the others only a new joint state
+  roofline      K3 (fused cost-softmax-weighted-sum) achieved HBM GB/s vs the measured peak (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU restatement of the reference pipeline (oracle/) on this box's host cores (N = 1 only), with its parallel efficiency
+  correctness   N > 1: max |action| difference across ranks and between the peer-memory exchange and the NCCL all-gather
+--impl reference times that CPU restatement as the reference arm (the reference's own engines, IsaacGym/PhysX and mppi_torch, are
+closed / un-vendored and cannot run here: BASELINE.md section 2).
 """
 import argparse
 import copy
 import json
 import os
-import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -34,18 +37,57 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-K_PER_GPU = 10000
-T_HORIZON = 30
-WORKLOAD = "panda 7-DoF reach (BASELINE C2*): K=10000/GPU, T=30, dt=0.05, substeps=2, Gaussian sampling, cost O1 (PandaReachObjective, fused ops.pose_cost)"
 METRIC = "rollout_steps_per_sec"
 UNIT = "rollout-steps/s"
 
+PANDA_Q = [0.0, -0.94, 0.0, -2.8, 0.0, 1.8675, 0.0]
+CONFIGS = {
+    "c2": dict(cfg="config_panda_b200", K=10000, T=30, baseline_gpus=1, q=None,
+               workload="panda 7-DoF reach (BASELINE C2*): K=10000, T=30, dt=0.05, substeps=2, Gaussian sampling, cost O1 (PandaReachObjective)"),
+    "c3": dict(cfg="config_boxer_push_b200", K=4000, T=20, baseline_gpus=1, q=[0.0, 2.5, 0.0],
+               workload="boxer_push non-prehensile contact (BASELINE C3): K=4000, T=20, dt=0.05, substeps=2, cost O2 (PushObjective)"),
+    "c4": dict(cfg="config_heijn_push_b200", K=16000, T=25, baseline_gpus=4, q=[0.0, 0.0, 0.0],
+               workload="heijn_push omni base + obstacles (BASELINE C4): K=16000, T=25, dt=0.1, substeps=1, cost O2 (PushObjective)"),
+    "c5": dict(cfg="config_panda_pick_b200", K=65536, T=30, baseline_gpus=8, q=PANDA_Q + [0.02, 0.02],
+               workload="panda_pick 7-DoF + grasp contacts (BASELINE C5): K=65536, T=30, dt=0.05, substeps=2, cost O3 (PandaPickObjective)"),
+}
+# kept for the tools/ scripts that import bench
+K_PER_GPU = CONFIGS["c2"]["K"]
+T_HORIZON = CONFIGS["c2"]["T"]
+
+
+def make_objective(name, device="cuda", fused=True, cpu_threads=1):
+    from mppi_isaac_b200.objectives import PandaPickObjective, PandaReachObjective, PushObjective
+    if name == "c2":
+        if device == "cpu":
+            from oracle.backend import OraclePandaReachObjective
+            return OraclePandaReachObjective(nthreads=cpu_threads)
+        return PandaReachObjective(fused=fused)
+    if name == "c3":
+        return PushObjective(robot="boxer", link="ee_link")
+    if name == "c4":
+        return PushObjective()
+    return PandaPickObjective()
+
+
+def load_cfg(name, k_total, device):
+    from mppi_isaac_b200.utils.config_store import load_isaacgym_config
+    c = CONFIGS[name]
+    cfg = copy.deepcopy(load_isaacgym_config(c["cfg"]))
+    cfg.mppi.num_samples, cfg.mppi.horizon, cfg.mppi.device = int(k_total), int(c["T"]), device
+    return cfg
+
 
 def panda_cfg(K, device):
-    from mppi_isaac_b200.utils.config_store import load_isaacgym_config
-    cfg = copy.deepcopy(load_isaacgym_config("config_panda_b200"))
-    cfg.mppi.num_samples, cfg.mppi.horizon, cfg.mppi.device = int(K), T_HORIZON, device
-    return cfg
+    return load_cfg("c2", K, device)
+
+
+def base_config(name, world, scaling):
+    """The `config` object of the JSON line: identical keys and values in both arms (b200 / reference)."""
+    c = CONFIGS[name]
+    k_total = c["K"] * (world if scaling == "weak" else 1)
+    return {"workload": c["workload"], "name": name, "K_total": k_total, "T": c["T"], "scaling": scaling,
+            "parallelism": f"sample-shard x{world}"}
 
 
 def synthetic_state(seed=1234 + 2):
@@ -58,7 +100,39 @@ def synthetic_state(seed=1234 + 2):
     return q0, goal
 
 
+def init_world(planner, name):
+    """Synthetic initial world of a configuration (host-side setters; the planner then holds it on its device)."""
+    c = CONFIGS[name]
+    if name == "c2":
+        q0, goal = synthetic_state()
+        planner.sim.set_actor_position_by_name(goal, "goal")
+        planner.sim.reset_robot_state(q0, np.zeros(7))
+    else:
+        planner.sim.reset_robot_state(c["q"], [0.0] * len(c["q"]))
+
+
+def world_messages(planner, rng=None, dq=0.0, goal_shift=None, base_shift=None):
+    """(dof_bytes, root_bytes, n_bytes): the world -> planner message of the reference (torch.save bytes of the (1, 2*ndof) DOF row and
+    the (1, A, 13) root states, transport.py:5-14), built from the planner's current world with an optional perturbation."""
+    from mppi_isaac_b200.utils.transport import torch_to_bytes
+    sim = planner.sim
+    nd, nv = sim.scene.ndof, sim.scene.virtual_dofs
+    st = sim._state0.detach().cpu().numpy().copy()
+    q, qd = st[nv:nd].copy(), st[nd + nv:2 * nd].copy()
+    if rng is not None and dq:
+        q = q + rng.uniform(-dq, dq, q.shape).astype(np.float32)
+        qd = qd + rng.uniform(-2 * dq, 2 * dq, qd.shape).astype(np.float32)
+    dof = torch.from_numpy(np.stack([q, qd], 1).reshape(1, -1).astype(np.float32))
+    root = sim._root0.detach().cpu().clone().unsqueeze(0)
+    if goal_shift is not None:
+        root[0, sim._get_actor_index_by_name("goal"), 0:3] += torch.as_tensor(goal_shift, dtype=torch.float32)
+    if base_shift is not None:
+        root[0, sim.scene.robot_actor, 0:3] += torch.as_tensor(base_shift, dtype=torch.float32)
+    return torch_to_bytes(dof), torch_to_bytes(root), dof.numel() * 4 + root.numel() * 4
+
+
 def world_bytes(planner, q, qd, goal):
+    """panda reach message from explicit (q, qd, goal) -- used by tools/."""
     from mppi_isaac_b200.utils.transport import torch_to_bytes
     dof = torch.tensor([[v for a, b in zip(q, qd) for v in (a, b)]], dtype=torch.float32)
     root = torch.from_numpy(planner.sim.scene.root_state0.copy()).unsqueeze(0)
@@ -66,43 +140,51 @@ def world_bytes(planner, q, qd, goal):
     return torch_to_bytes(dof), torch_to_bytes(root), dof.numel() * 4 + root.numel() * 4
 
 
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+class Clocks:
+    """SM clock and throttle reasons sampled IN PROCESS through NVML (what nvidia-smi reads) between the timed plans: the plans are
+    bracketed by CUDA events one by one, so a sample never sits inside a timed interval, and every rank takes the same samples (no
+    rank is slowed down relative to the others, which matters once the exchange is fused into the kernels)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake"}
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
-
-    def start(self):
+    def __init__(self, cuda_index):
+        self.ok, self.sm, self.mask, self.h = False, [], 0, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(cuda_index).uuid)
+                try:
+                    self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+                except TypeError:
+                    self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(vis.split(",")[cuda_index]) if vis and vis.split(",")[cuda_index].isdigit() else cuda_index
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = f"{type(e).__name__}: {e}"
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def sample(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.mask |= int(get(self.h))
+        except Exception:  # noqa: BLE001
+            pass
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        self.thread.join(timeout=2)
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+    def summary(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"NVML unavailable ({getattr(self, 'err', '?')})"]}
+        busy = sorted(self.sm)
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for bit, n in self.REASONS.items() if self.mask & bit), "samples": len(self.sm),
+                "how": "NVML in process, one sample after every timed plan (outside the CUDA-event brackets), all ranks alike"}
 
 
 def measured_peak_gbs():
@@ -116,50 +198,69 @@ def measured_peak_gbs():
 # --------------------------------------------------------------------------------------------------
 # CPU restatement arm (cpu_baseline and --impl reference)
 # --------------------------------------------------------------------------------------------------
-def cpu_plan_rate(k_sample, steps, warmup, cores):
-    """Plans of the oracle pipeline (sample -> rollout -> Objective -> reduce -> finalize) on `cores` host threads."""
+def cpu_plan_rate(name, k_sample, steps, warmup, threads):
+    """Seconds per plan of the oracle pipeline (sample -> rollout -> Objective -> reduce -> finalize) on `threads` host threads:
+    persistent worker pool inside the oracle, the Objective of c2 evaluated by the oracle's threaded cost function, torch intra-op
+    threads = `threads` for the torch-op Objectives of the contact configurations."""
     from mppi_isaac_b200 import MPPIisaacPlanner
-    from mppi_isaac_b200.objectives import PandaReachObjective
     from oracle.backend import OracleBackend
-    torch.set_num_threads(max(1, min(8, cores)))            # the Objective's torch ops; more threads only add overhead here
-    planner = MPPIisaacPlanner(panda_cfg(k_sample, "cpu"), PandaReachObjective(), backend=OracleBackend(nthreads=min(cores, 64)))
-    q0, goal = synthetic_state()
-    planner.sim.set_actor_position_by_name(goal, "goal")
-    planner.sim.reset_robot_state(q0, np.zeros(7))
+    torch.set_num_threads(max(1, min(threads, 32)))
+    planner = MPPIisaacPlanner(load_cfg(name, k_sample, "cpu"), make_objective(name, "cpu", cpu_threads=threads), backend=OracleBackend(nthreads=threads))
+    init_world(planner, name)
     for _ in range(warmup):
         planner.mppi.command()
     t0 = time.perf_counter()
     for _ in range(steps):
         planner.mppi.command()
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    return dt
+    return (time.perf_counter() - t0) / max(steps, 1)
 
 
-def pick_cpu_sample(cores, budget_s):
-    """Largest K (<= 10 000, multiple of 4) whose single plan fits `budget_s` on this host, from a K=256 probe."""
-    probe = cpu_plan_rate(512, 2, 1, cores)
-    per_sample = probe / 512
-    k = int(min(K_PER_GPU, max(256, budget_s / per_sample)))
-    return max(256, (k // 4) * 4)
+def pick_cpu_sample(name, threads, budget_s, k_max):
+    """Largest K (<= the configuration's K, multiple of 4) whose single plan fits `budget_s` on this host, from a small probe."""
+    k_probe = max(64, min(512, 8 * threads // 4 * 4))
+    probe = cpu_plan_rate(name, k_probe, 2, 1, threads)
+    k = int(min(k_max, max(k_probe, budget_s / (probe / k_probe))))
+    return max(64, (k // 4) * 4)
+
+
+def cpu_baseline(name, n_plans=5, budget_s=2.0):
+    cores = os.cpu_count() or 1
+    T = CONFIGS[name]["T"]
+    k_s = pick_cpu_sample(name, cores, budget_s, CONFIGS[name]["K"])
+    dt = cpu_plan_rate(name, k_s, n_plans, 1, cores)
+    k1 = max(64, min(256, k_s))
+    dt1 = cpu_plan_rate(name, k1, 3, 1, 1)
+    v, v1 = k_s * T / dt, k1 * T / dt1
+    return {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_plans} plans of K={k_s} of the K={CONFIGS[name]['K']} workload, CPU restatement (oracle/) on {cores} threads (persistent pool)",
+            "plan_hz_at_config_K_est": 1.0 / (dt * CONFIGS[name]["K"] / k_s),
+            "parallel_efficiency": v / (cores * v1),
+            "one_thread": {"value": v1, "unit": UNIT, "sample": f"3 plans of K={k1} on 1 thread",
+                           "plan_hz_at_config_K_est": 1.0 / (dt1 * CONFIGS[name]["K"] / k1)}}, dt, k_s
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    import __graft_entry__
     from oracle import oracle as orc
     orc.build()
     cores = os.cpu_count() or 1
-    k_s = pick_cpu_sample(cores, budget_s=2.0)
-    dt = cpu_plan_rate(k_s, args.steps, args.warmup, cores)
-    value = k_s * T_HORIZON / dt
+    name = args.config
+    T = CONFIGS[name]["T"]
+    k_s = pick_cpu_sample(name, cores, 2.0, CONFIGS[name]["K"])
+    dt = cpu_plan_rate(name, k_s, args.steps, args.warmup, cores)
+    value = k_s * T / dt
+    k1 = max(64, min(256, k_s))
+    dt1 = cpu_plan_rate(name, k1, 2, 1, 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt * 1e3, "plan_hz_at_sample": 1.0 / dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dt * 1e3, "plan_hz_at_sample": 1.0 / dt, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU restatement of the reference pipeline (oracle/), not IsaacGym/PhysX: those cannot run here"},
+        "config": base_config(name, world, args.scaling),
+        "note": "CPU restatement of the reference pipeline (oracle/), not IsaacGym/PhysX: those cannot run here (BASELINE.md section 2)",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} plans of K={k_s} of the K=10000 workload (rate is per rollout-step, K-independent)"},
+                         "sample": f"{args.steps} plans of K={k_s} of the K={CONFIGS[name]['K']} workload (rate is per rollout-step, K-independent)",
+                         "parallel_efficiency": value / (cores * (k1 * T / dt1))},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -201,11 +302,9 @@ def time_kernels(planner, reps=20):
     def t(fn):
         return graph_time_us(fn, reps)
 
-    out = {
-        "sample_us": t(lambda: be.sample(m.seed, 0, m.k_offset, m.K_total, m.U, None, m.actions, m.noise, m.plan_ctr)),
-        "rollout_us": t(lambda: sim.rollout_all(m.actions)),
-        "cost_objective_us": t(lambda: m._cost_batched()),      # the Objective as benchmarked (one fused ops.pose_cost launch)
-    }
+    out = {"sample_us": t(lambda: m._sample()),
+           "rollout_us": t(lambda: sim.rollout_all(m.actions)),
+           "cost_objective_us": t(lambda: m._cost_batched())}      # the Objective as benchmarked
     obj = planner.objective
     if getattr(obj, "fused", False):
         obj.fused = False
@@ -220,7 +319,7 @@ def time_kernels(planner, reps=20):
     return out
 
 
-def k3_roofline(planner, peak_gbs, peak_src, K_list):
+def k3_roofline(planner, peak_gbs, K_list):
     """K3 alone, inputs rotated over > L2 worth of distinct buffers so every launch reads HBM (cold L2)."""
     from mppi_isaac_b200.backend import CudaBackend
     from mppi_isaac_b200.model.blob import MppibParams
@@ -233,12 +332,12 @@ def k3_roofline(planner, peak_gbs, peak_src, K_list):
         be = CudaBackend(dev)
         be.create(planner.sim.scene.model, p)
         bytes_alg = 4 * K * T * (nu + 1) + 4 * (T * nu + 2)
-        nbuf = max(2, int(np.ceil(300e6 / bytes_alg)))            # > 2x the 126 MB L2
-        nbuf = min(nbuf, 64)
+        nbuf = min(64, max(2, int(np.ceil(300e6 / bytes_alg))))            # > 2x the 126 MB L2
         xs = [torch.randn((T, nu, K), device=dev) * 0.3 for _ in range(nbuf)]
         cs = [torch.rand((T, K), device=dev) * 10 for _ in range(nbuf)]
         U = torch.zeros((T, nu), device=dev)
         partial = torch.zeros(2 + T * nu, device=dev)
+
         def sweep():
             for i in range(nbuf):
                 be.reduce(cs[i], xs[i], U, partial)
@@ -250,144 +349,211 @@ def k3_roofline(planner, peak_gbs, peak_src, K_list):
     return res
 
 
+def timed_plans(planner, steps, warmup, flush, barrier, clocks=None):
+    """`steps` plans, each bracketed by CUDA events on the launching stream, L2 flushed before every one; returns per-plan ms."""
+    for _ in range(max(warmup, 3)):
+        planner.mppi.command()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    barrier()
+    for i in range(steps):
+        flush.zero_()
+        starts[i].record()
+        planner.mppi.command()
+        ends[i].record()
+        if clocks is not None:
+            clocks.sample()          # host side, between two enqueued plans: not inside any event bracket
+    barrier()
+    return [s.elapsed_time(e) for s, e in zip(starts, ends)]
+
+
 def run_gpu_arm(args, rank, world, local_rank):
     import torch.distributed as dist
     import __graft_entry__
     __graft_entry__.build()
     from mppi_isaac_b200 import MPPIisaacPlanner
-    from mppi_isaac_b200.objectives import PandaReachObjective
     from mppi_isaac_b200.utils.transport import bytes_to_torch
 
+    name = args.config
+    C = CONFIGS[name]
+    T = C["T"]
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
-    k_total = K_PER_GPU * world
-    planner = MPPIisaacPlanner(panda_cfg(k_total, dev), PandaReachObjective(), use_cuda_graph=True)
-    assert planner.sim.num_envs == K_PER_GPU
-    q0, goal = synthetic_state()
-    dof_b, root_b, h2d = world_bytes(planner, q0, np.zeros(7), goal)
-    planner.objective.reset()
-    planner.reset_rollout_sim(dof_b, root_b)
+    k_total = C["K"] * (world if args.scaling == "weak" else 1)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    planner = MPPIisaacPlanner(load_cfg(name, k_total, dev), make_objective(name), use_cuda_graph=True)
+    init_world(planner, name)
+    nu = planner.mppi.nu
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
-    # ---- device-resident timing: K plans, CUDA events around each plan, L2 flushed between plans -------------------
-    for _ in range(max(args.warmup, 3)):
-        planner.mppi.command()
+    clocks = Clocks(local_rank)
+
+    # ---- device-resident timing ------------------------------------------------------------------------------------
+    per_step_ms = timed_plans(planner, args.steps, args.warmup, flush, barrier, clocks)
     graph_on = planner.mppi._graph is not None
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()          # before the barrier: spawning nvidia-smi takes milliseconds, and with the exchange fused
-    barrier()                    # into the kernels every rank's first timed plan would wait for a late rank 0
-    for i in range(args.steps):
-        flush.zero_()
-        starts[i].record()
-        planner.mppi.command()
-        ends[i].record()
-    barrier()
-    per_step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    total_ms = torch.tensor([sum(per_step_ms)], dtype=torch.float64, device=dev)
-    # ---- end to end through the plugin API with host buffers ----------------------------------------------------
-    # the caller's side of the wire (building / pickling the world state) is prepared outside the timed region: a
-    # different synthetic joint state per step, in the reference's own torch.save byte format (transport.py:5-14)
+    total_s = reduce_max(sum(per_step_ms)) * 1e-3
+    value = k_total * T * args.steps / total_s
+    p50_ms = reduce_max(float(np.percentile(per_step_ms, 50)))
+
+    # ---- end to end through the plugin API with host buffers ----------------------------------------------------------
+    # the caller's side of the wire (building / pickling the world state) is prepared outside the timed region, in the reference's own
+    # torch.save byte format (transport.py:5-14).  Odd steps carry a NEW root message (the goal has moved: parse + upload of the root
+    # states), even steps only a new joint state.
     rng = np.random.default_rng(99)
-    inputs = [world_bytes(planner, q0 + rng.uniform(-0.05, 0.05, 7), rng.uniform(-0.1, 0.1, 7), goal)[:2] for _ in range(args.steps)]
-    for _ in range(3):
-        bytes_to_torch(planner.compute_action_tensor(dof_b, root_b))
-    barrier()
-    outs = []
-    t0 = time.perf_counter()
+    has_goal = "goal" in [a.name for a in planner.sim.env_cfg]
+    msgs, h2d = [], 0
     for i in range(args.steps):
-        outs.append(planner.compute_action_tensor(*inputs[i]))     # bytes in -> H2D -> plan -> D2H -> bytes out
-    torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    assert all(bytes_to_torch(o).shape == (planner.mppi.nu,) for o in outs)
-    # the reference's in-process entry point: compute_action(q, qdot) with host lists in, host tensor out
-    qs = [list(q0 + rng.uniform(-0.05, 0.05, 7)) for _ in range(args.steps)]
-    qds = [list(rng.uniform(-0.1, 0.1, 7)) for _ in range(args.steps)]
-    for _ in range(3):
-        planner.compute_action(qs[0], qds[0])
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        planner.compute_action(qs[i], qds[i])
-    torch.cuda.synchronize()
-    e2e2_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    clocks = sampler.stop() if rank == 0 else None
+        gs = rng.uniform(-0.02, 0.02, 3) if (has_goal and i % 2 == 1) else None
+        d, r, nbytes = world_messages(planner, rng, dq=0.02, goal_shift=gs)
+        msgs.append((d, r)); h2d = nbytes
+    d0, r0, _ = world_messages(planner)
+
+    def e2e_loop(inputs):
+        for _ in range(3):
+            bytes_to_torch(planner.compute_action_tensor(d0, r0))
+        barrier()
+        outs = []
+        t0 = time.perf_counter()
+        for d, r in inputs:
+            outs.append(planner.compute_action_tensor(d, r))     # bytes in -> H2D -> plan -> D2H -> bytes out
+        torch.cuda.synchronize()
+        dt = reduce_max(time.perf_counter() - t0)
+        assert all(bytes_to_torch(o).shape == (nu,) for o in outs)
+        return dt
+    e2e_s = e2e_loop(msgs)
+    e2e_static_s = e2e_loop([(m[0], r0) for m in msgs])                                      # joint state only
+    e2e_moving_s = e2e_loop([(m[0], world_messages(planner, goal_shift=rng.uniform(-0.02, 0.02, 3))[1]) for m in msgs]) if has_goal else None
+    e2e = {"value": k_total * T * args.steps / e2e_s, "unit": UNIT, "plan_hz": args.steps / e2e_s, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": nu * 4, "api": "MPPIisaacPlanner.compute_action_tensor(dof_bytes, root_bytes) -> bytes",
+           "inputs": "new joint state every call; every other call also a new root-state message (moved goal)",
+           "plan_hz_joint_state_only": args.steps / e2e_static_s,
+           "plan_hz_new_root_message_every_call": (args.steps / e2e_moving_s) if e2e_moving_s else None}
+    # the reference's in-process entry point: compute_action(q, qdot) with host lists in, host tensor out (fixed-base robots)
+    if planner.sim.scene.virtual_dofs == 0:
+        nd = planner.sim.scene.ndof
+        st = planner.sim._state0.detach().cpu().numpy()
+        qs = [list(st[:nd] + rng.uniform(-0.02, 0.02, nd)) for _ in range(args.steps)]
+        qds = [list(rng.uniform(-0.05, 0.05, nd)) for _ in range(args.steps)]
+        for _ in range(3):
+            planner.compute_action(qs[0], qds[0])
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            planner.compute_action(qs[i], qds[i])
+        torch.cuda.synchronize()
+        e2e["compute_action_plan_hz"] = args.steps / reduce_max(time.perf_counter() - t0)
+    # a moved robot base changes a kernel constant: the captured graph is dropped and re-captured inside the call
+    if world == 1 and planner.sim.scene.virtual_dofs == 0:
+        db, rb, _ = world_messages(planner, base_shift=[0.01, 0.0, 0.0])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        planner.compute_action_tensor(db, rb)
+        torch.cuda.synchronize()
+        e2e["ms_first_call_after_base_move_graph_recapture"] = (time.perf_counter() - t0) * 1e3
+        planner.compute_action_tensor(d0, r0)
+
+    # ---- multi-GPU correctness keys -----------------------------------------------------------------------------------
+    correctness = None
     if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e2e2_s, op=dist.ReduceOp.MAX)
-    total_s = float(total_ms.item()) * 1e-3
-    value = k_total * T_HORIZON * args.steps / total_s
-    e2e_value = k_total * T_HORIZON * args.steps / float(e2e_s.item())
+        def one_plan(pl):
+            init_world(pl, name)
+            pl.mppi.U.zero_(); pl.mppi.plan_ctr.zero_()
+            pl.mppi.command()
+            torch.cuda.synchronize()
+            return pl.mppi._action.detach().clone(), pl.mppi.U.detach().clone()
+        a_peer, u_peer = one_plan(planner)
+        gathered = [torch.zeros_like(a_peer) for _ in range(world)]
+        dist.all_gather(gathered, a_peer)
+        across = max(float((g - gathered[0]).abs().max()) for g in gathered)
+        os.environ["MPPIB_EXCHANGE"] = "nccl"
+        p_nccl = MPPIisaacPlanner(load_cfg(name, k_total, dev), make_objective(name), use_cuda_graph=True)
+        os.environ["MPPIB_EXCHANGE"] = "peer"
+        a_nccl, u_nccl = one_plan(p_nccl)
+        correctness = {"action_max_abs_diff_across_ranks": reduce_max(across),
+                       "peer_vs_nccl_max_abs_diff": reduce_max(max(float((a_peer - a_nccl).abs().max()), float((u_peer - u_nccl).abs().max()))),
+                       "peer_exchange_active": bool(planner.mppi._peer_exchange), "nccl_planner_used_peer": bool(p_nccl.mppi._peer_exchange)}
+        p_nccl.mppi.invalidate_graph(); p_nccl.mppi.close_peers()
+        del p_nccl
+
+    # ---- weak-scaling companion of a strong-scaling run ----------------------------------------------------------------
+    weak = None
+    if world > 1 and args.scaling == "strong":
+        planner.mppi.invalidate_graph()
+        pw = MPPIisaacPlanner(load_cfg(name, C["K"] * world, dev), make_objective(name), use_cuda_graph=True)
+        init_world(pw, name)
+        ms = timed_plans(pw, args.steps, args.warmup, flush, barrier)
+        tw = reduce_max(sum(ms)) * 1e-3
+        weak = {"K_total": C["K"] * world, "value": C["K"] * world * T * args.steps / tw, "unit": UNIT, "ms_per_step": tw * 1e3 / args.steps,
+                "ms_per_step_p50": reduce_max(float(np.percentile(ms, 50)))}
+        pw.mppi.invalidate_graph(); pw.mppi.close_peers()
+        del pw
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        launches_per_plan = (5 if world == 1 else 6)   # shift, sample, rollout, fused pose cost (Objective), reduce(+finalize fused at 1 GPU) [, finalize]
+        fused_obj = bool(getattr(planner.objective, "fused", False))
+        n_obj = 1 if fused_obj else None
+        launches_per_plan = (4 + (n_obj or 0) if world == 1 else 5 + (n_obj or 0))   # shift, sample, rollout, [fused cost], reduce(+finalize at 1 GPU) [, finalize]
+        cfg_line = base_config(name, world, args.scaling)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_s * 1e3 / args.steps, "plan_hz": args.steps / total_s, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "K_per_gpu": K_PER_GPU, "K_total": k_total, "T": T_HORIZON, "parallelism": f"sample-shard x{world}",
-                       "exchange": "none" if world == 1 else ("peer-memory stores fused into K3 (NVLink), flags acquired by K4" if planner.mppi._peer_exchange else "NCCL all-gather"),
-                       "cuda_graph": graph_on, "l2": "flushed (256 MiB write) before every timed plan",
-                       "ms_per_step_p10_p50_p90_max": [float(np.percentile(per_step_ms, p)) for p in (10, 50, 90, 100)]},
-            "e2e": {"value": e2e_value, "unit": UNIT, "plan_hz": args.steps / float(e2e_s.item()), "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": planner.mppi.nu * 4, "api": "MPPIisaacPlanner.compute_action_tensor(dof_bytes, root_bytes) -> bytes",
-                    "compute_action_plan_hz": args.steps / float(e2e2_s.item())},
-            "gpu_launches": launches_per_plan * args.steps,
-            "clocks": clocks,
+            "ms_per_step": total_s * 1e3 / args.steps, "ms_per_step_p50": p50_ms, "plan_hz": args.steps / total_s, "plan_hz_p50": 1e3 / p50_ms,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg_line,
+            "gpu_config": {"K_per_gpu": planner.sim.num_envs, "baseline_gpus": C["baseline_gpus"],
+                           "exchange": "none" if world == 1 else ("peer-memory stores fused into K3 (NVLink), flags acquired by K4" if planner.mppi._peer_exchange else "NCCL all-gather"),
+                           "cuda_graph": graph_on, "l2": "flushed (256 MiB write) before every timed plan",
+                           "k2_mapping": "lanes-per-rollout (rollout_lanes.cu)" if os.environ.get("MPPIB_K2_LANES", "1") != "0" and name == "c2" else "thread-per-rollout (rollout.cu)",
+                           "ms_per_step_p10_p50_p90_max": [float(np.percentile(per_step_ms, p)) for p in (10, 50, 90, 100)]},
+            "e2e": e2e,
+            "gpu_launches": (launches_per_plan * args.steps) if n_obj else None,
+            "clocks": clocks.summary(),
         }
+        if not n_obj:
+            line["gpu_launches"] = 4 * args.steps if world == 1 else 5 * args.steps
+            line["gpu_launches_note"] = "own kernels only (shift, sample, rollout, reduce[, finalize]); this configuration's Objective runs as torch ops"
+        if correctness:
+            line["correctness"] = correctness
+        if weak:
+            line["weak"] = weak
         if world == 1:
-            # transparency: the same plan with the Objective written as plain torch ops (~28 element-wise launches instead of the
-            # one fused ops.pose_cost launch) -- what an unmodified user Objective costs
-            planner.objective.fused = False
-            planner.mppi.invalidate_graph()
-            for _ in range(3):
+            if fused_obj:
+                # transparency: the same plan with the Objective written as plain torch ops (~28 element-wise launches instead of the
+                # one fused ops.pose_cost launch) -- what an unmodified user Objective costs, device-timed and end to end
+                planner.objective.fused = False
+                planner.mppi.invalidate_graph()
+                ms = timed_plans(planner, min(args.steps, 30), 3, flush, barrier)
+                t_e2e = e2e_loop(msgs)
+                line["objective_as_torch_ops"] = {"ms_per_step": float(np.mean(ms)), "plan_hz": 1e3 / float(np.mean(ms)),
+                                                  "value": k_total * T / (float(np.mean(ms)) * 1e-3), "unit": UNIT,
+                                                  "e2e_plan_hz": args.steps / t_e2e, "e2e_value": k_total * T * args.steps / t_e2e}
+                planner.objective.fused = True
+                planner.mppi.invalidate_graph()
                 planner.mppi.command()
-            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 30))]
-            for a, b in ev:
-                flush.zero_()
-                a.record()
-                planner.mppi.command()
-                b.record()
-            torch.cuda.synchronize()
-            ms_torch_obj = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-            line["objective_as_torch_ops"] = {"ms_per_step": ms_torch_obj, "plan_hz": 1e3 / ms_torch_obj,
-                                              "value": k_total * T_HORIZON / (ms_torch_obj * 1e-3), "unit": UNIT}
-            planner.objective.fused = True
-            planner.mppi.invalidate_graph()
-            planner.mppi.command()
             kt = time_kernels(planner)
-            roof = k3_roofline(planner, peak, peak_src, [K_PER_GPU, 65536, 262144])
-            head = roof[0]
+            ks = sorted({planner.sim.num_envs, 65536, 262144})
+            roof = k3_roofline(planner, peak, ks)
+            head = next(r for r in roof if r["K"] == planner.sim.num_envs)
+            traffic = {(10000, 30, 7): 9635000}.get((head["K"], T, nu))
             line["roofline"] = {"kernel": "K3 reduce_kernel (fused cost accumulate + softmax + weighted control sum)", "bound": "hbm",
-                                "achieved": head["GBps"], "peak": peak, "unit": "GB/s", "frac": head["frac"],
-                                "traffic": 9635000 if (head["K"], T_HORIZON) == (10000, 30) else None,
-                                "traffic_source": "ncu --set full dram__bytes_read.sum + write of one K3 launch at K=10000 (profiles/r1_reduce_v2.md): 1.004 x algorithmic",
+                                "achieved": head["GBps"], "peak": peak, "unit": "GB/s", "frac": head["frac"], "traffic": traffic,
+                                "traffic_source": "ncu --set full dram__bytes_read.sum + write of one K3 launch at this K (profiles/): 1.004 x algorithmic" if traffic else None,
                                 "peak_source": peak_src, "bytes_per_launch": head["bytes"], "us_per_launch": head["us"], "K": head["K"],
-                                "note": "9.6 MB per launch at the named K is ~1.5 us of HBM time, i.e. launch/latency bound; see sweep for the asymptote",
+                                "note": "the named K is launch/latency bound (9.6 MB = 1.5 us of HBM time at C2*); the sweep shows the asymptote",
                                 "sweep": roof}
             line["kernels_us"] = kt
-            cores = os.cpu_count() or 1
-            k_s = pick_cpu_sample(cores, budget_s=2.0)
-            n_cpu = 5
-            dt = cpu_plan_rate(k_s, n_cpu, 1, cores)
-            line["cpu_baseline"] = {"value": k_s * T_HORIZON / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{n_cpu} plans of K={k_s} of the K=10000 workload, CPU restatement (oracle/) on {cores} threads",
-                                    "plan_hz_at_K10000_est": 1.0 / (dt * K_PER_GPU / k_s)}
-            # one host thread: how the reference configures PhysX (num_threads never set, isaacgym_wrapper.py:21-39)
-            dt1 = cpu_plan_rate(256, 3, 1, 1)
-            line["cpu_baseline"]["one_thread"] = {"value": 256 * T_HORIZON / dt1, "unit": UNIT, "sample": "3 plans of K=256 on 1 thread",
-                                                  "plan_hz_at_K10000_est": 1.0 / (dt1 * K_PER_GPU / 256)}
+            line["cpu_baseline"], _, _ = cpu_baseline(name)
         print(json.dumps(line), flush=True)
     if world > 1:
         shutdown_distributed(planner)
@@ -418,6 +584,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -59,9 +59,12 @@ class OracleBackend:
 
     def rollout(self, state0, state, actions, t0, nsteps, obs, act_t0=0, root0=None):
         T, K, nu = self.params.T, self.params.K, self.model.nu
-        a = np.zeros((T, nu, K), np.float32)
         src = _np(actions).reshape(-1, nu, K)
-        a[act_t0:act_t0 + src.shape[0]] = src
+        if act_t0 == 0 and src.shape[0] == T and src.flags["C_CONTIGUOUS"] and src.dtype == np.float32:
+            a = src                                     # whole-horizon launch: the caller's buffer as it is
+        else:
+            a = np.zeros((T, nu, K), np.float32)
+            a[act_t0:act_t0 + src.shape[0]] = src
         st = _np(state) if state is not None else None
         s0 = _np(state0)
         import ctypes as C
@@ -74,6 +77,10 @@ class OracleBackend:
                                  f(r0), f(st), f(a), C.c_int32(t0), C.c_int32(nsteps), f(o), C.c_int32(int(self.use_double)), C.c_int32(self.nthreads))
 
     def reduce(self, cost, x, U, partial):
+        if self.nthreads > 1:          # timing arm: threaded, no staging copies (the single-threaded form below is the parity checker)
+            c = cost if cost.is_contiguous() else cost.contiguous()
+            partial.copy_(torch.from_numpy(orc.reduce_mt(self.model, self.params, _np(c), _np(x), _np(U), self.nthreads)))
+            return
         p, _ = orc.reduce(self.model, self.params, _np(cost.contiguous()), _np(x), _np(U))
         partial.copy_(torch.from_numpy(p))
 
@@ -88,3 +95,25 @@ class OracleBackend:
         U.copy_(torch.from_numpy(orc.shift(self.model, self.params, _np(U))))
         if plan_ctr is not None:
             plan_ctr += 1
+
+
+class OraclePandaReachObjective:
+    """The panda reach Objective (O1) of the CPU timing arm: the same two terms as ``PandaReachObjective`` evaluated by the
+    oracle's threaded ``oracle_cost_pose`` -- the CPU counterpart of the fused ``ops.pose_cost`` kernel the GPU arm uses."""
+
+    def __init__(self, nthreads=1, actor="panda", link="panda_ee_tip", goal="goal"):
+        self.weights = {"robot_to_goal": 1.0, "robot_ori": 0.5}
+        self.actor, self.link, self.goal, self.nthreads = actor, link, goal, nthreads
+        self._out = None
+
+    def reset(self):
+        pass
+
+    def compute_cost(self, sim):
+        ee = sim.get_actor_link_by_name(self.actor, self.link)
+        goal = sim.get_actor_position_by_name(self.goal)
+        n = ee.shape[0]
+        if self._out is None or self._out.shape[0] != n:
+            self._out = torch.empty((n,), dtype=torch.float32)
+        orc.cost_pose(_np(ee), _np(goal), self.weights["robot_to_goal"], self.weights["robot_ori"], _np(self._out), self.nthreads)
+        return self._out

@@ -27,6 +27,10 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include <algorithm>
@@ -68,17 +72,75 @@ inline void box_muller(uint32_t a, uint32_t b, float* z0, float* z1) {
     *z1 = (float)(r * std::sin(th));
 }
 
+// Persistent worker pool (the CPU arm of bench.py times whole plans: spawning and joining a set of std::threads per stage
+// cost more than a stage at 128 threads).  parallel_for hands out small index blocks from an atomic counter, so threads
+// that finish early (contacts make rollouts unequal) take more blocks.
+class Pool {
+  public:
+    static Pool& get() { static Pool p; return p; }
+    void run(int n, int nthreads, int grain, const std::function<void(int, int)>& f) {
+        std::unique_lock<std::mutex> user(user_mu_);          // one parallel region at a time
+        ensure(nthreads - 1);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            job_ = &f; n_ = n; grain_ = grain; next_.store(0); active_ = nthreads - 1; pending_ = nthreads - 1; ++epoch_;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+  private:
+    Pool() = default;
+    ~Pool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; ++epoch_; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    void ensure(int workers) {
+        while ((int)th_.size() < workers) {
+            const int id = (int)th_.size();
+            th_.emplace_back([this, id] {
+                unsigned long long seen = 0;
+                for (;;) {
+                    std::unique_lock<std::mutex> lk(mu_);
+                    cv_.wait(lk, [&] { return stop_ || epoch_ != seen; });
+                    if (stop_) return;
+                    seen = epoch_;
+                    const bool mine = id < active_;
+                    lk.unlock();
+                    if (mine) {
+                        work();
+                        std::lock_guard<std::mutex> lk2(mu_);
+                        if (--pending_ == 0) done_cv_.notify_all();
+                    }
+                }
+            });
+        }
+    }
+    void work() {
+        for (;;) {
+            const int a = next_.fetch_add(grain_);
+            if (a >= n_) break;
+            (*job_)(a, std::min(n_, a + grain_));
+        }
+    }
+    std::mutex mu_, user_mu_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<std::thread> th_;
+    const std::function<void(int, int)>* job_ = nullptr;
+    std::atomic<int> next_{0};
+    int n_ = 0, grain_ = 1, active_ = 0, pending_ = 0;
+    unsigned long long epoch_ = 0;
+    bool stop_ = false;
+};
+
 template <class F>
 void parallel_for(int n, int nthreads, F f) {
     if (nthreads <= 1 || n < 2 * nthreads) { f(0, n); return; }
-    std::vector<std::thread> th;
-    int chunk = (n + nthreads - 1) / nthreads;
-    for (int i = 0; i < nthreads; ++i) {
-        int a = i * chunk, b = std::min(n, a + chunk);
-        if (a >= b) break;
-        th.emplace_back([=]() { f(a, b); });
-    }
-    for (auto& t : th) t.join();
+    const int grain = std::max(1, n / (nthreads * 8));
+    Pool::get().run(n, nthreads, grain, std::function<void(int, int)>(f));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -869,6 +931,72 @@ void oracle_reduce(const MppibModel* m, const MppibParams* p, const float* cost,
     }
     partial[0] = (float)beta; partial[1] = (float)eta;
     for (int i = 0; i < T * nu; ++i) partial[2 + i] = (float)W[i];
+}
+
+// The same reduction on `nthreads` host threads (bench.py's CPU arm): per-thread (beta, eta, W) over blocks of samples,
+// merged with the shard-combine rule of oracle_finalize.  The single-threaded oracle_reduce above stays the parity checker.
+void oracle_reduce_mt(const MppibModel* m, const MppibParams* p, const float* cost, const float* x, const float* U,
+                      float* partial, int32_t nthreads) {
+    const int K = p->K, T = p->T, nu = m->nu, NR = T * nu;
+    std::vector<double> S(K);
+    std::vector<double> g((size_t)NR, 0.0);               // lambda * Sigma^-1 U folded per row
+    if (p->mode == MPPIB_MODE_SIMPLE)
+        for (int t = 0; t < T; ++t) for (int i = 0; i < nu; ++i) {
+            double ac = 0;
+            for (int j = 0; j < nu; ++j) ac += (double)p->sigma_inv[i * nu + j] * (double)U[t * nu + j];
+            g[(size_t)t * nu + i] = (double)p->lambda_ * ac;
+        }
+    std::mutex mu;
+    double beta = std::numeric_limits<double>::infinity();
+    parallel_for(K, nthreads, [&](int a, int b) {
+        double bl = std::numeric_limits<double>::infinity();
+        std::vector<double> acc(b - a, 0.0);
+        double gt = 1;
+        for (int t = 0; t < T; ++t) { for (int k = a; k < b; ++k) acc[k - a] += gt * (double)cost[(size_t)t * K + k]; gt *= (double)p->gamma; }
+        if (p->mode == MPPIB_MODE_SIMPLE)
+            for (int r = 0; r < NR; ++r) { const double gr = g[r]; for (int k = a; k < b; ++k) acc[k - a] += gr * (double)x[(size_t)r * K + k]; }
+        for (int k = a; k < b; ++k) { S[k] = acc[k - a]; if (std::isfinite(S[k]) && S[k] < bl) bl = S[k]; }
+        std::lock_guard<std::mutex> lk(mu);
+        if (bl < beta) beta = bl;
+    });
+    double eta = 0; std::vector<double> W((size_t)NR, 0.0);
+    parallel_for(K, nthreads, [&](int a, int b) {
+        std::vector<double> w(b - a), Wl((size_t)NR, 0.0);
+        double el = 0;
+        for (int k = a; k < b; ++k) { w[k - a] = std::isfinite(S[k]) ? std::exp(-(S[k] - beta) / (double)p->lambda_) : 0.0; el += w[k - a]; }
+        for (int r = 0; r < NR; ++r) { double s = 0; for (int k = a; k < b; ++k) s += w[k - a] * (double)x[(size_t)r * K + k]; Wl[r] = s; }
+        std::lock_guard<std::mutex> lk(mu);
+        eta += el;
+        for (int r = 0; r < NR; ++r) W[r] += Wl[r];
+    });
+    partial[0] = (float)beta; partial[1] = (float)eta;
+    for (int i = 0; i < NR; ++i) partial[2 + i] = (float)W[i];
+}
+
+// CPU restatement of the pose-reach cost term (examples/panda/planner.py:22-40 as ops.pose_cost / mppib_cost_pose evaluate it):
+// cost[i] = w_pos |a[i,0:3] - b[i,0:3]| + w_ori |euler_ZYX(R(a[i,3:7]))[0:2]|, quaternion read real-first; strided views as
+// in include/mppib.h.  Threaded over rows so that the CPU arm evaluates its Objective inside the parallel region.
+void oracle_cost_pose(int64_t n, const float* a, int64_t a_si, int64_t a_sr, const float* b, int64_t b_si, int64_t b_sr, float w_pos,
+                      float w_ori, float* cost, int32_t nthreads) {
+    parallel_for((int)n, nthreads, [&](int lo, int hi) {
+        for (int i = lo; i < hi; ++i) {
+            const float* ai = a + (size_t)i * a_si;
+            float c = 0.f;
+            if (w_pos != 0.f) {
+                const float* bi = b + (size_t)i * b_si;
+                const float dx = ai[0] - bi[0], dy = ai[a_sr] - bi[b_sr], dz = ai[2 * a_sr] - bi[2 * b_sr];
+                c += w_pos * std::sqrt(dx * dx + dy * dy + dz * dz);
+            }
+            if (w_ori != 0.f) {
+                const float r = ai[3 * a_sr], qi = ai[4 * a_sr], qj = ai[5 * a_sr], qk = ai[6 * a_sr];
+                const float two_s = 2.0f / (r * r + qi * qi + qj * qj + qk * qk);
+                const float m00 = 1.f - two_s * (qj * qj + qk * qk), m10 = two_s * (qi * qj + qk * r), m20 = two_s * (qi * qk - qj * r);
+                const float yaw = std::atan2(m10, m00), pitch = std::asin(-m20);
+                c += w_ori * std::sqrt(yaw * yaw + pitch * pitch);
+            }
+            cost[i] = c;
+        }
+    });
 }
 
 // Savitzky-Golay window 9, polyorder 2, mode='interp' (SURVEY Appendix C), along T for one column.

@@ -125,3 +125,24 @@ def shift(model, params, U):
     U = np.array(U, np.float32).reshape(params.T, model.nu).copy()
     lib().oracle_shift(C.byref(model), C.byref(params), _f(U))
     return U
+
+
+def reduce_mt(model, params, cost, x, U, nthreads):
+    """Threaded variant for the CPU timing arm (same rule, per-thread partials merged); numpy views, no copies."""
+    T, nu = params.T, model.nu
+    partial = np.zeros(2 + T * nu, np.float32)
+    lib().oracle_reduce_mt(C.byref(model), C.byref(params), _f(cost), _f(x), _f(U), _f(partial), C.c_int32(int(nthreads)))
+    return partial
+
+
+def cost_pose(a, b, w_pos, w_ori, out, nthreads):
+    """a: (N, >=7) float32 strided view, b: (N, >=3) strided view or None; out: contiguous (N,) float32 (numpy arrays)."""
+    n = a.shape[0]
+    ap = a.ctypes.data_as(C.POINTER(C.c_float))
+    if b is None:
+        bp, bsi, bsr = None, 0, 0
+    else:
+        bp, bsi, bsr = b.ctypes.data_as(C.POINTER(C.c_float)), b.strides[0] // 4, b.strides[1] // 4
+    lib().oracle_cost_pose(C.c_int64(n), ap, C.c_int64(a.strides[0] // 4), C.c_int64(a.strides[1] // 4), bp, C.c_int64(bsi), C.c_int64(bsr),
+                           C.c_float(w_pos), C.c_float(w_ori), _f(out), C.c_int32(int(nthreads)))
+    return out
