@@ -223,8 +223,16 @@ def pick_cpu_sample(name, threads, budget_s, k_max):
     return max(64, (k // 4) * 4)
 
 
+def host_cores():
+    """Host threads this process may run on (the affinity mask, not the machine's CPU count)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
 def cpu_baseline(name, n_plans=5, budget_s=2.0):
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     T = CONFIGS[name]["T"]
     k_s = pick_cpu_sample(name, cores, budget_s, CONFIGS[name]["K"])
     dt = cpu_plan_rate(name, k_s, n_plans, 1, cores)
@@ -244,7 +252,7 @@ def run_reference_arm(args, rank, world):
         return
     from oracle import oracle as orc
     orc.build()
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     name = args.config
     T = CONFIGS[name]["T"]
     k_s = pick_cpu_sample(name, cores, 2.0, CONFIGS[name]["K"])

@@ -45,6 +45,7 @@ struct MppibContext {
     void* peer_win[MPPIB_MAX_PEERS];           // window base of every rank (own entry = local allocation)
     unsigned long long peer_timeout_ns;
     float* action_mirror;                      // pinned host mirror of the action written by K4 (nullable)
+    int k3_variant;                            // 0 = warp-specialised K3 (default), 1 = block-synchronous K3 (MPPIB_K3_VARIANT / _WIDE / _GRID knobs)
     int k2_lanes;                              // K2 mapping for eligible scenes: 1 = one body per lane (default), 0 = one thread per rollout
 };
 

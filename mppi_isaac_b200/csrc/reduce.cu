@@ -115,6 +115,82 @@ __device__ __forceinline__ void finalize_rows(const MppibParams& p, int nu, cons
     if (threadIdx.x == 0 && stats) { stats[0] = b; stats[1] = e; }
 }
 
+// The last CTA of a K3 launch: fold the per-CTA partials (128-bit L2 loads, 8 in flight per thread), write the shard row, push it into
+// every rank's peer window (multi-GPU) and, for single-GPU plans, do K4's work in place.  `tiles` = at least MAX_GRID + 4 * (P + 3)
+// floats of idle shared memory, `misc` = 8 floats.
+__device__ __forceinline__ void fold_and_finish(const MppibParams& p, int nu, float* __restrict__ scratch, unsigned int* __restrict__ ticket,
+                                                float* __restrict__ partial, const PeerArgs& peers, float* __restrict__ fin_U, float* __restrict__ fin_action,
+                                                float* __restrict__ fin_stats, float* __restrict__ fin_mirror, float* tiles, float* misc, float inv_lambda) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NR = p.T * nu, P = 2 + NR;
+    const int G = (int)gridDim.x;
+    float* sc = tiles;                   // [MAX_GRID] scale of every CTA partial (the ring is idle now)
+    float* fold = tiles + MAX_GRID;      // [4][PP]
+    {
+        float b = (tid < G) ? __ldcg(scratch + (size_t)tid * ((((P + 3) >> 2) << 2))) : INFINITY;
+        const float b2 = (tid + NT < G) ? __ldcg(scratch + (size_t)(tid + NT) * ((((P + 3) >> 2) << 2))) : INFINITY;   // CTAs 256..511
+        float bm = warp_min(fminf(b, b2));
+        if (lane == 0) misc[warp] = bm;
+        __syncthreads();
+        float bb = INFINITY;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) bb = fminf(bb, misc[w8]);
+        if (tid < G) sc[tid] = (b == INFINITY) ? 0.f : expf(-(b - bb) * inv_lambda);
+        if (tid + NT < G) sc[tid + NT] = (b2 == INFINITY) ? 0.f : expf(-(b2 - bb) * inv_lambda);
+        __syncthreads();
+        // parallel fold with deep memory-level parallelism: P4 = ceil(P/4) float4 columns x 4 CTA groups of 64 threads;
+        // thread (cg, e4) sums CTAs c = cg, cg+4, ... with 8 independent 128-bit L2 loads in flight
+        // (scratch rows are padded to a multiple of 4 floats, so every row is 16-byte aligned)
+        const int P4 = (P + 3) >> 2, PP = P4 << 2;
+        const int cg = tid >> 6, e4 = tid & 63;
+        for (int e = e4; e < P4; e += 64) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int c = cg;
+            for (; c + 28 < G; c += 32) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(scratch + (size_t)(c + 4 * u) * PP) + e);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const float sc_ = sc[c + 4 * u]; acc.x += sc_ * v[u].x; acc.y += sc_ * v[u].y; acc.z += sc_ * v[u].z; acc.w += sc_ * v[u].w; }
+            }
+            for (; c < G; c += 4) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(scratch + (size_t)c * PP) + e);
+                const float sc_ = sc[c];
+                acc.x += sc_ * v.x; acc.y += sc_ * v.y; acc.z += sc_ * v.z; acc.w += sc_ * v.w;
+            }
+            reinterpret_cast<float4*>(fold + (size_t)cg * PP)[e] = acc;
+        }
+        __syncthreads();
+        // fused exchange: this rank's row goes straight into the window of every rank (remote stores over NVLink),
+        // then one release-store of the arrival flag per peer; K4 on each rank acquires its own flags
+        uint32_t seq = 0;
+        if (peers.world > 1) seq = *reinterpret_cast<const volatile uint32_t*>(peers.win[peers.rank]) + 1u;
+        const size_t row_off = MPPIB_WIN_DATA_OFF / sizeof(float) + ((size_t)(seq & 1u) * peers.world + peers.rank) * peers.pcap;
+        for (int e = tid; e < P; e += NT) {
+            const float v0 = fold[e] + fold[PP + e] + fold[2 * PP + e] + fold[3 * PP + e];
+            const float v = e == 0 ? bb : v0;
+            partial[e] = v;
+            for (int g = 0; g < peers.world; ++g) reinterpret_cast<float*>(peers.win[g])[row_off + e] = v;
+        }
+        if (peers.world > 1) {
+            __threadfence_system();
+            __syncthreads();
+            if (tid < peers.world) {
+                uint32_t* flag = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(peers.win[tid]) + MPPIB_WIN_FLAGS_OFF) + (seq & 1u) * MPPIB_MAX_PEERS + peers.rank;
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
+            }
+        }
+        if (tid == 0) *ticket = 0u;
+        if (fin_U != nullptr) {
+            // single-GPU plans: this CTA is the last one alive and holds the shard row -> do K4's work here (U update, savgol,
+            // first action) instead of launching another kernel.  Every CTA read U in its prologue, long before this point.
+            __threadfence();
+            __syncthreads();
+            finalize_rows(p, nu, partial, 1, P, fin_U, fin_action, fin_stats, fin_mirror, tiles);
+        }
+    }
+}
+
 template <int W, int NS, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 mppib_reduce_kernel(const __grid_constant__ MppibParams p, const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_c,
@@ -267,72 +343,185 @@ mppib_reduce_kernel(const __grid_constant__ MppibParams p, const __grid_constant
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    const int G = (int)gridDim.x;
-    float* sc = tiles;                   // [MAX_GRID] scale of every CTA partial (the ring is idle now)
-    float* fold = tiles + MAX_GRID;      // [4][PP]
+    fold_and_finish(p, nu, scratch, ticket, partial, peers, fin_U, fin_action, fin_stats, fin_mirror, tiles, misc, inv_lambda);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K3, warp-specialised (the default): ONE producer warp streams 32-sample tiles through an NSTAGE-deep ring with TMA, SEVEN
+// consumer warps each own WHOLE tiles end to end -- S_k, minimum, weights, weighted row sums, online merge into the warp's own
+// running (beta, eta, W) in registers -- so nothing inside the streaming loop is CTA-wide: no __syncthreads, the only
+// synchronisation is the full / empty mbarrier pair of a ring stage (the first version above runs three block barriers per
+// tile; ncu: barrier stall 2.0 per issued instruction at K = 262 144, profiles/r1_reduce_v2.md).
+//   tile i of this CTA -> ring stage i % NSTAGE, consumer i % NCONS;  full[s]: TMA complete_tx;  empty[s]: the consumer's arrive
+//   per tile and warp: phase A lane = sample (S_k = sum_t gamma^t c[t][k] + sum_r g[r] x[r][k], conflict-free column reads),
+//                      phase B warp shuffles (min, exp, sum), weights to a 32-float per-warp strip,
+//                      phase C lane = row (r = lane, lane + 32, ...: W[r] += sum_k w_k x[r][k], rotated LDS.128, conflict-free)
+// After the loop the seven warp partials are merged once through shared memory; the per-CTA partial, the ticket and the
+// last-CTA fold / exchange / fused K4 are shared with the kernel above (fold_and_finish).
+constexpr int WS_W = 32;          // samples per tile
+constexpr int WS_NCONS = 7;       // consumer warps (warp 0 is the producer)
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int RPL>   // rows of W per lane: T*nu <= 32 * RPL
+__global__ void __launch_bounds__(NT, 1)
+mppib_reduce_ws_kernel(const __grid_constant__ MppibParams p, const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_c,
+                       int nu, int xbox_rows, int nstage, const float* __restrict__ U, float* __restrict__ scratch, unsigned int* __restrict__ ticket,
+                       float* __restrict__ partial, const __grid_constant__ PeerArgs peers, float* __restrict__ fin_U, float* __restrict__ fin_action,
+                       float* __restrict__ fin_stats, float* __restrict__ fin_mirror) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int K = p.K, T = p.T, NR = T * nu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float inv_lambda = 1.0f / p.lambda_;
+    const bool simple = p.mode == MPPIB_MODE_SIMPLE;
+    const int P = 2 + NR;
+
+    const int tile_floats = (NR + T) * WS_W;                                  // a multiple of 32 floats: stages stay 128-B aligned
+    float* tiles = reinterpret_cast<float*>(smem_raw);                        // [nstage][(NR+T)*32]
+    const int NR4 = (NR + 3) & ~3, T4 = (T + 3) & ~3, P4 = (P + 3) & ~3;
+    float* g = tiles + (size_t)nstage * tile_floats;                          // [NR4] lambda * Sigma^-1 U (SIMPLE), zero padded
+    float* gp = g + NR4;                                                      // [T4]  gamma^t, zero padded
+    float* wk = gp + T4;                                                      // [8][32] weights of the tile a warp is working on
+    float* cpart = wk + 8 * WS_W;                                             // [NCONS][P4] warp partials (after the loop)
+    float* misc = cpart + WS_NCONS * P4;                                      // [8]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (((size_t)((misc + 8) - tiles) * 4 + 15) & ~(size_t)15));   // [nstage]
+    uint64_t* empty = full + nstage;                                          // [nstage]
+
+    const int ntiles = (K + WS_W - 1) / WS_W;
+    const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const uint32_t tile_bytes = (uint32_t)tile_floats * 4u;
+
+    if (tid == 0) {
+        for (int s = 0; s < nstage; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (int r = tid; r < NR4; r += NT) {
+        float acc = 0.f;
+        if (simple && r < NR) {
+            const int t = r / nu, i = r % nu;
+            for (int j = 0; j < nu; ++j) acc += p.sigma_inv[i * nu + j] * U[t * nu + j];
+            acc *= p.lambda_;
+        }
+        g[r] = acc;
+    }
+    for (int t = tid; t < T4; t += NT) gp[t] = t < T ? powf(p.gamma, (float)t) : 0.f;
+    __syncthreads();
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- producer: one elected lane keeps the ring full
+        if (lane == 0) {
+            for (int i = 0; i < my_tiles; ++i) {
+                const int s = i % nstage, n = i / nstage;
+                if (n > 0) mbar_wait(&empty[s], (uint32_t)((n - 1) & 1));     // the consumer of tile i - nstage is done with the stage
+                const int k0 = ((int)blockIdx.x + i * (int)gridDim.x) * WS_W;
+                float* dst = tiles + (size_t)s * tile_floats;
+                mbar_expect_tx(&full[s], tile_bytes);
+                for (int r0 = 0; r0 < NR; r0 += xbox_rows) tma_load_2d(dst + (size_t)r0 * WS_W, &tm_x, k0, r0, &full[s]);
+                tma_load_2d(dst + (size_t)NR * WS_W, &tm_c, k0, 0, &full[s]);
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- consumers: whole tiles, no block-wide synchronisation
+        const int c = warp - 1;
+        float* wme = wk + warp * WS_W;
+        float b_run = INFINITY, e_run = 0.f, w_run[RPL];
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) w_run[i] = 0.f;
+        for (int i = c; i < my_tiles; i += WS_NCONS) {
+            const int s = i % nstage;
+            const int k0 = ((int)blockIdx.x + i * (int)gridDim.x) * WS_W;
+            const float* xs = tiles + (size_t)s * tile_floats;                // [NR][32]
+            const float* cs = xs + (size_t)NR * WS_W;                         // [T][32]
+            mbar_wait(&full[s], (uint32_t)((i / nstage) & 1));
+            // ---- A: S of sample k0 + lane (four independent accumulation chains; padded g / gp entries are zero and the
+            // rows they would multiply are clamped to a valid one)
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            for (int t = 0; t < T4; t += 4) {
+                const float4 g4 = *reinterpret_cast<const float4*>(gp + t);
+                a0 = fmaf(g4.x, cs[t * WS_W + lane], a0);
+                a1 = fmaf(g4.y, cs[min(t + 1, T - 1) * WS_W + lane], a1);
+                a2 = fmaf(g4.z, cs[min(t + 2, T - 1) * WS_W + lane], a2);
+                a3 = fmaf(g4.w, cs[min(t + 3, T - 1) * WS_W + lane], a3);
+            }
+            if (simple) {
+                for (int r = 0; r < NR4; r += 4) {
+                    const float4 g4 = *reinterpret_cast<const float4*>(g + r);
+                    a0 = fmaf(g4.x, xs[r * WS_W + lane], a0);
+                    a1 = fmaf(g4.y, xs[min(r + 1, NR - 1) * WS_W + lane], a1);
+                    a2 = fmaf(g4.z, xs[min(r + 2, NR - 1) * WS_W + lane], a2);
+                    a3 = fmaf(g4.w, xs[min(r + 3, NR - 1) * WS_W + lane], a3);
+                }
+            }
+            const float sum = (a0 + a1) + (a2 + a3);
+            // ---- B: tile minimum, weights, their sum
+            const bool valid = (k0 + lane < K) && isfinite(sum);
+            const float S = valid ? sum : INFINITY;
+            const float b_c = warp_min(S);
+            const float w = (S == INFINITY) ? 0.f : expf(-(S - b_c) * inv_lambda);
+            const float e_c = warp_sum(w);
+            if (b_c != INFINITY) {                                            // warp-uniform
+                wme[lane] = w;
+                __syncwarp();
+                const float b_out = fminf(b_run, b_c);
+                const float s_old = (b_run == INFINITY) ? 0.f : expf(-(b_run - b_out) * inv_lambda);
+                const float s_new = expf(-(b_c - b_out) * inv_lambda);
+                // ---- C: weighted row sums, lane = row
+                const float4* w4 = reinterpret_cast<const float4*>(wme);
+#pragma unroll
+                for (int rr = 0; rr < RPL; ++rr) {
+                    const int r = lane + 32 * rr;
+                    if (r < NR) {
+                        const float4* xr = reinterpret_cast<const float4*>(xs + (size_t)r * WS_W);
+                        float acc = 0.f;
+#pragma unroll
+                        for (int j = 0; j < WS_W / 4; ++j) {
+                            const int jj = (j + lane) & (WS_W / 4 - 1);       // rotation => conflict-free LDS.128
+                            const float4 a = xr[jj], b = w4[jj];
+                            acc += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+                        }
+                        w_run[rr] = w_run[rr] * s_old + acc * s_new;
+                    }
+                }
+                e_run = e_run * s_old + e_c * s_new;
+                b_run = b_out;
+            }
+            __syncwarp();                                                     // every lane is done with the stage and with wme
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        // this warp's partial -> shared memory
+        float* mine = cpart + (size_t)c * P4;
+        if (lane == 0) { mine[0] = b_run; mine[1] = e_run; }
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr) { const int r = lane + 32 * rr; if (r < NR) mine[2 + r] = w_run[rr]; }
+    }
+    __syncthreads();
+    // ---- merge the warp partials into the CTA partial (global scratch), then ticket -> the last CTA folds all of them
     {
-        float b = (tid < G) ? __ldcg(scratch + (size_t)tid * ((((P + 3) >> 2) << 2))) : INFINITY;
-        const float b2 = (tid + NT < G) ? __ldcg(scratch + (size_t)(tid + NT) * ((((P + 3) >> 2) << 2))) : INFINITY;   // CTAs 256..511
-        float bm = warp_min(fminf(b, b2));
-        if (lane == 0) misc[warp] = bm;
-        __syncthreads();
+        float* mine = scratch + (size_t)blockIdx.x * P4;
         float bb = INFINITY;
 #pragma unroll
-        for (int w8 = 0; w8 < 8; ++w8) bb = fminf(bb, misc[w8]);
-        if (tid < G) sc[tid] = (b == INFINITY) ? 0.f : expf(-(b - bb) * inv_lambda);
-        if (tid + NT < G) sc[tid + NT] = (b2 == INFINITY) ? 0.f : expf(-(b2 - bb) * inv_lambda);
-        __syncthreads();
-        // parallel fold with deep memory-level parallelism: P4 = ceil(P/4) float4 columns x 4 CTA groups of 64 threads;
-        // thread (cg, e4) sums CTAs c = cg, cg+4, ... with 8 independent 128-bit L2 loads in flight
-        // (scratch rows are padded to a multiple of 4 floats, so every row is 16-byte aligned)
-        const int P4 = (P + 3) >> 2, PP = P4 << 2;
-        const int cg = tid >> 6, e4 = tid & 63;
-        for (int e = e4; e < P4; e += 64) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            int c = cg;
-            for (; c + 28 < G; c += 32) {
-                float4 v[8];
+        for (int c = 0; c < WS_NCONS; ++c) bb = fminf(bb, cpart[(size_t)c * P4]);
+        float sc[WS_NCONS];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(scratch + (size_t)(c + 4 * u) * PP) + e);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { const float sc_ = sc[c + 4 * u]; acc.x += sc_ * v[u].x; acc.y += sc_ * v[u].y; acc.z += sc_ * v[u].z; acc.w += sc_ * v[u].w; }
-            }
-            for (; c < G; c += 4) {
-                const float4 v = __ldcg(reinterpret_cast<const float4*>(scratch + (size_t)c * PP) + e);
-                const float sc_ = sc[c];
-                acc.x += sc_ * v.x; acc.y += sc_ * v.y; acc.z += sc_ * v.z; acc.w += sc_ * v.w;
-            }
-            reinterpret_cast<float4*>(fold + (size_t)cg * PP)[e] = acc;
-        }
-        __syncthreads();
-        // fused exchange: this rank's row goes straight into the window of every rank (remote stores over NVLink),
-        // then one release-store of the arrival flag per peer; K4 on each rank acquires its own flags
-        uint32_t seq = 0;
-        if (peers.world > 1) seq = *reinterpret_cast<const volatile uint32_t*>(peers.win[peers.rank]) + 1u;
-        const size_t row_off = MPPIB_WIN_DATA_OFF / sizeof(float) + ((size_t)(seq & 1u) * peers.world + peers.rank) * peers.pcap;
+        for (int c = 0; c < WS_NCONS; ++c) { const float bc = cpart[(size_t)c * P4]; sc[c] = (bc == INFINITY) ? 0.f : expf(-(bc - bb) * inv_lambda); }
         for (int e = tid; e < P; e += NT) {
-            const float v0 = fold[e] + fold[PP + e] + fold[2 * PP + e] + fold[3 * PP + e];
-            const float v = e == 0 ? bb : v0;
-            partial[e] = v;
-            for (int g = 0; g < peers.world; ++g) reinterpret_cast<float*>(peers.win[g])[row_off + e] = v;
-        }
-        if (peers.world > 1) {
-            __threadfence_system();
-            __syncthreads();
-            if (tid < peers.world) {
-                uint32_t* flag = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(peers.win[tid]) + MPPIB_WIN_FLAGS_OFF) + (seq & 1u) * MPPIB_MAX_PEERS + peers.rank;
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
-            }
-        }
-        if (tid == 0) *ticket = 0u;
-        if (fin_U != nullptr) {
-            // single-GPU plans: this CTA is the last one alive and holds the shard row -> do K4's work here (U update, savgol,
-            // first action) instead of launching another kernel.  Every CTA read U in its prologue, long before this point.
-            __threadfence();
-            __syncthreads();
-            finalize_rows(p, nu, partial, 1, P, fin_U, fin_action, fin_stats, fin_mirror, tiles);
+            float v = 0.f;
+#pragma unroll
+            for (int c = 0; c < WS_NCONS; ++c) v += sc[c] * cpart[(size_t)c * P4 + e];
+            mine[e] = e == 0 ? bb : v;
         }
     }
+    __threadfence();
+    __syncthreads();
+    __shared__ unsigned int s_last_ws;
+    if (tid == 0) s_last_ws = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last_ws) return;
+    __threadfence();
+    fold_and_finish(p, nu, scratch, ticket, partial, peers, fin_U, fin_action, fin_stats, fin_mirror, tiles, misc, inv_lambda);
 }
 
 // K4: combine G shard partials, U update, optional Savitzky-Golay (window 9, order 2, 'interp' edges), action out.
@@ -458,6 +647,53 @@ int launch_reduce_t(MppibContext* c, const float* cost, const float* x, const fl
     return 0;
 }
 
+
+// shared memory of the warp-specialised kernel with `nstage` ring stages
+static size_t reduce_ws_smem_bytes(int T, int nu, int nstage) {
+    const int NR = T * nu, P4 = (2 + NR + 3) & ~3;
+    size_t fl = (size_t)nstage * (size_t)(NR + T) * WS_W + ((NR + 3) & ~3) + ((T + 3) & ~3) + 8 * WS_W + (size_t)WS_NCONS * P4 + 8;
+    const size_t fold = MAX_GRID + 4 * (size_t)(2 + NR + 3) + 64;            // the last CTA reuses the ring for the fold
+    if ((size_t)nstage * (size_t)(NR + T) * WS_W < fold) fl += fold;
+    return sizeof(float) * fl + 16 + sizeof(uint64_t) * 2 * nstage + 128;
+}
+static int reduce_ws_stages(int T, int nu) {
+    int ns = 8;
+    while (ns > 1 && reduce_ws_smem_bytes(T, nu, ns) > 224 * 1024) --ns;
+    return ns;
+}
+
+template <int RPL>
+int launch_reduce_ws_t(MppibContext* c, const float* cost, const float* x, const float* U, float* partial, float* fin_U, float* fin_action,
+                       float* fin_stats, cudaStream_t s) {
+    const int T = c->params.T, nu = c->model.nu, NR = T * nu, K = c->params.K;
+    const int nstage = reduce_ws_stages(T, nu);
+    const size_t smem = reduce_ws_smem_bytes(T, nu, nstage);
+    static size_t smem_attr[64] = {0};
+    size_t& attr = smem_attr[c->device & 63];
+    if (smem > attr) {
+        MPPIB_CHECK_CUDA(cudaFuncSetAttribute(mppib_reduce_ws_kernel<RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    int xbox_rows = NR < 256 ? NR : 256;
+    while (NR % xbox_rows != 0) --xbox_rows;
+    // tensor maps are rebuilt only when a buffer, the shape or the device changes (the eager / stepwise path calls this per plan)
+    struct MapCache { const void* x; const void* c; int K, T, nu, dev; CUtensorMap tm_x, tm_c; };
+    static thread_local MapCache mc = {nullptr, nullptr, 0, 0, 0, -1, {}, {}};
+    if (mc.x != x || mc.c != cost || mc.K != K || mc.T != T || mc.nu != nu || mc.dev != c->device) {
+        if (int rc = make_map(&mc.tm_x, x, NR, K, xbox_rows, WS_W)) return rc;
+        if (int rc = make_map(&mc.tm_c, cost, T, K, T, WS_W)) return rc;
+        mc.x = x; mc.c = cost; mc.K = K; mc.T = T; mc.nu = nu; mc.dev = c->device;
+    }
+    const int ntiles = (K + WS_W - 1) / WS_W;
+    int grid = ntiles < c->num_sms ? ntiles : c->num_sms;
+    if (grid > MAX_GRID) grid = MAX_GRID;
+    MPPIB_REQUIRE(grid <= c->reduce_max_ctas, "mppib_reduce: scratch too small");
+    mppib_reduce_ws_kernel<RPL><<<grid, NT, smem, s>>>(c->params, mc.tm_x, mc.tm_c, nu, xbox_rows, nstage, U, c->reduce_scratch, c->reduce_ticket, partial,
+                                                      reduce_peers(c), fin_U, fin_action, fin_stats, fin_U ? c->action_mirror : nullptr);
+    MPPIB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace
 
 int launch_reduce(MppibContext* c, const float* cost, const float* x, const float* U, float* partial, float* fin_U, float* fin_action,
@@ -466,6 +702,13 @@ int launch_reduce(MppibContext* c, const float* cost, const float* x, const floa
     MPPIB_REQUIRE(c->params.K >= 4 && c->params.K % 4 == 0, "mppib_reduce: K=%d must be a positive multiple of 4 (16-byte rows for TMA / 128-bit loads)", c->params.K);
     MPPIB_REQUIRE(T * nu <= RPT * NT, "mppib_reduce: T*nu = %d exceeds %d", T * nu, RPT * NT);
     MPPIB_REQUIRE(T <= 256, "mppib_reduce: T = %d exceeds the 256-row TMA box", T);
+    // default: the warp-specialised kernel (two ring stages at least); MPPIB_K3_VARIANT=64x3|64x1|32x4|32x2 selects the block-synchronous one
+    if (c->k3_variant == 0 && reduce_ws_stages(T, nu) >= 2) {
+        const int NR = T * nu;
+        if (NR <= 32 * 4) return launch_reduce_ws_t<4>(c, cost, x, U, partial, fin_U, fin_action, fin_stats, s);
+        if (NR <= 32 * 8) return launch_reduce_ws_t<8>(c, cost, x, U, partial, fin_U, fin_action, fin_stats, s);
+        return launch_reduce_ws_t<16>(c, cost, x, U, partial, fin_U, fin_action, fin_stats, s);
+    }
     // wide tiles once every SM has one; narrow tiles keep all SMs busy at small K
     bool wide = c->params.K >= 64 * c->num_sms && reduce_smem_bytes<64, 3>(T, nu) <= 226 * 1024;   // tools/tune_reduce.py: 12.5 -> 11.7 us at K = 10 000
     if (const char* e = getenv("MPPIB_K3_WIDE")) wide = atoi(e) != 0 && reduce_smem_bytes<64, 3>(T, nu) <= 226 * 1024;   // tuning knob

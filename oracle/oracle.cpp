@@ -139,7 +139,8 @@ class Pool {
 template <class F>
 void parallel_for(int n, int nthreads, F f) {
     if (nthreads <= 1 || n < 2 * nthreads) { f(0, n); return; }
-    const int grain = std::max(1, n / (nthreads * 8));
+    // blocks of whole cache lines of the k-innermost arrays (16 floats): neighbouring threads never write the same line
+    const int grain = std::max(16, (n / (nthreads * 4)) & ~15);
     Pool::get().run(n, nthreads, grain, std::function<void(int, int)>(f));
 }
 

@@ -153,6 +153,7 @@ def test_compute_action_with_obstacles_rebuilds_the_gpu_planner():
     cpu = MPPIisaacPlanner(point_cfg(K=256, T=12, device="cpu"), PointReachObjective(), backend=OracleBackend())
     q, qd = [0.1, 0.0, 0.0], [0.0, 0.0, 0.0]
     a0 = gpu.compute_action(q, qd)                                       # no obstacle yet: graph captured on the first handle
+    cpu.compute_action(q, qd)
     for it in range(3):
         ag, ac = gpu.compute_action(q, qd, obst=obst), cpu.compute_action(q, qd, obst=obst)
         assert torch.isfinite(ag).all() and float(ag.abs().max()) > 0.0
