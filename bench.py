@@ -231,18 +231,36 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_baseline(name, n_plans=5, budget_s=2.0):
+def best_thread_count(name):
+    """Thread count that gives the highest plan rate on THIS host: shared boxes report 128 logical CPUs of which far fewer are
+    available (tools/cpu_scaling.py on the GPU box: linear to 16 threads, best at 32, slower beyond) -- an all-CPUs run would
+    understate the CPU arm.  Probed on a small K with the candidates {all, 1/2, 1/4, 1/8 of the affinity mask, 32, 16}."""
     cores = host_cores()
+    cands = sorted({c for c in (cores, cores // 2, cores // 4, cores // 8, 32, 16) if 1 <= c <= cores}, reverse=True)
+    k_probe = 2048
+    rates = {}
+    for c in cands:
+        rates[c] = k_probe / cpu_plan_rate(name, k_probe, 2, 1, c)
+    best = max(rates, key=rates.get)
+    return best, {str(c): round(r * CONFIGS[name]["T"]) for c, r in rates.items()}
+
+
+def cpu_baseline(name, n_plans=5, budget_s=2.0, threads=None):
+    probe = None
+    if threads is None:
+        threads, probe = best_thread_count(name)
     T = CONFIGS[name]["T"]
-    k_s = pick_cpu_sample(name, cores, budget_s, CONFIGS[name]["K"])
-    dt = cpu_plan_rate(name, k_s, n_plans, 1, cores)
+    k_s = pick_cpu_sample(name, threads, budget_s, CONFIGS[name]["K"])
+    dt = cpu_plan_rate(name, k_s, n_plans, 1, threads)
     k1 = max(64, min(256, k_s))
     dt1 = cpu_plan_rate(name, k1, 3, 1, 1)
     v, v1 = k_s * T / dt, k1 * T / dt1
-    return {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n_plans} plans of K={k_s} of the K={CONFIGS[name]['K']} workload, CPU restatement (oracle/) on {cores} threads (persistent pool)",
+    return {"value": v, "unit": UNIT, "cores": threads, "host_cpus": host_cores(), "kind": "port",
+            "sample": f"{n_plans} plans of K={k_s} of the K={CONFIGS[name]['K']} workload, CPU restatement (oracle/) on {threads} threads "
+                      f"(persistent pool; the thread count with the highest rate on this host)",
+            "thread_probe_rollout_steps_per_s": probe,
             "plan_hz_at_config_K_est": 1.0 / (dt * CONFIGS[name]["K"] / k_s),
-            "parallel_efficiency": v / (cores * v1),
+            "parallel_efficiency": v / (threads * v1),
             "one_thread": {"value": v1, "unit": UNIT, "sample": f"3 plans of K={k1} on 1 thread",
                            "plan_hz_at_config_K_est": 1.0 / (dt1 * CONFIGS[name]["K"] / k1)}}, dt, k_s
 
@@ -252,11 +270,11 @@ def run_reference_arm(args, rank, world):
         return
     from oracle import oracle as orc
     orc.build()
-    cores = host_cores()
     name = args.config
     T = CONFIGS[name]["T"]
-    k_s = pick_cpu_sample(name, cores, 2.0, CONFIGS[name]["K"])
-    dt = cpu_plan_rate(name, k_s, args.steps, args.warmup, cores)
+    threads, probe = best_thread_count(name)
+    k_s = pick_cpu_sample(name, threads, 2.0, CONFIGS[name]["K"])
+    dt = cpu_plan_rate(name, k_s, args.steps, args.warmup, threads)
     value = k_s * T / dt
     k1 = max(64, min(256, k_s))
     dt1 = cpu_plan_rate(name, k1, 2, 1, 1)
@@ -266,9 +284,9 @@ def run_reference_arm(args, rank, world):
         "dtype": "f32", "data": "synthetic",
         "config": base_config(name, world, args.scaling),
         "note": "CPU restatement of the reference pipeline (oracle/), not IsaacGym/PhysX: those cannot run here (BASELINE.md section 2)",
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} plans of K={k_s} of the K={CONFIGS[name]['K']} workload (rate is per rollout-step, K-independent)",
-                         "parallel_efficiency": value / (cores * (k1 * T / dt1))},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "host_cpus": host_cores(), "kind": "port",
+                         "sample": f"{args.steps} plans of K={k_s} of the K={CONFIGS[name]['K']} workload on {threads} threads (rate is per rollout-step, K-independent)",
+                         "thread_probe_rollout_steps_per_s": probe, "parallel_efficiency": value / (threads * (k1 * T / dt1))},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -146,6 +146,13 @@ __device__ __forceinline__ void fold_and_finish(const MppibParams& p, int nu, fl
         for (int e = e4; e < P4; e += 64) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             int c = cg;
+            for (; c + 60 < G; c += 64) {        // 16 independent 128-bit loads in flight: 148 CTA rows are two to three L2 round trips
+                float4 v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(scratch + (size_t)(c + 4 * u) * PP) + e);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) { const float sc_ = sc[c + 4 * u]; acc.x += sc_ * v[u].x; acc.y += sc_ * v[u].y; acc.z += sc_ * v[u].z; acc.w += sc_ * v[u].w; }
+            }
             for (; c + 28 < G; c += 32) {
                 float4 v[8];
 #pragma unroll
@@ -393,10 +400,19 @@ mppib_reduce_ws_kernel(const __grid_constant__ MppibParams p, const __grid_const
     const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const uint32_t tile_bytes = (uint32_t)tile_floats * 4u;
 
+    auto issue_tile = [&](int i) {   // elected producer lane: TMA tile i of this CTA into ring stage i % nstage
+        const int s = i % nstage;
+        const int k0 = ((int)blockIdx.x + i * (int)gridDim.x) * WS_W;
+        float* dst = tiles + (size_t)s * tile_floats;
+        mbar_expect_tx(&full[s], tile_bytes);
+        for (int r0 = 0; r0 < NR; r0 += xbox_rows) tma_load_2d(dst + (size_t)r0 * WS_W, &tm_x, k0, r0, &full[s]);
+        tma_load_2d(dst + (size_t)NR * WS_W, &tm_c, k0, 0, &full[s]);
+    };
     if (tid == 0) {
         for (int s = 0; s < nstage; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int i = 0; i < nstage && i < my_tiles; ++i) issue_tile(i);   // the first ring fill is in flight while the prologue below runs
     }
     for (int r = tid; r < NR4; r += NT) {
         float acc = 0.f;
@@ -407,20 +423,19 @@ mppib_reduce_ws_kernel(const __grid_constant__ MppibParams p, const __grid_const
         }
         g[r] = acc;
     }
-    for (int t = tid; t < T4; t += NT) gp[t] = t < T ? powf(p.gamma, (float)t) : 0.f;
+    {
+        const float lg = log2f(p.gamma);
+        for (int t = tid; t < T4; t += NT) gp[t] = t < T ? exp2f(lg * (float)t) : 0.f;
+    }
     __syncthreads();
 
     if (warp == 0) {
         // ---------------------------------------------------------------- producer: one elected lane keeps the ring full
         if (lane == 0) {
-            for (int i = 0; i < my_tiles; ++i) {
+            for (int i = nstage; i < my_tiles; ++i) {
                 const int s = i % nstage, n = i / nstage;
-                if (n > 0) mbar_wait(&empty[s], (uint32_t)((n - 1) & 1));     // the consumer of tile i - nstage is done with the stage
-                const int k0 = ((int)blockIdx.x + i * (int)gridDim.x) * WS_W;
-                float* dst = tiles + (size_t)s * tile_floats;
-                mbar_expect_tx(&full[s], tile_bytes);
-                for (int r0 = 0; r0 < NR; r0 += xbox_rows) tma_load_2d(dst + (size_t)r0 * WS_W, &tm_x, k0, r0, &full[s]);
-                tma_load_2d(dst + (size_t)NR * WS_W, &tm_c, k0, 0, &full[s]);
+                mbar_wait(&empty[s], (uint32_t)((n - 1) & 1));                // the consumer of tile i - nstage is done with the stage
+                issue_tile(i);
             }
         }
     } else {
