@@ -37,6 +37,13 @@ mppib_cost_pose_kernel(long long n, const float* __restrict__ a, long long a_si,
 int launch_cost_pose(long long n, const float* a, long long a_si, long long a_sr, const float* b, long long b_si, long long b_sr, float w_pos,
                      float w_ori, float* cost, int accumulate, cudaStream_t s) {
     if (n <= 0) return 0;
+    // this entry has no handle: run on the device that owns `cost` (the caller's current device may be another one, e.g. a planner
+    // on cuda:1 served from a thread whose current device is cuda:0), and give the caller's device back afterwards
+    cudaPointerAttributes attr;
+    MPPIB_CHECK_CUDA(cudaPointerGetAttributes(&attr, cost));
+    MPPIB_REQUIRE(attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged, "mppib_cost_pose: `cost` is not device memory");
+    DeviceGuard guard(attr.device);
+    MPPIB_CHECK_CUDA(guard.err);
     const int block = 256;
     const long long want = (n + block - 1) / block;
     const int grid = (int)(want < 148LL * 8 ? want : 148LL * 8);
