@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import torch
 
@@ -54,6 +55,14 @@ def _ptr(t):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
+def _destroy_handle(lib, handle_value):
+    """Finalizer of a live MppibHandle (garbage collection or interpreter exit): frees the handle's device scratch."""
+    try:
+        lib.mppib_destroy(C.c_void_p(handle_value))
+    except Exception:  # noqa: BLE001
+        pass
+
+
 class CudaBackend:
     """One handle per GPU (``MppibHandle``).  All tensor arguments must live on ``self.device``."""
 
@@ -85,19 +94,17 @@ class CudaBackend:
             self.destroy()
         self.model, self.params = model, params
         self._check(self.lib.mppib_create(C.byref(model), C.byref(params), C.c_int32(self.device.index), C.byref(self.handle)), "mppib_create")
+        self._finalizer = weakref.finalize(self, _destroy_handle, self.lib, self.handle.value)   # also runs at interpreter exit
         if self._mirror_keepalive is not None:           # a re-created handle keeps writing the action to the same pinned mirror
             self.set_action_mirror(self._mirror_keepalive)
 
     def destroy(self):
         if self.handle:
+            fin = getattr(self, "_finalizer", None)
+            if fin is not None:
+                fin.detach()
             self.lib.mppib_destroy(self.handle)
             self.handle = C.c_void_p(0)
-
-    def __del__(self):
-        try:
-            self.destroy()
-        except Exception:
-            pass
 
     def set_params(self, params: MppibParams):
         self.params = params
