@@ -46,6 +46,7 @@ struct MppibContext {
     unsigned long long peer_timeout_ns;
     float* action_mirror;                      // pinned host mirror of the action written by K4 (nullable)
     int k3_variant;                            // 0 = warp-specialised K3 (default), 1 = block-synchronous K3 (MPPIB_K3_VARIANT / _WIDE / _GRID knobs)
+    int k2_pairs;                              // lanes kernel: -1 = choose by K (default), 0 / 1 = force one / two rollouts per lane group (MPPIB_K2_PAIRS)
     int k2_lanes;                              // K2 mapping for eligible scenes: 1 = one body per lane (default), 0 = one thread per rollout
 };
 

@@ -375,7 +375,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <int RPL>   // rows of W per lane: T*nu <= 32 * RPL
 __global__ void __launch_bounds__(NT, 1)
 mppib_reduce_ws_kernel(const __grid_constant__ MppibParams p, const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_c,
-                       int nu, int xbox_rows, int nstage, const float* __restrict__ U, float* __restrict__ scratch, unsigned int* __restrict__ ticket,
+                       int nu, int xbox_rows, int nstage, int ncons, const float* __restrict__ U, float* __restrict__ scratch, unsigned int* __restrict__ ticket,
                        float* __restrict__ partial, const __grid_constant__ PeerArgs peers, float* __restrict__ fin_U, float* __restrict__ fin_action,
                        float* __restrict__ fin_stats, float* __restrict__ fin_mirror) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -438,14 +438,16 @@ mppib_reduce_ws_kernel(const __grid_constant__ MppibParams p, const __grid_const
                 issue_tile(i);
             }
         }
-    } else {
+    } else if (warp <= ncons) {
         // ---------------------------------------------------------------- consumers: whole tiles, no block-wide synchronisation
+        // nstage is a multiple of ncons, so ring stage s is always drained by consumer s % ncons: a consumer waits for phase n of
+        // full[s] only after it has itself consumed phase n - 1 (the parity test cannot tell phases two apart)
         const int c = warp - 1;
         float* wme = wk + warp * WS_W;
         float b_run = INFINITY, e_run = 0.f, w_run[RPL];
 #pragma unroll
         for (int i = 0; i < RPL; ++i) w_run[i] = 0.f;
-        for (int i = c; i < my_tiles; i += WS_NCONS) {
+        for (int i = c; i < my_tiles; i += ncons) {
             const int s = i % nstage;
             const int k0 = ((int)blockIdx.x + i * (int)gridDim.x) * WS_W;
             const float* xs = tiles + (size_t)s * tile_floats;                // [NR][32]
@@ -511,6 +513,11 @@ mppib_reduce_ws_kernel(const __grid_constant__ MppibParams p, const __grid_const
         if (lane == 0) { mine[0] = b_run; mine[1] = e_run; }
 #pragma unroll
         for (int rr = 0; rr < RPL; ++rr) { const int r = lane + 32 * rr; if (r < NR) mine[2 + r] = w_run[rr]; }
+    } else {
+        // spare warp (fewer ring stages than warps): an empty partial
+        float* mine = cpart + (size_t)(warp - 1) * P4;
+        if (lane == 0) { mine[0] = INFINITY; mine[1] = 0.f; }
+        for (int r = lane; r < NR; r += 32) mine[2 + r] = 0.f;
     }
     __syncthreads();
     // ---- merge the warp partials into the CTA partial (global scratch), then ticket -> the last CTA folds all of them
@@ -681,7 +688,11 @@ template <int RPL>
 int launch_reduce_ws_t(MppibContext* c, const float* cost, const float* x, const float* U, float* partial, float* fin_U, float* fin_action,
                        float* fin_stats, cudaStream_t s) {
     const int T = c->params.T, nu = c->model.nu, NR = T * nu, K = c->params.K;
-    const int nstage = reduce_ws_stages(T, nu);
+    // consumers = min(7, stages that fit); the ring depth is rounded down to a multiple of the consumer count so that a stage always
+    // belongs to the same consumer (see the kernel)
+    const int nstage_max = reduce_ws_stages(T, nu);
+    const int ncons = nstage_max < WS_NCONS ? nstage_max : WS_NCONS;
+    const int nstage = ncons * (nstage_max / ncons);
     const size_t smem = reduce_ws_smem_bytes(T, nu, nstage);
     static size_t smem_attr[64] = {0};
     size_t& attr = smem_attr[c->device & 63];
@@ -703,7 +714,7 @@ int launch_reduce_ws_t(MppibContext* c, const float* cost, const float* x, const
     int grid = ntiles < c->num_sms ? ntiles : c->num_sms;
     if (grid > MAX_GRID) grid = MAX_GRID;
     MPPIB_REQUIRE(grid <= c->reduce_max_ctas, "mppib_reduce: scratch too small");
-    mppib_reduce_ws_kernel<RPL><<<grid, NT, smem, s>>>(c->params, mc.tm_x, mc.tm_c, nu, xbox_rows, nstage, U, c->reduce_scratch, c->reduce_ticket, partial,
+    mppib_reduce_ws_kernel<RPL><<<grid, NT, smem, s>>>(c->params, mc.tm_x, mc.tm_c, nu, xbox_rows, nstage, ncons, U, c->reduce_scratch, c->reduce_ticket, partial,
                                                       reduce_peers(c), fin_U, fin_action, fin_stats, fin_U ? c->action_mirror : nullptr);
     MPPIB_CHECK_CUDA(cudaGetLastError());
     return 0;

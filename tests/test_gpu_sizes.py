@@ -138,6 +138,33 @@ def test_c5_full_size_determinism_and_shard_invariance():
     assert torch.equal(o8, o1[:, :, 3 * 8192:4 * 8192])
 
 
+@pytest.mark.parametrize("which,K", [("gripper", 65536), ("point", 65536), ("panda", 131072), ("gripper", 8192)])
+def test_k3_ring_parity_at_streaming_sizes(oracle, which, K):
+    """K3 against the oracle at sizes where every CTA streams more tiles than the ring holds (the producer waits on `empty`
+    barriers, stages are refilled several times): C5's shapes (nu = 9: 300-row tiles, 5 stages / 5 consumers, two TMA boxes per
+    tile), a narrow one (nu = 3: 7 stages of 48 rows) and the headline's (nu = 7, 7 stages)."""
+    from mppi_isaac_b200.model.blob import MODE_SIMPLE
+    from scenes import gripper_setup, point_setup
+    setup, T = {"gripper": (gripper_setup, 30), "point": (point_setup, 12), "panda": (panda_setup, 30)}[which]
+    sc, p, _ = setup(K=K, T=T)
+    nu = sc.nu
+    be = gpu_backend(sc, p)
+    rng = np.random.default_rng(7)
+    U = rng.uniform(-0.1, 0.1, (T, nu)).astype(np.float32)
+    x = (rng.standard_normal((T, nu, K)) * 0.3).astype(np.float32)
+    cost = rng.uniform(0, 10, (T, K)).astype(np.float32)
+    cost[:, K // 3] = np.nan
+    partial = torch.zeros(2 + T * nu, device=DEV)
+    for _ in range(2):                                                     # twice: the barriers start from a clean phase every launch
+        be.reduce(dev(cost), dev(x), dev(U), partial)
+    torch.cuda.synchronize()
+    p_ref = oracle.reduce_mt(sc.model, p, cost, x, U, NTH)
+    pg = partial.cpu().numpy()
+    assert abs(pg[0] - p_ref[0]) <= 1e-5 * max(1, abs(p_ref[0]))
+    np.testing.assert_allclose(pg[1], p_ref[1], rtol=5e-5)
+    np.testing.assert_allclose(pg[2:], p_ref[2:], rtol=0, atol=5e-5 * max(1.0, np.abs(p_ref[2:]).max()))
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # regressions of the round-1 review (ADVICE.md)
 # ------------------------------------------------------------------------------------------------------------------
