@@ -26,7 +26,7 @@
 //
 // Scalar type F (lanes_math.cuh): float = one rollout per lane group; P2 = two rollouts per lane group with every arithmetic
 // instruction a packed FFMA2 / FMUL2 / FADD2 (1.4x the fp32 rate per issue slot, control / address instructions shared by the
-// pair).  The packed instantiation is used when K gives every scheduler at least two such warps.
+// pair); measured slower than the float instantiation on B200 and therefore opt-in (MPPIB_K2_PAIRS=1), see launch_rollout_lanes.
 #include "common.cuh"
 #include "lanes_math.cuh"
 
@@ -441,12 +441,11 @@ bool rollout_lanes_eligible(const MppibModel& m) {
 }
 
 int launch_rollout_lanes(MppibContext* c, const float* state0, float* state, const float* actions, int t0, int nsteps, float* obs, cudaStream_t s) {
-    // two rollouts per lane group (packed f32x2 arithmetic) once that still leaves every scheduler two warps; below that the kernel
-    // time is the latency of a single warp and the one-rollout instantiation has the shorter instruction stream
-    const int G = c->model.nb <= 4 ? 4 : 8;
-    const long long warps_packed = (long long)c->params.K / ((32 / G) * 2);
-    bool packed = warps_packed >= 2LL * 4 * c->num_sms;
-    if (c->k2_pairs >= 0) packed = c->k2_pairs != 0;
+    // One rollout per lane group by default.  The packed instantiation (two rollouts per group, FFMA2 / FMUL2 / FADD2) halves the
+    // arithmetic instruction count per rollout but measured SLOWER at every K on B200 (K = 10 000: 258 vs 218 us, K = 65 536: 1188 vs
+    // 1124 us, profiles/r2_rollout_lanes.md): register-pair moves, doubled address arithmetic and 168 registers with spills eat the
+    // gain.  It stays selectable (MPPIB_K2_PAIRS=1) for re-measurement.
+    bool packed = c->k2_pairs > 0;
     if (packed) return launch_lanes_f<lm::P2>(c, state0, state, actions, t0, nsteps, obs, s);
     return launch_lanes_f<float>(c, state0, state, actions, t0, nsteps, obs, s);
 }
