@@ -29,6 +29,24 @@ import torch
 from ..model.blob import MODE_SIMPLE
 
 
+class _NoRange:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NVTX_ON = os.environ.get("MPPIB_NVTX", "0") not in ("", "0")
+
+
+def _nvtx(name: str):
+    """NVTX range around a plan stage (MPPIB_NVTX=1): shows up in an Nsight timeline; off by default (no overhead)."""
+    if _NVTX_ON and torch.cuda.is_available():
+        return torch.cuda.nvtx.range(name)
+    return _NoRange()
+
+
 def _primes(n: int):
     out, c = [], 2
     while len(out) < n:
@@ -262,17 +280,21 @@ class MPPIPlanner:
 
     def _plan_batched(self):
         be = self.backend
-        be.shift(self.U, self.plan_ctr)
-        self._sample()
-        self.sim.rollout_all(self.actions)
-        cost = self._cost_batched()
+        with _nvtx("mppi/shift+K1 sample"):
+            be.shift(self.U, self.plan_ctr)
+            self._sample()
+        with _nvtx("mppi/K2 rollout"):
+            self.sim.rollout_all(self.actions)
+        with _nvtx("mppi/objective cost"):
+            cost = self._cost_batched()
         x = self.noise if be.params.mode == MODE_SIMPLE else self.actions
-        if self.world == 1 and hasattr(be, "reduce_finalize"):
-            be.reduce_finalize(cost, x, self.U, self.partial, self._action, self.stats)      # K3 + K4 in one launch
-            return
-        be.reduce(cost, x, self.U, self.partial)
-        partials, G = self._exchange()
-        be.finalize(partials, G, self.U, self._action, self.stats)
+        with _nvtx("mppi/K3 reduce + exchange + K4 update"):
+            if self.world == 1 and hasattr(be, "reduce_finalize"):
+                be.reduce_finalize(cost, x, self.U, self.partial, self._action, self.stats)      # K3 + K4 in one launch
+                return
+            be.reduce(cost, x, self.U, self.partial)
+            partials, G = self._exchange()
+            be.finalize(partials, G, self.U, self._action, self.stats)
 
     def _plan_stepwise(self, state):
         be, sim, T = self.backend, self.sim, self.T

@@ -5,6 +5,10 @@
 Objectives call (``examples/panda/planner.py:30-32``); pytorch3d is not installed here.  NOTE the reference
 feeds an *xyzw* quaternion into pytorch3d's *wxyz* API -- ``quaternion_to_matrix``
 keeps pytorch3d's real-first convention so that the literal arithmetic of those Objectives is reproduced.
+
+Provenance: ``quaternion_to_matrix``, ``_angle_from_tan`` and ``matrix_to_euler_angles`` follow the public formulas of
+pytorch3d's ``transforms/rotation_conversions.py`` (Meta Platforms, BSD licence) -- third-party code the reference depends on,
+not code of ``/root/reference``; they have to reproduce that library's numbers exactly, so their structure is the library's.
 """
 import torch
 

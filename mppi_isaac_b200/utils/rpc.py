@@ -73,6 +73,8 @@ class RpcServer:
         identity, blob = parts[:-2], parts[-1]
         try:
             header, name, args = _unpack(blob)
+            if not isinstance(header, dict) or not isinstance(name, str) or not isinstance(args, (list, tuple)):
+                return True                  # a malformed frame must not take the (single-threaded) server down: drop it
             request_id = header.get("response_to") or header["message_id"]
         except Exception:
             return True                      # not a zerorpc event: drop it

@@ -353,6 +353,15 @@ def test_rpc_server_client_speak_the_zerorpc_wire_format():
         assert raw.poll(5000)
         header, name, args = msgpack.unpackb(raw.recv_multipart()[-1], raw=False)
         assert name == "OK" and args == [None] and header["response_to"] == "m2" and "message_id" in header
+        # malformed events (a non-string method name, a header that is no map, args that are no list) are dropped, the server lives on
+        for bad in ([{"message_id": "m3", "v": 3}, 17, []], [["not", "a", "map"], "update_weights", []], [{"message_id": "m4", "v": 3}, "update_weights", 5],
+                    [{"message_id": "m5"}, None, None]):
+            raw.send_multipart([b"", msgpack.packb(bad, use_bin_type=True)])
+        raw.send_multipart([b"", b"\xc1 not msgpack"])
+        raw.send_multipart([b"", msgpack.packb([{"message_id": "m6", "v": 3}, "update_weights", [{"b": 2.0}]], use_bin_type=True)])
+        assert raw.poll(5000)
+        header, name, args = msgpack.unpackb(raw.recv_multipart()[-1], raw=False)
+        assert name == "OK" and header["response_to"] == "m6" and planner.weights == {"b": 2.0}
         raw.close()
         cli.close()
     finally:
