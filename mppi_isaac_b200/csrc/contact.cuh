@@ -104,7 +104,8 @@ __device__ __forceinline__ void init(const MppibModel& m, const MppibParams& p, 
         const int sb = L.sh0 + s * SHN;
         stx3(xs, sb + SH_HALF, lane, half);
         XS(sb + SH_MU) = mu;
-        XS(sb + SH_RAD) = sqrtf(dot(half, half));
+        // bounding radius; a sphere shape (isaacgym_utils.py:42-52: gym.create_sphere(radius = size[0])) keeps its radius in half.x
+        XS(sb + SH_RAD) = m.shape_type[s] == MPPIB_SHAPE_SPHERE ? half.x : sqrtf(dot(half, half));
     }
     for (int f = 0; f < m.nfree; ++f) {
         const int fb = L.fb0 + f * FBN;
@@ -253,16 +254,72 @@ __device__ __forceinline__ void points_in_box(const MppibModel& m, const Layout&
     }
 }
 
+// ONE contact of a sphere against a box (closest point of the box to the centre; centre inside the box: least-penetration face) or
+// against another sphere.  The normal of a contact pushes side A out of side B.  Same arithmetic as oracle.cpp sphere_contact.
+__device__ __forceinline__ void sphere_contact(const MppibModel& m, const Layout& L, float* xs, int lane, int& nc, int a, int b) {
+    const int sa = L.sh0 + a * SHN, sb = L.sh0 + b * SHN;
+    const float mu = 0.5f * (XS(sa + SH_MU) + XS(sb + SH_MU)), mg = m.contact_margin;
+    const int refa = shape_ref(m, a), refb = shape_ref(m, b), slota = m.shape_slot[a], slotb = m.shape_slot[b];
+    const V3 ca = ldx3(xs, sa + SH_C, lane), cbv = ldx3(xs, sb + SH_C, lane);
+    if (m.shape_type[a] == MPPIB_SHAPE_SPHERE && m.shape_type[b] == MPPIB_SHAPE_SPHERE) {
+        const V3 d = ca - cbv;
+        const float dist = sqrtf(dot(d, d)), ra = XS(sa + SH_HALF), rb = XS(sb + SH_HALF), rs = ra + rb;
+        if (!(dist < rs + mg) || !(dist > 0.f)) return;
+        const V3 n = (1.0f / dist) * d;
+        add_contact(m, L, xs, lane, nc, refa, refb, slota, slotb, cbv + rb * n, n, rs - dist, mu);
+        return;
+    }
+    const bool sphere_is_a = m.shape_type[a] == MPPIB_SHAPE_SPHERE;
+    const int ss = sphere_is_a ? sa : sb, sx = sphere_is_a ? sb : sa;
+    const float r = XS(ss + SH_HALF);
+    const V3 cs = sphere_is_a ? ca : cbv, cx = sphere_is_a ? cbv : ca;
+    const M3 Rx = ldxM3(xs, sx + SH_R, lane);
+    const V3 hx = ldx3(xs, sx + SH_HALF, lane);
+    const V3 x = mulT(Rx, cs - cx);
+    V3 q = mk(fminf(fmaxf(x.x, -hx.x), hx.x), fminf(fmaxf(x.y, -hx.y), hx.y), fminf(fmaxf(x.z, -hx.z), hx.z));
+    const V3 dd = x - q;
+    const float d2 = dot(dd, dd);
+    V3 nl = mk(0, 0, 0); float pen;
+    if (d2 > 0.f) {                                    // centre outside the box
+        const float dist = sqrtf(d2);
+        if (!(dist < r + mg)) return;
+        nl = (1.0f / dist) * dd;
+        pen = r - dist;
+    } else {                                           // centre inside: out through the nearest face
+        int ax = 0; float best = hx.x - fabsf(x.x);
+        const float p1 = hx.y - fabsf(x.y), p2 = hx.z - fabsf(x.z);
+        if (p1 < best) { best = p1; ax = 1; }
+        if (p2 < best) { best = p2; ax = 2; }
+        const float xa = ax == 0 ? x.x : (ax == 1 ? x.y : x.z);
+        const float sg = xa >= 0.f ? 1.f : -1.f;
+        if (ax == 0) { nl.x = sg; q.x = sg * hx.x; } else if (ax == 1) { nl.y = sg; q.y = sg * hx.y; } else { nl.z = sg; q.z = sg * hx.z; }
+        pen = best + r;
+    }
+    const V3 n = mul(Rx, nl);                          // from the box towards the sphere
+    const V3 pt = cx + mul(Rx, q);
+    if (sphere_is_a) add_contact(m, L, xs, lane, nc, refa, refb, slota, slotb, pt, n, pen, mu);
+    else add_contact(m, L, xs, lane, nc, refa, refb, slota, slotb, pt, mk(-n.x, -n.y, -n.z), pen, mu);
+}
+
+// contacts of the ordered pair (a, b): boxes by sample points in both directions, anything with a sphere analytically
+__device__ __forceinline__ void pair_contacts(const MppibModel& m, const Layout& L, float* xs, int lane, int& nc, int a, int b) {
+    if (m.shape_type[a] == MPPIB_SHAPE_SPHERE || m.shape_type[b] == MPPIB_SHAPE_SPHERE) { sphere_contact(m, L, xs, lane, nc, a, b); return; }
+    points_in_box(m, L, xs, lane, nc, a, b, false);
+    points_in_box(m, L, xs, lane, nc, b, a, true);
+}
+
 // broad phase: bounding spheres, then the 6 face axes of the two boxes (conservative: never rejects boxes closer than the margin).
 // Without it every articulation link "near" a large static box (table: 1.4 x 2.5 m) paid 52 point-in-box tests per substep.
 __device__ __forceinline__ bool near_shapes(const MppibModel& m, const Layout& L, const float* xs, int lane, int a, int b) {
     const int sa = L.sh0 + a * SHN, sb = L.sh0 + b * SHN;
     const V3 d = ldx3(xs, sa + SH_C, lane) - ldx3(xs, sb + SH_C, lane);
-    const float r = XS(sa + SH_RAD) + XS(sb + SH_RAD);
+    const float mg = m.contact_margin;
+    const bool sph = m.shape_type[a] == MPPIB_SHAPE_SPHERE || m.shape_type[b] == MPPIB_SHAPE_SPHERE;
+    const float r = XS(sa + SH_RAD) + XS(sb + SH_RAD) + (sph ? mg : 0.f);      // (a sphere's bound is exact: the margin counts)
     if (dot(d, d) > r * r) return false;
+    if (sph) return true;                                                       // the narrow phase is exact and cheap
     const M3 Ra = ldxM3(xs, sa + SH_R, lane), Rb = ldxM3(xs, sb + SH_R, lane);
     const V3 ha = ldx3(xs, sa + SH_HALF, lane), hb = ldx3(xs, sb + SH_HALF, lane);
-    const float mg = m.contact_margin;
     const V3 tb = mulT(Rb, d), ta = mulT(Ra, d);
     // C = Rb^T Ra, row i = (column i of Rb) . (columns of Ra)
     const V3 b0 = mk(Rb.m00, Rb.m10, Rb.m20), b1 = mk(Rb.m01, Rb.m11, Rb.m21), b2 = mk(Rb.m02, Rb.m12, Rb.m22);
@@ -328,16 +385,14 @@ __device__ __forceinline__ int detect(const MppibModel& m, const Layout& L, floa
             if (b == a || shape_ref(m, b) == shape_ref(m, a)) continue;
             if (m.shape_owner_kind[b] == MPPIB_OWNER_FREE && b < a) continue;
             if (!near_shapes(m, L, xs, lane, a, b)) continue;
-            points_in_box(m, L, xs, lane, nc, a, b, false);
-            points_in_box(m, L, xs, lane, nc, b, a, true);
+            pair_contacts(m, L, xs, lane, nc, a, b);
         }
     }
     for (int a = 0; a < ns; ++a) {   // articulation link vs static box
         if (m.shape_owner_kind[a] != MPPIB_OWNER_LINK || shape_ref(m, a) == REF_STATIC) continue;
         for (int b = 0; b < ns; ++b) {
             if (m.shape_owner_kind[b] != MPPIB_OWNER_STATIC || !near_shapes(m, L, xs, lane, a, b)) continue;
-            points_in_box(m, L, xs, lane, nc, a, b, false);
-            points_in_box(m, L, xs, lane, nc, b, a, true);
+            pair_contacts(m, L, xs, lane, nc, a, b);
         }
     }
     return nc;

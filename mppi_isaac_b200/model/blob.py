@@ -262,17 +262,24 @@ def build_scene(actor_cfgs: list, gravity=(0.0, 0.0, -9.8), assets_dirs=None, su
             continue
         if a.type not in ("box", "sphere"):
             raise NotImplementedError(f"actor asset of type {a.type} is not yet implemented!")      # isaacgym_utils.py:54-56
+        stype = SHAPE_BOX
         if a.type == "sphere":
-            # spheres collide through their bounding box, like every non-box robot collision geometry on this path;
-            # size[0] is the radius (isaacgym_utils.py:42-52).  Only FIXED spheres: the obstacles of compute_action(obst=...),
-            # whose pose is re-read from the root state at the start of every plan and held over the horizon.
+            # a true sphere primitive (gym.create_sphere(radius = size[0]), isaacgym_utils.py:42-52): one analytic contact against
+            # boxes / other spheres.  Only FIXED spheres: the obstacles of compute_action(obst=...), whose pose is re-read from the
+            # root state at the start of every plan; like every `fixed: True` actor of the reference (fix_base_link) they are static
+            # bodies -- the velocity columns of their root-state row are data for the Objective, not motion.
             if not a.fixed:
-                raise NotImplementedError(f"free sphere actor '{a.name}': only fixed sphere obstacles are supported (as bounding boxes)")
+                raise NotImplementedError(f"free sphere actor '{a.name}': only fixed sphere obstacles are supported")
             half = np.full(3, float(a.size[0]))
+            stype = SHAPE_SPHERE
         else:
             half = 0.5 * np.asarray(a.size, float)[:3]
-        sigma = np.asarray(a.noise_sigma_size if a.noise_sigma_size is not None else [0, 0, 0], float)[:3]
-        sh = dict(kind=OWNER_STATIC, owner=-1, actor=ai, half=half, pos=np.zeros(3), quat=np.array([0, 0, 0, 1.0]),
+        sigma = np.asarray(a.noise_sigma_size if a.noise_sigma_size is not None else [0, 0, 0], float).reshape(-1)
+        if stype == SHAPE_SPHERE:
+            sigma = np.full(3, 2.0 * float(sigma[0]) if sigma.size else 0.0)      # the noise acts on the RADIUS (half extents take sigma / 2)
+        else:
+            sigma = np.resize(sigma, 3) if sigma.size >= 3 else np.zeros(3)
+        sh = dict(stype=stype, kind=OWNER_STATIC, owner=-1, actor=ai, half=half, pos=np.zeros(3), quat=np.array([0, 0, 0, 1.0]),
                   friction=float(a.friction), fric_pct=float(a.noise_percentage_friction), sigma=sigma, body=body_offset[ai])
         if not a.fixed:
             if nfree >= MAX_FREE:
@@ -295,7 +302,7 @@ def build_scene(actor_cfgs: list, gravity=(0.0, 0.0, -9.8), assets_dirs=None, su
                 Rg, pg = np.asarray(col["R"], float), np.asarray(col["p"], float)
                 R_bl, p_bl = robot.link_R[l], robot.link_p[l]            # link frame in its owning body's frame
                 pos = p_bl + R_bl @ (pg + Rg @ cen)
-                shapes.append(dict(kind=OWNER_LINK, owner=int(robot.link_body[l]), actor=-1, half=half, pos=pos,
+                shapes.append(dict(stype=SHAPE_SPHERE if col["kind"] == "sphere" else SHAPE_BOX, kind=OWNER_LINK, owner=int(robot.link_body[l]), actor=-1, half=half, pos=pos,
                                    quat=R_to_quat_xyzw(R_bl @ Rg), friction=float(rcfg.friction), fric_pct=0.0, sigma=np.zeros(3),
                                    body=body_offset[ra] + l))
     if len(shapes) > MAX_SHAPES:
@@ -305,7 +312,7 @@ def build_scene(actor_cfgs: list, gravity=(0.0, 0.0, -9.8), assets_dirs=None, su
         if sh["body"] not in contact_slot and len(contact_slot) < MAX_SLOTS:
             contact_slot[sh["body"]] = len(contact_slot)
     for si, sh in enumerate(shapes):
-        m.shape_type[si], m.shape_owner_kind[si], m.shape_owner[si], m.shape_actor[si] = SHAPE_BOX, sh["kind"], sh["owner"], sh["actor"]
+        m.shape_type[si], m.shape_owner_kind[si], m.shape_owner[si], m.shape_actor[si] = sh["stype"], sh["kind"], sh["owner"], sh["actor"]
         m.shape_slot[si] = contact_slot.get(sh["body"], -1)
         _set(m.shape_half[si], sh["half"]); _set(m.shape_pos[si], sh["pos"]); _set(m.shape_quat[si], sh["quat"])
         m.shape_friction[si], m.shape_fric_pct[si] = sh["friction"], sh["fric_pct"]

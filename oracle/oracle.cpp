@@ -334,7 +334,7 @@ struct Articulation {
 enum { REF_STATIC = -1, REF_FREE0 = 64 };
 
 template <class S> struct FreeBody { S x[3], q[4], v[3], w[3], mass, half[3], Iinv[3]; M3<S> R, IinvW; };
-template <class S> struct ShapeW { M3<S> R; S c[3], half[3], mu, rad; int ref, slot, kind; };
+template <class S> struct ShapeW { M3<S> R; S c[3], half[3], mu, rad; int ref, slot, kind, type; };
 template <class S> struct Contact { int refA, refB, slotA, slotB, penalty; S p[3], n[3], d, mu, ln, lt1, lt2, t1[3], t2[3], kn, kt1, kt2; };
 
 template <class S> void mat_vec(const M3<S>& R, const S* v, S* o) { for (int r = 0; r < 3; ++r) o[r] = R.a[r][0] * v[0] + R.a[r][1] * v[1] + R.a[r][2] * v[2]; }
@@ -495,14 +495,63 @@ struct ContactWorld {
                 w.half[r] = shalf[s][r];
             }
             w.mu = smu[s];
-            w.rad = std::sqrt(w.half[0] * w.half[0] + w.half[1] * w.half[1] + w.half[2] * w.half[2]);
+            w.type = m->shape_type[s];
+            // bounding radius; a sphere shape (isaacgym_utils.py:42-52: gym.create_sphere(radius = size[0])) keeps its radius in half[0]
+            w.rad = w.type == MPPIB_SHAPE_SPHERE ? w.half[0] : std::sqrt(w.half[0] * w.half[0] + w.half[1] * w.half[1] + w.half[2] * w.half[2]);
         }
+    }
+    // ONE contact of a sphere against a box (closest point of the box to the centre; centre inside the box: least-penetration face)
+    // or against another sphere.  The normal of a contact pushes side A out of side B.
+    void sphere_contact(const ShapeW<S>& a, const ShapeW<S>& b, int penalty) {
+        const S mu = (S)0.5 * (a.mu + b.mu), mg = (S)m->contact_margin;
+        if (a.type == MPPIB_SHAPE_SPHERE && b.type == MPPIB_SHAPE_SPHERE) {
+            S d[3], d2 = 0; for (int i = 0; i < 3; ++i) { d[i] = a.c[i] - b.c[i]; d2 += d[i] * d[i]; }
+            const S dist = std::sqrt(d2), rs = a.half[0] + b.half[0];
+            if (!(dist < rs + mg) || !(dist > 0)) return;
+            S n[3], pt[3]; for (int i = 0; i < 3; ++i) { n[i] = d[i] / dist; pt[i] = b.c[i] + n[i] * b.half[0]; }
+            add_contact(a.ref, b.ref, a.slot, b.slot, pt, n, rs - dist, mu, penalty);
+            return;
+        }
+        const bool sphere_is_a = a.type == MPPIB_SHAPE_SPHERE;
+        const ShapeW<S>& sp = sphere_is_a ? a : b;
+        const ShapeW<S>& bx = sphere_is_a ? b : a;
+        const S r = sp.half[0];
+        S rel[3], x[3], q[3], d2 = 0;
+        for (int i = 0; i < 3; ++i) rel[i] = sp.c[i] - bx.c[i];
+        matT_vec(bx.R, rel, x);
+        for (int i = 0; i < 3; ++i) { q[i] = std::min(std::max(x[i], -bx.half[i]), bx.half[i]); d2 += (x[i] - q[i]) * (x[i] - q[i]); }
+        S nl[3] = {0, 0, 0}, pen;
+        if (d2 > 0) {                                  // centre outside the box
+            const S dist = std::sqrt(d2);
+            if (!(dist < r + mg)) return;
+            for (int i = 0; i < 3; ++i) nl[i] = (x[i] - q[i]) / dist;
+            pen = r - dist;
+        } else {                                       // centre inside: out through the nearest face
+            int ax = 0; S best = bx.half[0] - std::fabs(x[0]);
+            for (int i = 1; i < 3; ++i) { const S pi = bx.half[i] - std::fabs(x[i]); if (pi < best) { best = pi; ax = i; } }
+            nl[ax] = x[ax] >= 0 ? (S)1 : (S)-1;
+            q[ax] = nl[ax] * bx.half[ax];
+            pen = best + r;
+        }
+        S n[3], pl[3], pt[3];
+        mat_vec(bx.R, nl, n);                          // from the box towards the sphere
+        mat_vec(bx.R, q, pl); for (int i = 0; i < 3; ++i) pt[i] = bx.c[i] + pl[i];
+        if (sphere_is_a) add_contact(sp.ref, bx.ref, sp.slot, bx.slot, pt, n, pen, mu, penalty);
+        else { S nn[3] = {-n[0], -n[1], -n[2]}; add_contact(bx.ref, sp.ref, bx.slot, sp.slot, pt, nn, pen, mu, penalty); }
+    }
+    // contacts of the ordered pair (a, b): boxes by sample points in both directions, anything with a sphere analytically
+    void pair_contacts(const ShapeW<S>& a, const ShapeW<S>& b, int penalty) {
+        if (a.type == MPPIB_SHAPE_SPHERE || b.type == MPPIB_SHAPE_SPHERE) { sphere_contact(a, b, penalty); return; }
+        points_in_box(a, b, false, penalty);
+        points_in_box(b, a, true, penalty);
     }
     // broad phase: bounding spheres, then the 6 face axes of the two boxes (conservative: never rejects boxes closer than the margin)
     bool near(const ShapeW<S>& a, const ShapeW<S>& b) const {
         S d[3], d2 = 0; for (int i = 0; i < 3; ++i) { d[i] = a.c[i] - b.c[i]; d2 += d[i] * d[i]; }
-        const S r = a.rad + b.rad; if (d2 > r * r) return false;
         const S mg = (S)m->contact_margin;
+        const bool sph = a.type == MPPIB_SHAPE_SPHERE || b.type == MPPIB_SHAPE_SPHERE;
+        const S r = a.rad + b.rad + (sph ? mg : (S)0); if (d2 > r * r) return false;      // (a sphere's bound is exact: the margin counts)
+        if (sph) return true;                                                            // the narrow phase is exact and cheap
         S C[3][3];                                   // C = Rb^T Ra
         for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { S v = 0; for (int k = 0; k < 3; ++k) v += b.R.a[k][i] * a.R.a[k][j]; C[i][j] = v; }
         S tb[3], ta[3]; matT_vec(b.R, d, tb); matT_vec(a.R, d, ta);
@@ -531,16 +580,14 @@ struct ContactWorld {
                 if (b == a || sh[b].ref == sh[a].ref) continue;
                 if (sh[b].kind == MPPIB_OWNER_FREE && b < a) continue;       // free-free pairs once
                 if (!near(sh[a], sh[b])) continue;
-                points_in_box(sh[a], sh[b], false, 0);
-                points_in_box(sh[b], sh[a], true, 0);
+                pair_contacts(sh[a], sh[b], 0);
             }
         }
         for (int a = 0; a < ns; ++a) {                                        // articulation link vs static box
             if (sh[a].kind != MPPIB_OWNER_LINK || sh[a].ref == REF_STATIC) continue;
             for (int b = 0; b < ns; ++b) {
                 if (sh[b].kind != MPPIB_OWNER_STATIC || !near(sh[a], sh[b])) continue;
-                points_in_box(sh[a], sh[b], false, 1);
-                points_in_box(sh[b], sh[a], true, 1);
+                pair_contacts(sh[a], sh[b], 1);
             }
         }
     }

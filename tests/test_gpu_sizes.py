@@ -244,3 +244,28 @@ def test_c_abi_runs_on_the_handles_device_from_any_thread():
     assert "err" not in out, out.get("err")
     assert out["dev"] == 0
     torch.testing.assert_close(out["a"], ref, atol=1e-6, rtol=0)
+
+
+def test_sphere_obstacle_rollout_lockstep(oracle):
+    """True sphere primitives (the obstacles of compute_action(obst=...)): the robot's collision box against a fixed sphere, GPU
+    kernel against the oracle in lock-step while the point robot is driven into the sphere from several directions."""
+    from mppi_isaac_b200.model.blob import SHAPE_SPHERE, build_scene, make_params
+    from mppi_isaac_b200.utils.config_store import ActorWrapper, IsaacGymConfig, load_actor_cfgs
+    from scenes import point_mppi
+    from mppi_isaac_b200.model.blob import OBS_CONTACT, OBS_DOF_STATE, OBS_LINK_STATE
+    K, T = 256, 20
+    actors = load_actor_cfgs(["point_robot", "goal"]) + [ActorWrapper(type="sphere", name="sphere0", handle=None, size=[0.2], fixed=True, init_pos=[0.8, 0.8, 0.1])]
+    sc = build_scene(actors)
+    m = sc.model
+    assert SHAPE_SPHERE in [m.shape_type[s] for s in range(m.nshapes)]
+    obs = [(OBS_LINK_STATE, sc.robot.link_names.index("base_link")), (OBS_DOF_STATE, 0)] + [(OBS_CONTACT, s) for s in range(m.ncontact_slots)]
+    p = make_params(point_mppi(K, T), IsaacGymConfig(), sc.nu, K, obs)
+    rng = np.random.default_rng(8)
+    ang = rng.uniform(0.2, 1.37, K)                                        # headings that hit the sphere head-on, by a corner, or graze it
+    a = np.zeros((T, 3, K), np.float32)
+    a[:, 0] = 1.4 * np.cos(ang); a[:, 1] = 1.4 * np.sin(ang)
+    s0 = np.array([0.1, 0.1, 0.0, 0.0, 0.0, 0.0], np.float32)
+    wx, wv = _lockstep(oracle, sc, p, s0, [], a, T, K, range(T), tol_x=1e-4, tol_v=5e-3)
+    # the rollouts really reach the sphere: some of them are stopped short of where free motion would take them (0.1 + 1.4 cos * 1 s)
+    st, _ = oracle.rollout(sc.model, p, s0, a, root0=sc.root_state0, nthreads=NTH)
+    assert (np.hypot(st[0] - 0.1, st[1] - 0.1) < 1.0).mean() > 0.3

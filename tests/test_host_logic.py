@@ -451,3 +451,26 @@ def test_compute_action_with_sphere_obstacles():
     for _ in range(40):
         p.dynamics(None, u)
     assert float(s._dof_state[0, 0]) > 1.5
+
+
+def test_sphere_obstacle_is_a_sphere_not_its_bounding_box():
+    """compute_action(obst=...) obstacles are gym.create_sphere actors (isaacgym_utils.py:42-52): a robot approaching along the
+    diagonal is stopped when the CORNER of its collision box reaches the sphere (centre distance r), 5.9 cm later than the corner
+    of the sphere's bounding box would stop it.  Point robot (collision box half extent 0.2) driven along (1, 1) from (0.1, 0.1)
+    towards a sphere of radius 0.2 at (0.8, 0.8): it comes to rest at x = y = 0.8 - 0.2 / sqrt(2) - 0.2 = 0.4586."""
+    p = make(point_cfg(K=16, T=12), PointReachObjective(), observe="all")
+    obst = {"o0": {"position": [0.8, 0.8, 0.1], "velocity": [0.0, 0.0, 0.0], "size": [0.2]}}
+    p.compute_action([0.1, 0.1, 0.0], [0.0, 0.0, 0.0], obst=obst)
+    p.compute_action([0.1, 0.1, 0.0], [0.0, 0.0, 0.0], obst=obst)
+    from mppi_isaac_b200.model.blob import SHAPE_SPHERE
+    m = p.sim.scene.model
+    assert SHAPE_SPHERE in [m.shape_type[s] for s in range(m.nshapes)]
+    s = p.sim
+    s.reset_robot_state([0.1, 0.1, 0.0], [0.0, 0.0, 0.0])
+    s.begin_step_mode()
+    u = torch.zeros(16, 3); u[:, 0] = 1.0; u[:, 1] = 1.0
+    for _ in range(60):
+        p.dynamics(None, u)
+    x, y = float(s._dof_state[0, 0]), float(s._dof_state[0, 2])
+    assert abs(x - y) < 1e-2, (x, y)         # (the x joint carries the y body: slightly different contact compliance)
+    assert 0.445 < x < 0.475 and 0.445 < y < 0.475, (x, y)      # bounding-box contact would hold it at 0.40
