@@ -168,6 +168,11 @@ def build_scene(actor_cfgs: list, gravity=(0.0, 0.0, -9.8), assets_dirs=None, su
     if planar and not rcfg.differential_drive:
         raise NotImplementedError("floating-base robots are supported as differential-drive bases only (planar reduction)")
     robot = load_robot(rcfg.urdf_file, fixed=not planar, assets_dirs=assets_dirs)
+    if rcfg.differential_drive and not (rcfg.left_wheel_joints or rcfg.right_wheel_joints):
+        # the reference's jackal.yaml names no wheel joints although apply_robot_cmd needs them (isaacgym_wrapper.py:553-556): take the
+        # URDF's own naming (front_left_wheel, rear_right_wheel, ...)
+        rcfg.left_wheel_joints = [n for n in robot.dof_names if "wheel" in n and "left" in n]
+        rcfg.right_wheel_joints = [n for n in robot.dof_names if "wheel" in n and "right" in n]
     if planar != bool(robot.planar_base):
         raise ValueError(f"compiled model of {rcfg.urdf_file} does not match `fixed: {rcfg.fixed}`")
     if robot.nb > MAX_BODIES or robot.nlinks > MAX_LINKS:

@@ -534,11 +534,12 @@ def test_k2_drive_saturation_resolve_path(oracle, setup, K):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("actor,link,u_lim", [("albert", "mmrobot_link7", 0.4), ("omnipanda", "panda_hand", 0.3), ("panda_effort", "panda_link7", 8.0),
-                                               ("panda", "panda_link7", 0.2)])
+                                               ("panda", "panda_link7", 0.2), ("jackal", "ee_link", 1.0)])
 def test_k2_rollout_parity_further_robots(oracle, actor, link, u_lim):
     """the remaining robots of the reference's example set run through the same kernel and match the oracle --
     albert (differential-drive base reduced to the plane + 7-DoF arm, 12 bodies, tree), omnipanda (x / y / yaw base joints + arm +
-    gripper, 12 DOF), the panda in EFFORT mode (commands are torques, isaacgym_wrapper.py:492-496), the plain panda."""
+    gripper, 12 DOF), the panda in EFFORT mode (commands are torques, isaacgym_wrapper.py:492-496), the plain panda, jackal (four-wheel
+    differential drive, planar base)."""
     from scenes import robot_setup
     K, T = 256, 12
     sc, p, state0 = robot_setup(actor, link, K=K, T=T, u_lim=u_lim)

@@ -474,3 +474,35 @@ def test_sphere_obstacle_is_a_sphere_not_its_bounding_box():
     x, y = float(s._dof_state[0, 0]), float(s._dof_state[0, 2])
     assert abs(x - y) < 1e-2, (x, y)         # (the x joint carries the y body: slightly different contact compliance)
     assert 0.445 < x < 0.475 and 0.445 < y < 0.475, (x, y)      # bounding-box contact would hold it at 0.40
+
+
+def test_jackal_four_wheel_differential_drive():
+    """jackal (conf/actors/jackal.yaml: 4 wheels, r = 0.14, L = 0.4, no wheel-joint lists in the reference's file
+    -> inferred from the URDF joint names).  Command map of isaacgym_wrapper.py:510-522 on all four wheels, planar base follows
+    the commanded body twist: 1 s of v = 0.5 m/s advances the base by 0.5 m along its heading; omega turns it."""
+    from mppi_isaac_b200.model.blob import OBS_DOF_STATE, OBS_LINK_STATE, build_scene, make_params
+    from mppi_isaac_b200.utils.config_store import IsaacGymConfig, MPPIConfig, load_actor_cfgs
+    from oracle import oracle as orc
+    sc = build_scene(load_actor_cfgs(["jackal", "goal"]))
+    m = sc.model
+    assert m.nb == 7 and m.nu == 2 and m.planar_base == 1 and sc.virtual_dofs == 3
+    r, L = 0.14, 0.4
+    wheels = {n: i for i, n in enumerate(sc.robot.dof_names)}
+    for n, sign in (("front_left_wheel", -1), ("rear_left_wheel", -1), ("front_right_wheel", 1), ("rear_right_wheel", 1)):
+        i = wheels[n]
+        assert abs(m.cmd_c0[i] - 1 / r) < 1e-5 and abs(m.cmd_c1[i] - sign * L / (2 * r)) < 1e-5
+    K, T = 4, 20
+    mc = MPPIConfig(num_samples=K, horizon=T, mppi_mode="simple", sampling_method="random", noise_sigma=[[1.0, 0], [0, 1.0]],
+                    u_min=[-1.0, -2.0], u_max=[1.0, 2.0], lambda_=0.1)
+    p = make_params(mc, IsaacGymConfig(), sc.nu, K, [(OBS_LINK_STATE, 0), (OBS_DOF_STATE, 0)])
+    a = np.zeros((T, 2, K), np.float32)
+    a[:, 0, :] = 0.5
+    a[:, 1, 1] = 1.0                                                         # rollout 1 also turns
+    dof0 = sc.dof_state0
+    s0 = np.concatenate([dof0[0::2], dof0[1::2]]).astype(np.float32)
+    st, obs = orc.rollout(m, p, s0, a, root0=sc.root_state0)
+    fwd = np.array([m.fwd_axis[0], m.fwd_axis[1]])
+    adv = (st[0:2, 0] - s0[0:2]) @ fwd
+    assert abs(adv - 0.5) < 0.03 and abs(st[2, 0] - s0[2]) < 1e-3            # straight: 0.5 m in 1 s, no yaw
+    assert abs((st[2, 1] - s0[2]) - 1.0) < 0.06                              # omega = 1 rad/s for 1 s
+    assert abs(st[7 + wheels["front_left_wheel"], 0] - 0.5 / r) < 0.05      # wheel speed v / r

@@ -20,7 +20,8 @@ ROBOTS = [
     "panda_isaac/robots/franka_panda_gripper.urdf",
     "omni_panda/omniPandaWithGripper.urdf",
 ]
-FLOATING = ["boxer/boxer.urdf", "albert/albert.urdf"]          # differential-drive bases: compiled with the planar virtual-joint root
+FLOATING = ["boxer/boxer.urdf", "albert/albert.urdf", "jackal/jackal.urdf"]   # differential-drive bases: compiled with the planar virtual-joint root
+ROOT_MASS = {"jackal/jackal.urdf": 40.0}                              # ActorWrapper.mass of the actor file (conf/actors/jackal.yaml:8); default 1.0
 
 
 def main():
@@ -31,7 +32,7 @@ def main():
         save_compiled(model, out)
         print(f"{rel}: nb={model.nb} links={model.nlinks} -> {os.path.relpath(out)}")
     for rel in FLOATING:
-        model = compile_urdf(os.path.join(assets, "urdf", rel), fixed_base=False, root_mass_override=1.0)   # ActorWrapper.mass default
+        model = compile_urdf(os.path.join(assets, "urdf", rel), fixed_base=False, root_mass_override=ROOT_MASS.get(rel, 1.0))   # ActorWrapper.mass
         out = compiled_path(rel)
         save_compiled(model, out)
         print(f"{rel}: nb={model.nb} links={model.nlinks} planar base -> {os.path.relpath(out)}")
