@@ -141,13 +141,18 @@ def world_bytes(planner, q, qd, goal):
 
 
 class Clocks:
-    """SM clock and throttle reasons sampled IN PROCESS through NVML (what nvidia-smi reads) between the timed plans: the plans are
-    bracketed by CUDA events one by one, so a sample never sits inside a timed interval, and every rank takes the same samples (no
-    rank is slowed down relative to the others, which matters once the exchange is fused into the kernels)."""
+    """SM clock and throttle reasons DURING the timed region, sampled IN PROCESS through NVML (what nvidia-smi reads) by a background
+    thread on rank 0 only (every 25 ms; the NVML call releases the GIL).  Not from the timing loop itself: with the exchange fused into
+    the kernels every rank waits for the slowest one, and 8 ranks calling into the driver's NVML lock between plans produced
+    millisecond stragglers (profiles/r2_multigpu.md).  No nvidia-smi subprocess either (round-1 review)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake"}
 
-    def __init__(self, cuda_index):
-        self.ok, self.sm, self.mask, self.h = False, [], 0, None
+    def __init__(self, cuda_index, enabled=True, period_s=0.025):
+        self.ok, self.sm, self.mask, self.h, self.period = False, [], 0, None, period_s
+        self._stop, self._thread = threading.Event(), None
+        if not enabled:
+            self.err = "not sampled on this rank"
+            return
         try:
             import pynvml
             self.nv = pynvml
@@ -168,8 +173,6 @@ class Clocks:
             self.err = f"{type(e).__name__}: {e}"
 
     def sample(self):
-        if not self.ok:
-            return
         nv = self.nv
         self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
         try:
@@ -178,13 +181,32 @@ class Clocks:
         except Exception:  # noqa: BLE001
             pass
 
+    def start(self):
+        if not self.ok:
+            return
+
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self.sample()
+                except Exception:  # noqa: BLE001
+                    return
+                self._stop.wait(self.period)
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+
     def summary(self):
         if not self.ok:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"NVML unavailable ({getattr(self, 'err', '?')})"]}
         busy = sorted(self.sm)
         return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(n for bit, n in self.REASONS.items() if self.mask & bit), "samples": len(self.sm),
-                "how": "NVML in process, one sample after every timed plan (outside the CUDA-event brackets), all ranks alike"}
+                "how": f"NVML in process, background thread on rank 0, one sample per {int(self.period * 1e3)} ms while the timed plans run"}
 
 
 def measured_peak_gbs():
@@ -381,15 +403,23 @@ def timed_plans(planner, steps, warmup, flush, barrier, clocks=None):
         planner.mppi.command()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    import gc
+    gc.collect()
+    gc.disable()                     # a collection pause on one rank stalls every rank (they wait for its shard row)
+    if clocks is not None:
+        clocks.start()
     barrier()
-    for i in range(steps):
-        flush.zero_()
-        starts[i].record()
-        planner.mppi.command()
-        ends[i].record()
+    try:
+        for i in range(steps):
+            flush.zero_()
+            starts[i].record()
+            planner.mppi.command()
+            ends[i].record()
+        barrier()
+    finally:
+        gc.enable()
         if clocks is not None:
-            clocks.sample()          # host side, between two enqueued plans: not inside any event bracket
-    barrier()
+            clocks.stop()
     return [s.elapsed_time(e) for s, e in zip(starts, ends)]
 
 
@@ -424,7 +454,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     init_world(planner, name)
     nu = planner.mppi.nu
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
-    clocks = Clocks(local_rank)
+    clocks = Clocks(local_rank, enabled=(rank == 0))
 
     # ---- device-resident timing ------------------------------------------------------------------------------------
     per_step_ms = timed_plans(planner, args.steps, args.warmup, flush, barrier, clocks)
