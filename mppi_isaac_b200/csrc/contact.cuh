@@ -365,7 +365,26 @@ __device__ __forceinline__ void shapes_world(const MppibModel& m, const Layout& 
     }
 }
 
-__device__ __forceinline__ int detect(const MppibModel& m, const Layout& L, float* xs, int lane) {
+// Candidate partners of every shape as a bit mask (MPPIB_MAX_SHAPES <= 32), built once per CTA: a FREE shape is tested against every
+// shape of another body (free-free pairs once), a LINK shape against the STATIC ones.  The nested shape loops of detect() used to
+// re-derive this from the constant bank in every substep: 12 % of panda_pick's samples sat on those dependent constant loads
+// (profiles/r2_contact.md).
+__device__ __forceinline__ uint32_t partner_mask(const MppibModel& m, int a) {
+    const int ns = m.nshapes;
+    uint32_t mask = 0;
+    if (m.shape_owner_kind[a] == MPPIB_OWNER_FREE) {
+        for (int b = 0; b < ns; ++b) {
+            if (b == a || shape_ref(m, b) == shape_ref(m, a)) continue;
+            if (m.shape_owner_kind[b] == MPPIB_OWNER_FREE && b < a) continue;
+            mask |= 1u << b;
+        }
+    } else if (m.shape_owner_kind[a] == MPPIB_OWNER_LINK && shape_ref(m, a) != REF_STATIC) {
+        for (int b = 0; b < ns; ++b) if (m.shape_owner_kind[b] == MPPIB_OWNER_STATIC) mask |= 1u << b;
+    }
+    return mask;
+}
+
+__device__ __forceinline__ int detect(const MppibModel& m, const Layout& L, float* xs, int lane, const uint32_t* __restrict__ bmask) {
     int nc = 0;
     const int ns = m.nshapes;
     for (int a = 0; a < ns; ++a) {
@@ -381,17 +400,17 @@ __device__ __forceinline__ int detect(const MppibModel& m, const Layout& L, floa
                 if (pt.z < m.ground_margin) add_contact(m, L, xs, lane, nc, shape_ref(m, a), REF_STATIC, m.shape_slot[a], -1, pt, mk(0, 0, 1), -pt.z, mu);
             }
         }
-        for (int b = 0; b < ns; ++b) {
-            if (b == a || shape_ref(m, b) == shape_ref(m, a)) continue;
-            if (m.shape_owner_kind[b] == MPPIB_OWNER_FREE && b < a) continue;
+        for (uint32_t mask = bmask[a]; mask; mask &= mask - 1) {          // partners in ascending order, as the oracle's loop visits them
+            const int b = __ffs(mask) - 1;
             if (!near_shapes(m, L, xs, lane, a, b)) continue;
             pair_contacts(m, L, xs, lane, nc, a, b);
         }
     }
-    for (int a = 0; a < ns; ++a) {   // articulation link vs static box
-        if (m.shape_owner_kind[a] != MPPIB_OWNER_LINK || shape_ref(m, a) == REF_STATIC) continue;
-        for (int b = 0; b < ns; ++b) {
-            if (m.shape_owner_kind[b] != MPPIB_OWNER_STATIC || !near_shapes(m, L, xs, lane, a, b)) continue;
+    for (int a = 0; a < ns; ++a) {   // articulation link vs static shape
+        if (m.shape_owner_kind[a] != MPPIB_OWNER_LINK) continue;
+        for (uint32_t mask = bmask[a]; mask; mask &= mask - 1) {
+            const int b = __ffs(mask) - 1;
+            if (!near_shapes(m, L, xs, lane, a, b)) continue;
             pair_contacts(m, L, xs, lane, nc, a, b);
         }
     }

@@ -227,6 +227,11 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
     const int K = p.K, T = p.T, nu = m.nu, nb = m.nb;
     const int lane = threadIdx.x;
     const int k = blockIdx.x * 32 + lane;
+    __shared__ uint32_t s_bmask[MPPIB_MAX_SHAPES];        // candidate partners of every shape (contact::partner_mask), one table per CTA,
+    if (CONTACT) {                                        // filled by all 32 lanes before the lanes of a ragged last CTA leave
+        for (int s = lane; s < m.nshapes; s += 32) s_bmask[s] = contact::partner_mask(m, s);
+        __syncwarp();
+    }
     if (k >= K) return;
     const float h = p.dt / (float)p.substeps;
     const bool vel_mode = m.drive_mode == MPPIB_DRIVE_VELOCITY;
@@ -501,7 +506,7 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
                 // ------------------------------------------------------------------ contacts on the predicted velocities
                 for (int i = 0; i < nb; ++i) { xs[(L.jv0 + 2 * nb + i) * 32 + lane] = SM(i, F_QD) + h * SM(i, F_QDD); xs[(L.jv0 + i) * 32 + lane] = 0.f; }
                 contact::shapes_world<NSLOT>(m, L, sm, xs, lane, base.R, base.o, root0, false);
-                const int nc = contact::detect(m, L, xs, lane);
+                const int nc = contact::detect(m, L, xs, lane, s_bmask);
                 for (int f = 0; f < m.nfree; ++f) if (m.free_gravity[f]) {
                     const int fb = L.fb0 + f * contact::FBN;
                     xs[(fb + contact::FB_V) * 32 + lane] += h * m.gravity[0]; xs[(fb + contact::FB_V + 1) * 32 + lane] += h * m.gravity[1];
