@@ -142,12 +142,12 @@ def world_bytes(planner, q, qd, goal):
 
 class Clocks:
     """SM clock and throttle reasons DURING the timed region, sampled IN PROCESS through NVML (what nvidia-smi reads) by a background
-    thread on rank 0 only (every 25 ms; the NVML call releases the GIL).  Not from the timing loop itself: with the exchange fused into
+    thread on rank 0 only (every 2 ms; the NVML call releases the GIL).  Not from the timing loop itself: with the exchange fused into
     the kernels every rank waits for the slowest one, and 8 ranks calling into the driver's NVML lock between plans produced
     millisecond stragglers (profiles/r2_multigpu.md).  No nvidia-smi subprocess either (round-1 review)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake"}
 
-    def __init__(self, cuda_index, enabled=True, period_s=0.025):
+    def __init__(self, cuda_index, enabled=True, period_s=0.002):
         self.ok, self.sm, self.mask, self.h, self.period = False, [], 0, None, period_s
         self._stop, self._thread = threading.Event(), None
         if not enabled:
