@@ -601,10 +601,10 @@ def run_gpu_arm(args, rank, world, local_rank):
             ks = sorted({planner.sim.num_envs, 65536, 262144})
             roof = k3_roofline(planner, peak, ks)
             head = next(r for r in roof if r["K"] == planner.sim.num_envs)
-            traffic = {(10000, 30, 7): 9635000}.get((head["K"], T, nu))
+            traffic = {(10000, 30, 7): 9666560}.get((head["K"], T, nu))
             line["roofline"] = {"kernel": "K3 reduce_kernel (fused cost accumulate + softmax + weighted control sum)", "bound": "hbm",
                                 "achieved": head["GBps"], "peak": peak, "unit": "GB/s", "frac": head["frac"], "traffic": traffic,
-                                "traffic_source": "ncu --set full dram__bytes_read.sum + write of one K3 launch at this K (profiles/): 1.004 x algorithmic" if traffic else None,
+                                "traffic_source": "ncu --set full dram__bytes_read.sum + write of one K3 launch at this K (profiles/r2_ncu_summaries.txt): 1.007 x algorithmic; 1.0003 x at K = 262 144" if traffic else None,
                                 "peak_source": peak_src, "bytes_per_launch": head["bytes"], "us_per_launch": head["us"], "K": head["K"],
                                 "note": "the named K is launch/latency bound (9.6 MB = 1.5 us of HBM time at C2*); the sweep shows the asymptote",
                                 "sweep": roof}
