@@ -454,7 +454,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     init_world(planner, name)
     nu = planner.mppi.nu
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
-    clocks = Clocks(local_rank, enabled=(rank == 0))
+    clocks = Clocks(local_rank, enabled=(rank == 0 and os.environ.get("BENCH_NO_CLOCKS", "0") in ("", "0")))
 
     # ---- device-resident timing ------------------------------------------------------------------------------------
     per_step_ms = timed_plans(planner, args.steps, args.warmup, flush, barrier, clocks)
@@ -571,7 +571,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                            "exchange": "none" if world == 1 else ("peer-memory stores fused into K3 (NVLink), flags acquired by K4" if planner.mppi._peer_exchange else "NCCL all-gather"),
                            "cuda_graph": graph_on, "l2": "flushed (256 MiB write) before every timed plan",
                            "k2_mapping": "lanes-per-rollout (rollout_lanes.cu)" if os.environ.get("MPPIB_K2_LANES", "1") != "0" and name == "c2" else "thread-per-rollout (rollout.cu)",
-                           "ms_per_step_p10_p50_p90_max": [float(np.percentile(per_step_ms, p)) for p in (10, 50, 90, 100)]},
+                           "ms_per_step_p10_p50_p90_max": [float(np.percentile(per_step_ms, p)) for p in (10, 50, 90, 100)],
+                           "slowest_steps": sorted(range(len(per_step_ms)), key=lambda i: -per_step_ms[i])[:3]},
             "e2e": e2e,
             "gpu_launches": (launches_per_plan * args.steps) if n_obj else None,
             "clocks": clocks.summary(),
