@@ -524,6 +524,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     correctness = None
     if world > 1:
         def one_plan(pl):
+            pl.sim.reset_to_initial_poses()      # the e2e loops above left their last message (a shifted goal) in the timed planner's world
             init_world(pl, name)
             pl.mppi.U.zero_(); pl.mppi.plan_ctr.zero_()
             pl.mppi.command()
