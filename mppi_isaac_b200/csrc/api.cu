@@ -92,6 +92,8 @@ int32_t mppib_create(const MppibModel* model_h, const MppibParams* params_h, int
     c->num_sms = prop.multiProcessorCount;
     c->k2_lanes = 1;
     if (const char* e = getenv("MPPIB_K2_LANES")) c->k2_lanes = atoi(e) != 0;   // read once per handle, not per launch
+    c->k2_team = 0;
+    if (const char* e = getenv("MPPIB_K2_TEAM")) c->k2_team = atoi(e) != 0;
     c->k2_pairs = -1;
     if (const char* e = getenv("MPPIB_K2_PAIRS")) c->k2_pairs = atoi(e) != 0;
     c->k3_variant = (getenv("MPPIB_K3_VARIANT") || getenv("MPPIB_K3_WIDE") || getenv("MPPIB_K3_GRID")) ? 1 : 0;

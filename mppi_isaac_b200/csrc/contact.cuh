@@ -21,6 +21,9 @@ enum : int { FB_X = 0, FB_Q = 3, FB_V = 7, FB_W = 10, FB_MASS = 13, FB_HALF = 14
 enum : int { SH_R = 0, SH_C = 9, SH_HALF = 12, SH_MU = 15, SH_RAD = 16, SHN = 17 };
 // contact slots
 // CT_KN / CT_KT1 / CT_KT2 hold INVERSES: 1 / (k_n + gamma), 1 / k_t1, 1 / k_t2 (0 = row disabled); CT_T1 caches the first tangent
+// a contact row whose effective inverse mass is below K_ROW_MIN [1/kg] is dropped (bodies that cannot move along that direction; same
+// threshold in oracle.cpp -- an exact `> 0` would depend on the rotation arithmetic producing exact zeros)
+constexpr float K_ROW_MIN = 1e-9f;
 enum : int { CT_P = 0, CT_N = 3, CT_D = 6, CT_MU = 7, CT_LN = 8, CT_LT1 = 9, CT_LT2 = 10, CT_IDS = 11, CT_KN = 12, CT_KT1 = 13, CT_KT2 = 14, CT_T1 = 15, CTN = 18 };
 
 struct Layout {
@@ -434,9 +437,9 @@ __device__ __forceinline__ void solve(const MppibModel& m, const Layout& L, cons
         const float kn = inv_mass<NSLOT, CHAIN>(m, L, sm, xs, lane, refA, refB, pt, n);
         const float kt1 = inv_mass<NSLOT, CHAIN>(m, L, sm, xs, lane, refA, refB, pt, t1);
         const float kt2 = inv_mass<NSLOT, CHAIN>(m, L, sm, xs, lane, refA, refB, pt, t2);
-        XS(cb + CT_KN) = kn > 0.f ? 1.0f / (kn + gamma) : 0.f;
-        XS(cb + CT_KT1) = kt1 > 0.f ? 1.0f / kt1 : 0.f;
-        XS(cb + CT_KT2) = kt2 > 0.f ? 1.0f / kt2 : 0.f;
+        XS(cb + CT_KN) = kn > K_ROW_MIN ? 1.0f / (kn + gamma) : 0.f;
+        XS(cb + CT_KT1) = kt1 > K_ROW_MIN ? 1.0f / kt1 : 0.f;
+        XS(cb + CT_KT2) = kt2 > K_ROW_MIN ? 1.0f / kt2 : 0.f;
         stx3(xs, cb + CT_T1, lane, t1);
         const float d = XS(cb + CT_D);
         XS(cb + CT_D) = d > 0.f ? fminf(beta * d * ih, m.max_depen) : d * ih;      // from here on: the bias velocity

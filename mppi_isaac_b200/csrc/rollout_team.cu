@@ -1,0 +1,968 @@
+// rollout_team.cu -- K2 for TREES and for every scene WITH CONTACTS: a TEAM of G lanes per rollout (one articulation body per
+// lane; the same lanes become sample points, shape pairs and joints of a contact's chain in the contact phase).  Replaces
+// gym.simulate() / IsaacGymWrapper.step on the MPPI path (mppiisaac/planner/isaacgym_wrapper.py:524-572, :639-655) for the scenes
+// rollout_lanes.cu does not cover: panda + gripper, omnipanda, the planar differential-drive bases (boxer, albert, jackal), and
+// BASELINE C3 / C4 / C5 (boxer_push, heijn_push, panda_pick).  Same spec as rollout.cu + contact.cuh (the thread-per-rollout kernel,
+// kept as the A/B reference: MPPIB_K2_TEAM=0) and as oracle/oracle.cpp; tested against the same oracle.
+//
+// Why.  The thread-per-rollout contact kernels are ONE warp per SM walking a data-dependent stream of 23 - 32 k instructions per
+// (sub)step at CPI 3.7 (profiles/r2_contact.md): at the BASELINE shard sizes every CTA is resident at once, so their time is the
+// latency of a single warp, and 98 % of the machine idles.  A team shortens that stream: the articulation is the composite-rigid-body /
+// joint-space LDL^T formulation of rollout_lanes.cu generalised to trees (ancestor sums by pointer jumping, subtree sums as
+// differences of suffix sums in depth-first order), the 26 sample points of a box pair are tested by the lanes in parallel (appended
+// in the oracle's order by ballot + prefix popcount), and a Gauss-Seidel visit is three dot products per lane -- the lane's own
+// joint against the contact frame -- plus one butterfly all-reduce instead of three walks along the kinematic chain.
+//
+// Per-rollout data that several lanes need lives in shared memory, one contiguous block per rollout ([slot], not interleaved):
+// free bodies, world shapes, contacts, net forces -- ~0.7 k floats for panda_pick (the thread kernel: 1.6 k slots x 32 lanes per CTA).
+// Per-body data (q, qd, frame, motion subspace, 1 / D_j, velocity correction) stays in the registers of the body's lane.
+#include "common.cuh"
+#include "lanes_math.cuh"
+
+namespace {
+
+using namespace lm;
+typedef V3T<float> V3;
+typedef M3T<float> M3;
+typedef S3T<float> S3;
+typedef QT<float> Quat;
+typedef V6T<float> V6;
+
+__device__ __forceinline__ V3 mk(float x, float y, float z) { return mk3<float>(x, y, z); }
+__device__ __forceinline__ float dot6(const V6& a, const V6& b) { return dot(a.n, b.n) + dot(a.f, b.f); }
+__device__ __forceinline__ V3 mulM(const M3& m, V3 v) { return mulc(m, v.x, v.y, v.z); }
+__device__ __forceinline__ V3 mulMT(const M3& m, V3 v) {
+    return mk(m.m00 * v.x + m.m10 * v.y + m.m20 * v.z, m.m01 * v.x + m.m11 * v.y + m.m21 * v.z, m.m02 * v.x + m.m12 * v.y + m.m22 * v.z);
+}
+__device__ __forceinline__ M3 mulMM(const M3& a, const M3& b) {
+    M3 o;
+    o.m00 = a.m00 * b.m00 + a.m01 * b.m10 + a.m02 * b.m20; o.m01 = a.m00 * b.m01 + a.m01 * b.m11 + a.m02 * b.m21; o.m02 = a.m00 * b.m02 + a.m01 * b.m12 + a.m02 * b.m22;
+    o.m10 = a.m10 * b.m00 + a.m11 * b.m10 + a.m12 * b.m20; o.m11 = a.m10 * b.m01 + a.m11 * b.m11 + a.m12 * b.m21; o.m12 = a.m10 * b.m02 + a.m11 * b.m12 + a.m12 * b.m22;
+    o.m20 = a.m20 * b.m00 + a.m21 * b.m10 + a.m22 * b.m20; o.m21 = a.m20 * b.m01 + a.m21 * b.m11 + a.m22 * b.m21; o.m22 = a.m20 * b.m02 + a.m21 * b.m12 + a.m22 * b.m22;
+    return o;
+}
+
+// ---- shared-memory layout of ONE rollout (floats; same field order as contact.cuh so the two kernels can be read side by side)
+enum : int { REF_STATIC = -1, REF_FREE0 = 64 };
+enum : int { FB_X = 0, FB_Q = 3, FB_V = 7, FB_W = 10, FB_MASS = 13, FB_HALF = 14, FB_IINV = 17, FB_R = 20, FB_IW = 29, FBN = 35 };   // FB_MASS: inverse mass
+enum : int { SH_R = 0, SH_C = 9, SH_HALF = 12, SH_MU = 15, SH_RAD = 16, SHN = 17 };
+enum : int { CT_P = 0, CT_N = 3, CT_D = 6, CT_MU = 7, CT_LN = 8, CT_LT1 = 9, CT_LT2 = 10, CT_IDS = 11, CT_KN = 12, CT_KT1 = 13, CT_KT2 = 14, CT_T1 = 15, CTN = 18 };
+constexpr float K_ROW_MIN = 1e-9f;     // contact rows with a smaller effective inverse mass [1/kg] are dropped (contact.cuh, oracle.cpp)
+struct TLayout {
+    int fb0, sh0, ct0, net0, total;
+    __host__ __device__ TLayout(int nfree, int nshapes, int max_contacts) {
+        fb0 = 0; sh0 = fb0 + nfree * FBN; ct0 = sh0 + nshapes * SHN; net0 = ct0 + max_contacts * CTN; total = net0 + 3 * MPPIB_MAX_SLOTS;
+    }
+};
+__host__ __device__ inline int team_stride(int total, int G) { return ((total + 31) & ~31) + G; }   // stride % 32 == G: the teams of a warp start G banks apart
+
+__device__ __forceinline__ V3 ld3(const float* xs, int b) { return mk(xs[b], xs[b + 1], xs[b + 2]); }
+__device__ __forceinline__ void st3(float* xs, int b, V3 v) { xs[b] = v.x; xs[b + 1] = v.y; xs[b + 2] = v.z; }
+__device__ __forceinline__ M3 ldM3(const float* xs, int b) {
+    M3 m; m.m00 = xs[b]; m.m01 = xs[b + 1]; m.m02 = xs[b + 2]; m.m10 = xs[b + 3]; m.m11 = xs[b + 4]; m.m12 = xs[b + 5]; m.m20 = xs[b + 6]; m.m21 = xs[b + 7]; m.m22 = xs[b + 8]; return m;
+}
+__device__ __forceinline__ void stM3(float* xs, int b, const M3& m) {
+    xs[b] = m.m00; xs[b + 1] = m.m01; xs[b + 2] = m.m02; xs[b + 3] = m.m10; xs[b + 4] = m.m11; xs[b + 5] = m.m12; xs[b + 6] = m.m20; xs[b + 7] = m.m21; xs[b + 8] = m.m22;
+}
+
+// ---- Philox-keyed per-rollout randomisation: the same counters as contact.cuh / oracle actor_noise
+__device__ __forceinline__ uint4 philox(uint4 c, uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll 1
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x, hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+        k0 += W0; k1 += W1;
+    }
+    return c;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+    const float r = sqrtf(-2.0f * logf(u01(a)));
+    float s, c; sincospif(2.0f * u01(b), &s, &c);
+    z0 = r * c; z1 = r * s;
+}
+__device__ __forceinline__ void actor_noise(const MppibParams& p, uint32_t kg, int actor, V3& nsize, float& umass, float& ufric) {
+    const uint4 r0 = philox(make_uint4(kg, (uint32_t)actor, 0x5EEDu, 0u), p.rand_seed, 0x4D505049u);
+    const uint4 r1 = philox(make_uint4(kg, (uint32_t)actor, 0x5EEDu, 1u), p.rand_seed, 0x4D505049u);
+    float dummy;
+    box_muller(r0.x, r0.y, nsize.x, nsize.y);
+    box_muller(r0.z, r0.w, nsize.z, dummy);
+    umass = 2.0f * u01(r1.x) - 1.0f;
+    ufric = 2.0f * u01(r1.y) - 1.0f;
+}
+
+__device__ __forceinline__ int shape_ref(const MppibModel& m, int s) {
+    const int kind = m.shape_owner_kind[s];
+    if (kind == MPPIB_OWNER_FREE) return REF_FREE0 + m.shape_owner[s];
+    if (kind == MPPIB_OWNER_LINK && m.shape_owner[s] >= 0) return m.shape_owner[s];
+    return REF_STATIC;
+}
+// candidate partners of shape a (contact.cuh partner_mask)
+__device__ __forceinline__ uint32_t partner_mask(const MppibModel& m, int a) {
+    const int ns = m.nshapes;
+    uint32_t mask = 0;
+    if (m.shape_owner_kind[a] == MPPIB_OWNER_FREE) {
+        for (int b = 0; b < ns; ++b) {
+            if (b == a || shape_ref(m, b) == shape_ref(m, a)) continue;
+            if (m.shape_owner_kind[b] == MPPIB_OWNER_FREE && b < a) continue;
+            mask |= 1u << b;
+        }
+    } else if (m.shape_owner_kind[a] == MPPIB_OWNER_LINK && shape_ref(m, a) != REF_STATIC) {
+        for (int b = 0; b < ns; ++b) if (m.shape_owner_kind[b] == MPPIB_OWNER_STATIC) mask |= 1u << b;
+    }
+    return mask;
+}
+
+// team-wide helpers: G lanes, lane-in-team i, `tb` = first lane of the team in the warp
+// (the contact phase runs team-divergent loops -- the teams of a warp see different numbers of contacts -- so every shuffle / ballot /
+// barrier in it names only the lanes of the team: `tm`)
+template <int G> __device__ __forceinline__ float team_sum(float v, uint32_t tm) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(tm, v, o, G);
+    return v;
+}
+template <int G> __device__ __forceinline__ uint32_t team_ballot(bool pred, uint32_t tm, int tb) { return __ballot_sync(tm, pred) >> tb; }
+
+struct BodyConst {
+    float tqx, tqy, tqz, tqw, tpx, tpy, tpz, tax, tay, taz, jrev;
+    float mass, cx, cy, cz;
+    S3 Ic;
+    float q_lo, q_hi, qd_max, effort, damp, kd, dimp_drive, dimp_sat;
+};
+
+struct Kin { Quat qw; V3 o; M3 R; V6 S, Vl, V; };
+
+// per-lane tree tables
+template <int R> struct Tree {
+    int jump[R];        // ancestor at distance 2^r (lane in team), -1 none
+    uint32_t anc;       // bit j set: body j is this body or an ancestor of it
+    uint32_t desc;      // bit j set: body j is this body or a descendant
+    int end;            // first body after this body's subtree (depth-first numbering: the subtree is [i, end))
+};
+
+template <int G, int R>
+__device__ __forceinline__ void anc_add(float& x, const Tree<R>& tr) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) { const float t = shfl_at<G>(x, tr.jump[r] >= 0 ? tr.jump[r] : 0); if (tr.jump[r] >= 0) x += t; }
+}
+template <int G, int R> __device__ __forceinline__ void anc_add3(V3& v, const Tree<R>& tr) { anc_add<G, R>(v.x, tr); anc_add<G, R>(v.y, tr); anc_add<G, R>(v.z, tr); }
+// sum over the subtree = suffix sum over the depth-first order minus the suffix sum at the subtree's end
+template <int G, int R>
+__device__ __forceinline__ void subtree_add(float& x, int i, const Tree<R>& tr) {
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) { const float t = shfl_dn<G>(x, d); if (i + d < G) x += t; }
+    const float e = shfl_at<G>(x, tr.end < G ? tr.end : 0);
+    if (tr.end < G) x -= e;
+}
+template <int G, int R> __device__ __forceinline__ void subtree_add3(V3& v, int i, const Tree<R>& tr) { subtree_add<G, R>(v.x, i, tr); subtree_add<G, R>(v.y, i, tr); subtree_add<G, R>(v.z, i, tr); }
+
+template <int G, int R>
+__device__ __forceinline__ void kinematics(const BodyConst& bc, const Tree<R>& tr, float q, float qd, Kin& kn) {
+    float sh, ch;
+    sincos_cw(q * (0.5f * bc.jrev), &sh, &ch);
+    Quat ql;
+    ql.x = fmaf(ch, bc.tqx, sh * bc.tqy);
+    ql.y = fmaf(ch, bc.tqy, sh * (-bc.tqx));
+    ql.z = fmaf(ch, bc.tqz, sh * bc.tqw);
+    ql.w = fmaf(ch, bc.tqw, sh * (-bc.tqz));
+    V3 pl = mk(fmaf(q, bc.tax, bc.tpx), fmaf(q, bc.tay, bc.tpy), fmaf(q, bc.taz, bc.tpz));
+    // world frame = product of the local transforms along the path from the root: pointer jumping over the ancestors
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int src = tr.jump[r] >= 0 ? tr.jump[r] : 0;
+        Quat qp; V3 pp;
+        qp.x = shfl_at<G>(ql.x, src); qp.y = shfl_at<G>(ql.y, src); qp.z = shfl_at<G>(ql.z, src); qp.w = shfl_at<G>(ql.w, src);
+        pp.x = shfl_at<G>(pl.x, src); pp.y = shfl_at<G>(pl.y, src); pp.z = shfl_at<G>(pl.z, src);
+        if (tr.jump[r] >= 0) {
+            pl = qrot_add(pp, qp, pl);
+            ql = qmul(qp, ql);
+        }
+    }
+    kn.qw = ql; kn.o = pl;
+    kn.R = quat_to_R(ql);
+    const V3 axis = mk(kn.R.m02, kn.R.m12, kn.R.m22);
+    const bool rev = bc.jrev != 0.f;
+    const V3 oxa = cross(pl, axis);
+    kn.S.n = rev ? axis : mk(0.f, 0.f, 0.f);
+    kn.S.f = rev ? oxa : axis;
+    kn.Vl.n = scale(qd, kn.S.n); kn.Vl.f = scale(qd, kn.S.f);
+    kn.V = kn.Vl;
+    anc_add3<G, R>(kn.V.n, tr); anc_add3<G, R>(kn.V.f, tr);
+}
+
+// G lanes per rollout, NB >= nb joint-space rows (compile time), CONTACT: free bodies / collision shapes present
+template <int G, int NB, bool CONTACT>
+__global__ void __launch_bounds__(32)
+mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_constant__ MppibParams p,
+                          const float* __restrict__ state0, const float* __restrict__ root0, float* __restrict__ state,
+                          const float* __restrict__ actions, int t0, int nsteps, float* __restrict__ obs) {
+    constexpr int RPW = 32 / G;
+    constexpr int R = (G == 16) ? 4 : ((G == 8) ? 3 : 2);        // rounds of pointer jumping: depth < 2^R
+    extern __shared__ float sm_all[];
+    __shared__ uint32_t s_bmask[MPPIB_MAX_SHAPES];               // candidate partners of every shape
+    __shared__ uint32_t s_anc[MPPIB_MAX_BODIES];                 // ancestor-or-self mask of every body (the chain of a contact's link)
+    const int K = p.K, T = p.T, nu = m.nu, nb = m.nb;
+    const int lane = threadIdx.x & 31;
+    const int i = lane & (G - 1);
+    const int team = lane / G, tb = team * G;
+    const uint32_t tm = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << tb;      // the lanes of this team
+    const int k_first = (int)blockIdx.x * RPW;
+    if (k_first >= K) return;
+    int k = k_first + team;
+    const bool kval = k < K;
+    if (!kval) k = K - 1;
+    const bool bval = i < nb;
+    const int ib = bval ? i : 0;
+    const float h = p.dt / (float)p.substeps;
+    const bool vel_mode = m.drive_mode == MPPIB_DRIVE_VELOCITY;
+    const TLayout L(m.nfree, m.nshapes, m.max_contacts);
+    float* xs = sm_all + (size_t)team * team_stride(L.total, G);
+
+    // ---- tree tables
+    Tree<R> tr;
+    {
+        const int par = bval ? m.parent[ib] : -1;
+        tr.jump[0] = par;
+#pragma unroll
+        for (int r = 1; r < R; ++r) {
+            const int up = __shfl_sync(FULL, tr.jump[r - 1], tr.jump[r - 1] >= 0 ? tr.jump[r - 1] : 0, G);
+            tr.jump[r] = tr.jump[r - 1] >= 0 ? up : -1;
+        }
+        uint32_t anc = bval ? (1u << i) : 0u;
+#pragma unroll
+        for (int r = 0; r < R; ++r) { const uint32_t t = __shfl_sync(FULL, anc, tr.jump[r] >= 0 ? tr.jump[r] : 0, G); if (tr.jump[r] >= 0) anc |= t; }
+        tr.anc = anc;
+        uint32_t desc = 0;
+#pragma unroll
+        for (int j = 0; j < G; ++j) { const uint32_t aj = __shfl_sync(FULL, anc, j, G); if (bval && ((aj >> i) & 1u)) desc |= 1u << j; }
+        tr.desc = desc;
+        tr.end = bval ? i + __popc(desc) : G;
+        if (team == 0 && bval) s_anc[i] = anc;
+        if (CONTACT) for (int s = lane; s < m.nshapes; s += 32) s_bmask[s] = partner_mask(m, s);
+        __syncwarp();
+    }
+
+    // ---- per-lane model constants (lanes i >= nb: identity transform, no mass)
+    BodyConst bc;
+    float mc;      // mass of the subtree
+    {
+        Quat tq; tq.x = m.tree_quat[ib][0]; tq.y = m.tree_quat[ib][1]; tq.z = m.tree_quat[ib][2]; tq.w = m.tree_quat[ib][3];
+        V3 tp = mk(m.tree_p[ib][0], m.tree_p[ib][1], m.tree_p[ib][2]);
+        bc.jrev = m.jtype[ib] == MPPIB_JOINT_REVOLUTE ? 1.f : 0.f;
+        V3 tax = bc.jrev != 0.f ? mk(0.f, 0.f, 0.f) : mk(m.tree_R[ib][2], m.tree_R[ib][5], m.tree_R[ib][8]);
+        if (bval && m.parent[ib] < 0) {                 // the robot base pose is folded into a root body's parent transform
+            Quat bq; bq.x = m.base_quat[0]; bq.y = m.base_quat[1]; bq.z = m.base_quat[2]; bq.w = m.base_quat[3];
+            tp = qrot_add(mk(m.base_pos[0], m.base_pos[1], m.base_pos[2]), bq, tp);
+            tax = qrot_add(mk(0.f, 0.f, 0.f), bq, tax);
+            tq = qmul(bq, tq);
+        }
+        bc.mass = m.mass[ib];
+        const float inv_m = bc.mass > 0.f ? 1.0f / bc.mass : 0.f;
+        const V3 c = mk(inv_m * m.mcom[ib][0], inv_m * m.mcom[ib][1], inv_m * m.mcom[ib][2]);
+        const float mm = bc.mass;
+        bc.Ic.xx = m.inertia[ib][0] - mm * (c.y * c.y + c.z * c.z);
+        bc.Ic.yy = m.inertia[ib][1] - mm * (c.x * c.x + c.z * c.z);
+        bc.Ic.zz = m.inertia[ib][2] - mm * (c.x * c.x + c.y * c.y);
+        bc.Ic.xy = m.inertia[ib][3] + mm * c.x * c.y;
+        bc.Ic.xz = m.inertia[ib][4] + mm * c.x * c.z;
+        bc.Ic.yz = m.inertia[ib][5] + mm * c.y * c.z;
+        bc.q_lo = m.q_lo[ib]; bc.q_hi = m.q_hi[ib]; bc.qd_max = m.qd_max[ib]; bc.effort = m.effort[ib];
+        bc.damp = m.damping[ib]; bc.kd = m.kd[ib];
+        bc.dimp_drive = m.armature[ib] + h * (bc.kd + bc.damp);
+        bc.dimp_sat = m.armature[ib] + h * bc.damp;
+        bc.tqx = tq.x; bc.tqy = tq.y; bc.tqz = tq.z; bc.tqw = tq.w; bc.tpx = tp.x; bc.tpy = tp.y; bc.tpz = tp.z;
+        bc.tax = tax.x; bc.tay = tax.y; bc.taz = tax.z; bc.cx = c.x; bc.cy = c.y; bc.cz = c.z;
+        if (!bval) {
+            bc.tqx = 0.f; bc.tqy = 0.f; bc.tqz = 0.f; bc.tqw = 1.f; bc.tpx = bc.tpy = bc.tpz = 0.f; bc.tax = bc.tay = bc.taz = 0.f; bc.jrev = 0.f;
+            bc.mass = 0.f; bc.cx = bc.cy = bc.cz = 0.f;
+            bc.Ic.xx = bc.Ic.yy = bc.Ic.zz = bc.Ic.xy = bc.Ic.xz = bc.Ic.yz = 0.f;
+            bc.dimp_drive = 1.f; bc.dimp_sat = 1.f; bc.kd = 0.f; bc.damp = 0.f; bc.effort = 3.0e38f; bc.qd_max = 0.f; bc.q_lo = 0.f; bc.q_hi = 0.f;
+        }
+        mc = bc.mass;
+        subtree_add<G, R>(mc, i, tr);
+    }
+    const int ci0 = m.cmd_i0[ib], ci1 = m.cmd_i1[ib];
+    const float cc0 = bval ? p.u_scale * m.cmd_c0[ib] : 0.f, cc1 = bval ? p.u_scale * m.cmd_c1[ib] : 0.f;
+    const bool planar = m.planar_base != 0;
+    const float a0x = m.gravity_on ? -m.gravity[0] : 0.f, a0y = m.gravity_on ? -m.gravity[1] : 0.f, a0z = m.gravity_on ? -m.gravity[2] : 0.f;
+    const Quat bq0 = {m.base_quat[0], m.base_quat[1], m.base_quat[2], m.base_quat[3]};
+    const M3 Rbase = quat_to_R(bq0);
+    const V3 obase = mk(m.base_pos[0], m.base_pos[1], m.base_pos[2]);
+
+    float q = 0.f, qd = 0.f;
+    if (bval) {
+        q = state0 ? state0[i] : state[(size_t)i * K + k];
+        qd = state0 ? state0[nb + i] : state[(size_t)(nb + i) * K + k];
+    }
+
+    // =====================================================================================================================
+    // contact pipeline (team-parallel restatement of contact.cuh; the oracle's loop orders are kept)
+    // =====================================================================================================================
+    const uint32_t kg = p.k_offset + (uint32_t)k;
+    auto refresh_free = [&](int fb) {      // all lanes compute, lane 0 writes
+        const Quat fq = {xs[fb + FB_Q], xs[fb + FB_Q + 1], xs[fb + FB_Q + 2], xs[fb + FB_Q + 3]};
+        const M3 Rf = quat_to_R(fq);
+        const float i0 = xs[fb + FB_IINV], i1 = xs[fb + FB_IINV + 1], i2 = xs[fb + FB_IINV + 2];
+        __syncwarp(tm);
+        if (i == 0) {
+            stM3(xs, fb + FB_R, Rf);
+            xs[fb + FB_IW + 0] = Rf.m00 * i0 * Rf.m00 + Rf.m01 * i1 * Rf.m01 + Rf.m02 * i2 * Rf.m02;
+            xs[fb + FB_IW + 1] = Rf.m10 * i0 * Rf.m10 + Rf.m11 * i1 * Rf.m11 + Rf.m12 * i2 * Rf.m12;
+            xs[fb + FB_IW + 2] = Rf.m20 * i0 * Rf.m20 + Rf.m21 * i1 * Rf.m21 + Rf.m22 * i2 * Rf.m22;
+            xs[fb + FB_IW + 3] = Rf.m00 * i0 * Rf.m10 + Rf.m01 * i1 * Rf.m11 + Rf.m02 * i2 * Rf.m12;
+            xs[fb + FB_IW + 4] = Rf.m00 * i0 * Rf.m20 + Rf.m01 * i1 * Rf.m21 + Rf.m02 * i2 * Rf.m22;
+            xs[fb + FB_IW + 5] = Rf.m10 * i0 * Rf.m20 + Rf.m11 * i1 * Rf.m21 + Rf.m12 * i2 * Rf.m22;
+        }
+        __syncwarp(tm);
+    };
+    if (CONTACT) {
+        // one-time per rollout: randomised shape / body parameters (lane = shape / free body), initial free-body states
+        for (int s = i; s < m.nshapes; s += G) {
+            V3 half = mk(m.shape_half[s][0], m.shape_half[s][1], m.shape_half[s][2]);
+            float mu = m.shape_friction[s];
+            if (m.shape_actor[s] >= 0) {
+                V3 ns; float um, uf; actor_noise(p, kg, m.shape_actor[s], ns, um, uf);
+                half.x += 0.5f * m.shape_size_sigma[s][0] * ns.x; half.y += 0.5f * m.shape_size_sigma[s][1] * ns.y; half.z += 0.5f * m.shape_size_sigma[s][2] * ns.z;
+                mu *= 1.0f + m.shape_fric_pct[s] * uf;
+            }
+            const int sb = L.sh0 + s * SHN;
+            st3(xs, sb + SH_HALF, half);
+            xs[sb + SH_MU] = mu;
+            xs[sb + SH_RAD] = m.shape_type[s] == MPPIB_SHAPE_SPHERE ? half.x : sqrtf(dot(half, half));
+        }
+        for (int f = i; f < m.nfree; f += G) {
+            const int fb = L.fb0 + f * FBN;
+            V3 ns; float um, uf; actor_noise(p, kg, m.free_actor[f], ns, um, uf);
+            const float mass = m.free_mass[f] * (1.0f + m.free_mass_pct[f] * um);
+            V3 sg = mk(0.f, 0.f, 0.f);
+            for (int s = 0; s < m.nshapes; ++s)
+                if (m.shape_owner_kind[s] == MPPIB_OWNER_FREE && m.shape_owner[s] == f) { sg = mk(m.shape_size_sigma[s][0], m.shape_size_sigma[s][1], m.shape_size_sigma[s][2]); break; }
+            const V3 half = mk(m.free_half[f][0] + 0.5f * sg.x * ns.x, m.free_half[f][1] + 0.5f * sg.y * ns.y, m.free_half[f][2] + 0.5f * sg.z * ns.z);
+            const float m3 = mass / 3.0f;
+            xs[fb + FB_MASS] = 1.0f / mass;
+            st3(xs, fb + FB_HALF, half);
+            xs[fb + FB_IINV] = 1.0f / (m3 * (half.y * half.y + half.z * half.z));
+            xs[fb + FB_IINV + 1] = 1.0f / (m3 * (half.x * half.x + half.z * half.z));
+            xs[fb + FB_IINV + 2] = 1.0f / (m3 * (half.x * half.x + half.y * half.y));
+            for (int r = 0; r < 13; ++r)
+                xs[fb + r] = state0 ? root0[13 * m.free_actor[f] + r] : state[(size_t)(2 * nb + 13 * f + r) * K + k];
+        }
+        for (int s = i; s < 3 * MPPIB_MAX_SLOTS; s += G) xs[L.net0 + s] = 0.f;
+        __syncwarp(tm);
+        for (int f = 0; f < m.nfree; ++f) refresh_free(L.fb0 + f * FBN);
+    }
+    // world poses of the shapes: `statics` once per rollout, links and free bodies in every substep (lane = shape; a link's frame comes
+    // from the lane that owns the body)
+    auto shapes_world = [&](const Kin& kn, bool statics) {
+        const int ns = m.nshapes;
+        for (int s0 = 0; s0 < ns; s0 += G) {
+            const int s = s0 + i;
+            const bool act = s < ns;
+            const int sc = act ? s : 0;
+            const int kind = m.shape_owner_kind[sc];
+            const int own = m.shape_owner[sc];
+            const int src = (kind == MPPIB_OWNER_LINK && own >= 0) ? own : i;
+            M3 Ro; V3 po;
+            Ro.m00 = shfl_at<G>(kn.R.m00, src); Ro.m01 = shfl_at<G>(kn.R.m01, src); Ro.m02 = shfl_at<G>(kn.R.m02, src);
+            Ro.m10 = shfl_at<G>(kn.R.m10, src); Ro.m11 = shfl_at<G>(kn.R.m11, src); Ro.m12 = shfl_at<G>(kn.R.m12, src);
+            Ro.m20 = shfl_at<G>(kn.R.m20, src); Ro.m21 = shfl_at<G>(kn.R.m21, src); Ro.m22 = shfl_at<G>(kn.R.m22, src);
+            po.x = shfl_at<G>(kn.o.x, src); po.y = shfl_at<G>(kn.o.y, src); po.z = shfl_at<G>(kn.o.z, src);
+            if (!act || (kind == MPPIB_OWNER_STATIC) != statics) continue;
+            if (kind == MPPIB_OWNER_STATIC) {
+                const float* rs = root0 + 13 * m.shape_actor[s];
+                const Quat qs = {rs[3], rs[4], rs[5], rs[6]};
+                Ro = quat_to_R(qs); po = mk(rs[0], rs[1], rs[2]);
+            } else if (kind == MPPIB_OWNER_LINK) {
+                if (own < 0) { Ro = Rbase; po = obase; }
+            } else {
+                const int fb = L.fb0 + own * FBN;
+                Ro = ldM3(xs, fb + FB_R); po = ld3(xs, fb + FB_X);
+            }
+            const Quat qlc = {m.shape_quat[s][0], m.shape_quat[s][1], m.shape_quat[s][2], m.shape_quat[s][3]};
+            const int sb = L.sh0 + s * SHN;
+            stM3(xs, sb + SH_R, mulMM(Ro, quat_to_R(qlc)));
+            st3(xs, sb + SH_C, po + mulc(Ro, m.shape_pos[s][0], m.shape_pos[s][1], m.shape_pos[s][2]));
+        }
+        __syncwarp(tm);
+    };
+    int nc = 0;
+    // append the contacts of the lanes that raise `hit`, in lane order (the oracle's sample-point order)
+    auto append = [&](bool hit, int refA, int refB, int slotA, int slotB, V3 pt, V3 n, float d, float mu) {
+        const uint32_t bits = team_ballot<G>(hit, tm, tb);
+        const int slot = nc + __popc(bits & ((1u << i) - 1u));
+        if (hit && slot < m.max_contacts) {
+            const int cb = L.ct0 + slot * CTN;
+            st3(xs, cb + CT_P, pt); st3(xs, cb + CT_N, n);
+            xs[cb + CT_D] = d; xs[cb + CT_MU] = mu; xs[cb + CT_LN] = 0.f; xs[cb + CT_LT1] = 0.f; xs[cb + CT_LT2] = 0.f;
+            xs[cb + CT_IDS] = __int_as_float((refA + 2) | ((refB + 2) << 8) | ((slotA + 1) << 16) | ((slotB + 1) << 24));
+        }
+        nc = min(nc + __popc(bits), (int)m.max_contacts);
+    };
+    // sample points of box a inside box b (lane = sample point), `flip`: a is the B side of the pair
+    auto points_in_box = [&](int a, int b, bool flip) {
+        const int sa = L.sh0 + a * SHN, sb = L.sh0 + b * SHN;
+        const M3 Ra = ldM3(xs, sa + SH_R), Rb = ldM3(xs, sb + SH_R);
+        const V3 ca = ld3(xs, sa + SH_C), cbv = ld3(xs, sb + SH_C);
+        const V3 ha = ld3(xs, sa + SH_HALF), hb = ld3(xs, sb + SH_HALF);
+        const float mu = 0.5f * (xs[sa + SH_MU] + xs[sb + SH_MU]);
+        const int refa = shape_ref(m, a), refb = shape_ref(m, b), slota = m.shape_slot[a], slotb = m.shape_slot[b];
+        const V3 cl = mulMT(Rb, ca - cbv);
+        bool c0 = fabsf(cl.x) > hb.x, c1 = fabsf(cl.y) > hb.y, c2 = fabsf(cl.z) > hb.z;
+        if (!(c0 || c1 || c2)) c0 = c1 = c2 = true;
+        const float mg = m.contact_margin;
+        for (int i0 = 0; i0 < 27; i0 += G) {
+            const int idx = i0 + i;
+            bool hit = idx < 27 && idx != 13;
+            const int ix = idx / 9 - 1, iy = (idx / 3) % 3 - 1, iz = idx % 3 - 1;
+            const V3 pt = mulM(Ra, mk(ix * ha.x, iy * ha.y, iz * ha.z)) + ca;
+            const V3 x = mulMT(Rb, pt - cbv);
+            const float p0 = hb.x - fabsf(x.x), p1 = hb.y - fabsf(x.y), p2 = hb.z - fabsf(x.z);
+            if (!(p0 + mg > 0.f) || !(p1 + mg > 0.f) || !(p2 + mg > 0.f)) hit = false;
+            int ax = -1; float pen = 0.f;
+            if (c0) { ax = 0; pen = p0; }
+            if (c1 && (ax < 0 || p1 < pen)) { ax = 1; pen = p1; }
+            if (c2 && (ax < 0 || p2 < pen)) { ax = 2; pen = p2; }
+            const float xa = ax == 0 ? x.x : (ax == 1 ? x.y : x.z);
+            const float sg = xa >= 0.f ? 1.f : -1.f;
+            const V3 n = ax == 0 ? mk(sg * Rb.m00, sg * Rb.m10, sg * Rb.m20) : (ax == 1 ? mk(sg * Rb.m01, sg * Rb.m11, sg * Rb.m21) : mk(sg * Rb.m02, sg * Rb.m12, sg * Rb.m22));
+            if (!flip) append(hit, refa, refb, slota, slotb, pt, n, pen, mu);
+            else append(hit, refb, refa, slotb, slota, pt, mk(-n.x, -n.y, -n.z), pen, mu);
+        }
+    };
+    // ONE contact of a sphere against a box or a sphere (contact.cuh sphere_contact); all lanes compute, lane 0 appends
+    auto sphere_contact = [&](int a, int b) {
+        const int sa = L.sh0 + a * SHN, sb = L.sh0 + b * SHN;
+        const float mu = 0.5f * (xs[sa + SH_MU] + xs[sb + SH_MU]), mg = m.contact_margin;
+        const int refa = shape_ref(m, a), refb = shape_ref(m, b), slota = m.shape_slot[a], slotb = m.shape_slot[b];
+        const V3 ca = ld3(xs, sa + SH_C), cbv = ld3(xs, sb + SH_C);
+        bool hit = true; V3 pt = mk(0.f, 0.f, 0.f), n = mk(0.f, 0.f, 1.f); float pen = 0.f;
+        if (m.shape_type[a] == MPPIB_SHAPE_SPHERE && m.shape_type[b] == MPPIB_SHAPE_SPHERE) {
+            const V3 d = ca - cbv;
+            const float dist = sqrtf(dot(d, d)), ra = xs[sa + SH_HALF], rb = xs[sb + SH_HALF], rs = ra + rb;
+            if (!(dist < rs + mg) || !(dist > 0.f)) hit = false;
+            n = scale(1.0f / fmaxf(dist, 1e-30f), d);
+            pt = cbv + scale(rb, n); pen = rs - dist;
+        } else {
+            const bool sphere_is_a = m.shape_type[a] == MPPIB_SHAPE_SPHERE;
+            const int ss = sphere_is_a ? sa : sb, sx = sphere_is_a ? sb : sa;
+            const float r = xs[ss + SH_HALF];
+            const V3 cs = sphere_is_a ? ca : cbv, cx = sphere_is_a ? cbv : ca;
+            const M3 Rx = ldM3(xs, sx + SH_R);
+            const V3 hx = ld3(xs, sx + SH_HALF);
+            const V3 x = mulMT(Rx, cs - cx);
+            V3 qq = mk(fminf(fmaxf(x.x, -hx.x), hx.x), fminf(fmaxf(x.y, -hx.y), hx.y), fminf(fmaxf(x.z, -hx.z), hx.z));
+            const V3 dd = x - qq;
+            const float d2 = dot(dd, dd);
+            V3 nl = mk(0.f, 0.f, 0.f);
+            if (d2 > 0.f) {
+                const float dist = sqrtf(d2);
+                if (!(dist < r + mg)) hit = false;
+                nl = scale(1.0f / dist, dd);
+                pen = r - dist;
+            } else {
+                int ax = 0; float best = hx.x - fabsf(x.x);
+                const float p1 = hx.y - fabsf(x.y), p2 = hx.z - fabsf(x.z);
+                if (p1 < best) { best = p1; ax = 1; }
+                if (p2 < best) { best = p2; ax = 2; }
+                const float xa = ax == 0 ? x.x : (ax == 1 ? x.y : x.z);
+                const float sg = xa >= 0.f ? 1.f : -1.f;
+                if (ax == 0) { nl.x = sg; qq.x = sg * hx.x; } else if (ax == 1) { nl.y = sg; qq.y = sg * hx.y; } else { nl.z = sg; qq.z = sg * hx.z; }
+                pen = best + r;
+            }
+            n = mulM(Rx, nl);
+            pt = cx + mulM(Rx, qq);
+            if (!sphere_is_a) n = mk(-n.x, -n.y, -n.z);
+        }
+        append(hit && i == 0, refa, refb, slota, slotb, pt, n, pen, mu);
+    };
+    auto near_shapes = [&](int a, int b) -> bool {
+        const int sa = L.sh0 + a * SHN, sb = L.sh0 + b * SHN;
+        const V3 d = ld3(xs, sa + SH_C) - ld3(xs, sb + SH_C);
+        const float mg = m.contact_margin;
+        const bool sph = m.shape_type[a] == MPPIB_SHAPE_SPHERE || m.shape_type[b] == MPPIB_SHAPE_SPHERE;
+        const float r = xs[sa + SH_RAD] + xs[sb + SH_RAD] + (sph ? mg : 0.f);
+        if (dot(d, d) > r * r) return false;
+        if (sph) return true;
+        const M3 Ra = ldM3(xs, sa + SH_R), Rb = ldM3(xs, sb + SH_R);
+        const V3 ha = ld3(xs, sa + SH_HALF), hb = ld3(xs, sb + SH_HALF);
+        const V3 tbv = mulMT(Rb, d), ta = mulMT(Ra, d);
+        const V3 b0 = mk(Rb.m00, Rb.m10, Rb.m20), b1 = mk(Rb.m01, Rb.m11, Rb.m21), b2 = mk(Rb.m02, Rb.m12, Rb.m22);
+        const V3 a0 = mk(Ra.m00, Ra.m10, Ra.m20), a1 = mk(Ra.m01, Ra.m11, Ra.m21), a2 = mk(Ra.m02, Ra.m12, Ra.m22);
+        const float c00 = fabsf(dot(b0, a0)), c01 = fabsf(dot(b0, a1)), c02 = fabsf(dot(b0, a2));
+        const float c10 = fabsf(dot(b1, a0)), c11 = fabsf(dot(b1, a1)), c12 = fabsf(dot(b1, a2));
+        const float c20 = fabsf(dot(b2, a0)), c21 = fabsf(dot(b2, a1)), c22 = fabsf(dot(b2, a2));
+        if (fabsf(tbv.x) > hb.x + c00 * ha.x + c01 * ha.y + c02 * ha.z + mg) return false;
+        if (fabsf(ta.x) > ha.x + c00 * hb.x + c10 * hb.y + c20 * hb.z + mg) return false;
+        if (fabsf(tbv.y) > hb.y + c10 * ha.x + c11 * ha.y + c12 * ha.z + mg) return false;
+        if (fabsf(ta.y) > ha.y + c01 * hb.x + c11 * hb.y + c21 * hb.z + mg) return false;
+        if (fabsf(tbv.z) > hb.z + c20 * ha.x + c21 * ha.y + c22 * ha.z + mg) return false;
+        if (fabsf(ta.z) > ha.z + c02 * hb.x + c12 * hb.y + c22 * hb.z + mg) return false;
+        return true;
+    };
+    // partners of shape a: the broad phase of up to G partners in parallel (lane = partner), then the near ones in ascending order
+    auto pairs_of = [&](int a) {
+        uint32_t mask = s_bmask[a];
+        while (mask) {                                       // team-uniform
+            uint32_t mine = mask; int b = -1;
+            for (int j = 0; j <= i && mine; ++j) { b = __ffs(mine) - 1; mine &= mine - 1; }     // the (i+1)-th set bit, if there is one
+            const int cnt = __popc(mask);
+            const bool have = i < cnt;
+            const bool nearb = have && near_shapes(a, b);
+            uint32_t nbits = team_ballot<G>(nearb, tm, tb);
+            while (nbits) {                                  // team-uniform: lanes in ascending partner order
+                const int ln = __ffs(nbits) - 1; nbits &= nbits - 1;
+                const int bb = __shfl_sync(tm, b, ln, G);
+                if (m.shape_type[a] == MPPIB_SHAPE_SPHERE || m.shape_type[bb] == MPPIB_SHAPE_SPHERE) sphere_contact(a, bb);
+                else { points_in_box(a, bb, false); points_in_box(bb, a, true); }
+            }
+            for (int j = 0; j < G && mask; ++j) mask &= mask - 1;                               // drop the partners just handled
+        }
+    };
+    auto detect = [&]() {
+        nc = 0;
+        const int ns = m.nshapes;
+        for (int a = 0; a < ns; ++a) {
+            if (m.shape_owner_kind[a] != MPPIB_OWNER_FREE) continue;
+            const int sa = L.sh0 + a * SHN;
+            if (m.ground_plane) {
+                const M3 Ra = ldM3(xs, sa + SH_R); const V3 ca = ld3(xs, sa + SH_C), ha = ld3(xs, sa + SH_HALF);
+                const float mu = 0.5f * (xs[sa + SH_MU] + m.ground_friction);
+                for (int i0 = 0; i0 < 8; i0 += G) {
+                    const int idx = i0 + i;
+                    const int ix = (idx >> 2) * 2 - 1, iy = ((idx >> 1) & 1) * 2 - 1, iz = (idx & 1) * 2 - 1;
+                    const V3 pt = mulM(Ra, mk(ix * ha.x, iy * ha.y, iz * ha.z)) + ca;
+                    append(idx < 8 && pt.z < m.ground_margin, shape_ref(m, a), REF_STATIC, m.shape_slot[a], -1, pt, mk(0.f, 0.f, 1.f), -pt.z, mu);
+                }
+            }
+            pairs_of(a);
+        }
+        for (int a = 0; a < ns; ++a) {   // articulation link vs static shape
+            if (m.shape_owner_kind[a] != MPPIB_OWNER_LINK) continue;
+            pairs_of(a);
+        }
+        __syncwarp(tm);
+    };
+    // joint-space row of this lane's joint for a contact on body `ref` at pt along d:  S.f . d + S.n . (pt x d)  if the joint is on
+    // the chain of the body, else 0; `sgn` = +1 on side A, -1 on side B
+    auto jrow = [&](const Kin& kn, float sgn_chain, V3 pt, V3 d) -> float {
+        return sgn_chain * (dot(kn.S.f, d) + dot(kn.S.n, cross(pt, d)));
+    };
+    auto chain_sign = [&](int refA, int refB) -> float {
+        float s = 0.f;
+        if (refA >= 0 && refA < REF_FREE0 && ((s_anc[refA] >> i) & 1u) && bval) s = 1.f;
+        if (refB >= 0 && refB < REF_FREE0 && ((s_anc[refB] >> i) & 1u) && bval) s = -1.f;
+        return s;
+    };
+    // free-body part of the effective inverse mass / of the relative velocity (all lanes compute the same numbers)
+    auto free_inv_mass = [&](int ref, V3 pt, V3 dir) -> float {
+        if (ref < REF_FREE0) return 0.f;
+        const int fb = L.fb0 + (ref - REF_FREE0) * FBN;
+        const V3 r = pt - ld3(xs, fb + FB_X);
+        const V3 rxn = cross(r, dir);
+        const S3 Iw = {xs[fb + FB_IW], xs[fb + FB_IW + 1], xs[fb + FB_IW + 2], xs[fb + FB_IW + 3], xs[fb + FB_IW + 4], xs[fb + FB_IW + 5]};
+        return xs[fb + FB_MASS] + dot(cross(mul(Iw, rxn), r), dir);
+    };
+    auto free_velocity = [&](int ref, V3 pt) -> V3 {
+        if (ref < REF_FREE0) return mk(0.f, 0.f, 0.f);
+        const int fb = L.fb0 + (ref - REF_FREE0) * FBN;
+        return ld3(xs, fb + FB_V) + cross(ld3(xs, fb + FB_W), pt - ld3(xs, fb + FB_X));
+    };
+    // Gauss-Seidel soft-constraint solve on the predicted velocities (contact.cuh solve): vp = predicted qd of this lane's joint,
+    // dq = its velocity correction (in / out), invD = 1 / D_j
+    auto solve_contacts = [&](const Kin& kn, float vp, float invD, float& dq, bool last_substep) {
+        const float kp = m.contact_kp, kdc = m.contact_kd;
+        const float gamma = 1.0f / (h * (h * kp + kdc)), beta = h * kp / (h * kp + kdc), ih = 1.0f / h;
+        for (int c = 0; c < nc; ++c) {                       // per contact, once: tangent frame, inverse effective masses, bias velocity
+            const int cb = L.ct0 + c * CTN;
+            const int ids = __float_as_int(xs[cb + CT_IDS]);
+            const int refA = (ids & 0xFF) - 2, refB = ((ids >> 8) & 0xFF) - 2;
+            const V3 pt = ld3(xs, cb + CT_P), n = ld3(xs, cb + CT_N);
+            const V3 e = fabsf(n.x) < 0.9f ? mk(1.f, 0.f, 0.f) : mk(0.f, 1.f, 0.f);
+            V3 t1 = cross(n, e);
+            t1 = scale(rsqrtf(dot(t1, t1)), t1);
+            const V3 t2 = cross(n, t1);
+            const float sg = chain_sign(refA, refB);
+            const float jn = jrow(kn, sg, pt, n), j1 = jrow(kn, sg, pt, t1), j2 = jrow(kn, sg, pt, t2);
+            float kn_ = team_sum<G>(jn * jn * invD, tm), kt1 = team_sum<G>(j1 * j1 * invD, tm), kt2 = team_sum<G>(j2 * j2 * invD, tm);
+            kn_ += free_inv_mass(refA, pt, n) + free_inv_mass(refB, pt, n);
+            kt1 += free_inv_mass(refA, pt, t1) + free_inv_mass(refB, pt, t1);
+            kt2 += free_inv_mass(refA, pt, t2) + free_inv_mass(refB, pt, t2);
+            const float d = xs[cb + CT_D];
+            __syncwarp(tm);
+            if (i == 0) {
+                xs[cb + CT_KN] = kn_ > K_ROW_MIN ? 1.0f / (kn_ + gamma) : 0.f;
+                xs[cb + CT_KT1] = kt1 > K_ROW_MIN ? 1.0f / kt1 : 0.f;
+                xs[cb + CT_KT2] = kt2 > K_ROW_MIN ? 1.0f / kt2 : 0.f;
+                st3(xs, cb + CT_T1, t1);
+                xs[cb + CT_D] = d > 0.f ? fminf(beta * d * ih, m.max_depen) : d * ih;
+            }
+        }
+        __syncwarp(tm);
+        for (int it = 0; it < m.contact_iters; ++it) {
+            for (int c = 0; c < nc; ++c) {
+                const int cb = L.ct0 + c * CTN;
+                const float ikn = xs[cb + CT_KN];
+                if (!(ikn > 0.f)) continue;                  // team-uniform
+                const int ids = __float_as_int(xs[cb + CT_IDS]);
+                const int refA = (ids & 0xFF) - 2, refB = ((ids >> 8) & 0xFF) - 2;
+                const V3 pt = ld3(xs, cb + CT_P), n = ld3(xs, cb + CT_N), t1 = ld3(xs, cb + CT_T1);
+                const V3 t2 = cross(n, t1);
+                const float bias = xs[cb + CT_D], mu = xs[cb + CT_MU], ikt1 = xs[cb + CT_KT1], ikt2 = xs[cb + CT_KT2];
+                const float sg = chain_sign(refA, refB);
+                const float jn = jrow(kn, sg, pt, n), j1 = jrow(kn, sg, pt, t1), j2 = jrow(kn, sg, pt, t2);
+                const float vj = vp + dq;
+                // relative velocity along the contact frame: the joints' parts by an all-reduce, the free bodies' parts directly
+                const V3 vfree = free_velocity(refA, pt) - free_velocity(refB, pt);
+                const float vn = team_sum<G>(jn * vj, tm) + dot(vfree, n);
+                const float v1 = team_sum<G>(j1 * vj, tm) + dot(vfree, t1);
+                const float v2 = team_sum<G>(j2 * vj, tm) + dot(vfree, t2);
+                const float ln = xs[cb + CT_LN], lt1 = xs[cb + CT_LT1], lt2 = xs[cb + CT_LT2];
+                const float ln_new = fmaxf(0.f, ln + (-vn + bias - gamma * ln) * ikn);
+                const float lim = mu * ln_new;
+                const float lt1_new = ikt1 > 0.f ? fminf(fmaxf(lt1 - v1 * ikt1, -lim), lim) : lt1;
+                const float lt2_new = ikt2 > 0.f ? fminf(fmaxf(lt2 - v2 * ikt2, -lim), lim) : lt2;
+                const float dn = ln_new - ln, d1 = lt1_new - lt1, d2 = lt2_new - lt2;
+                dq += invD * (jn * dn + j1 * d1 + j2 * d2);  // this lane's joint (0 when it is not on the contact's chain)
+                __syncwarp(tm);                                // every lane has read the contact and the free bodies
+                if (i == 0) {
+                    xs[cb + CT_LN] = ln_new; xs[cb + CT_LT1] = lt1_new; xs[cb + CT_LT2] = lt2_new;
+                    const V3 P = scale(dn, n) + scale(d1, t1) + scale(d2, t2);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int ref = e == 0 ? refA : refB;
+                        if (ref < REF_FREE0) continue;
+                        const float sgn = e == 0 ? 1.0f : -1.0f;
+                        const int fb = L.fb0 + (ref - REF_FREE0) * FBN;
+                        const V3 r = pt - ld3(xs, fb + FB_X);
+                        const float im = sgn * xs[fb + FB_MASS];
+                        xs[fb + FB_V] += im * P.x; xs[fb + FB_V + 1] += im * P.y; xs[fb + FB_V + 2] += im * P.z;
+                        const S3 Iw = {xs[fb + FB_IW], xs[fb + FB_IW + 1], xs[fb + FB_IW + 2], xs[fb + FB_IW + 3], xs[fb + FB_IW + 4], xs[fb + FB_IW + 5]};
+                        const V3 dw = mul(Iw, cross(r, P));
+                        xs[fb + FB_W] += sgn * dw.x; xs[fb + FB_W + 1] += sgn * dw.y; xs[fb + FB_W + 2] += sgn * dw.z;
+                    }
+                }
+                __syncwarp(tm);
+            }
+        }
+        if (last_substep) {                                  // net contact force per body = the last substep's impulses / h
+            if (i == 0) {
+                for (int s = 0; s < 3 * MPPIB_MAX_SLOTS; ++s) xs[L.net0 + s] = 0.f;
+                for (int c = 0; c < nc; ++c) {
+                    const int cb = L.ct0 + c * CTN;
+                    const int ids = __float_as_int(xs[cb + CT_IDS]);
+                    const int slotA = ((ids >> 16) & 0xFF) - 1, slotB = ((ids >> 24) & 0xFF) - 1;
+                    if (slotA < 0 && slotB < 0) continue;
+                    const V3 n = ld3(xs, cb + CT_N), t1 = ld3(xs, cb + CT_T1);
+                    const V3 t2 = cross(n, t1);
+                    const V3 F = scale(ih, scale(xs[cb + CT_LN], n) + scale(xs[cb + CT_LT1], t1) + scale(xs[cb + CT_LT2], t2));
+                    if (slotA >= 0) { xs[L.net0 + 3 * slotA] += F.x; xs[L.net0 + 3 * slotA + 1] += F.y; xs[L.net0 + 3 * slotA + 2] += F.z; }
+                    if (slotB >= 0) { xs[L.net0 + 3 * slotB] -= F.x; xs[L.net0 + 3 * slotB + 1] -= F.y; xs[L.net0 + 3 * slotB + 2] -= F.z; }
+                }
+            }
+            __syncwarp(tm);
+        }
+    };
+    auto integrate_free = [&]() {
+        for (int f = 0; f < m.nfree; ++f) {
+            const int fb = L.fb0 + f * FBN;
+            const V3 x = ld3(xs, fb + FB_X), v = ld3(xs, fb + FB_V), w = ld3(xs, fb + FB_W);
+            const Quat fq = {xs[fb + FB_Q], xs[fb + FB_Q + 1], xs[fb + FB_Q + 2], xs[fb + FB_Q + 3]};
+            const Quat wq = {w.x, w.y, w.z, 0.f};
+            const Quat dqq = qmul(wq, fq);
+            Quat r = {fq.x + 0.5f * h * dqq.x, fq.y + 0.5f * h * dqq.y, fq.z + 0.5f * h * dqq.z, fq.w + 0.5f * h * dqq.w};
+            const float il = rsqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
+            __syncwarp(tm);
+            if (i == 0) {
+                xs[fb + FB_X] = x.x + h * v.x; xs[fb + FB_X + 1] = x.y + h * v.y; xs[fb + FB_X + 2] = x.z + h * v.z;
+                xs[fb + FB_Q] = r.x * il; xs[fb + FB_Q + 1] = r.y * il; xs[fb + FB_Q + 2] = r.z * il; xs[fb + FB_Q + 3] = r.w * il;
+            }
+            __syncwarp(tm);
+            refresh_free(fb);
+        }
+    };
+
+    // ---- observation rows of model step t from the frames of the CURRENT state
+    auto write_obs = [&](int t, const Kin& kn) {
+        const size_t TK = (size_t)T * K;
+        float* dst = obs + (size_t)t * K + k;
+        int row = 0;
+        for (int oi = 0; oi < p.nobs; ++oi) {
+            const int kind = p.obs[oi].kind, idx = p.obs[oi].index;
+            if (kind == MPPIB_OBS_LINK_STATE) {
+                const int b = m.link_body[idx];
+                if (kval && (b >= 0 ? i == b : i == 0)) {
+                    V3 ol, w, vO; Quat qb; M3 Rl;
+                    if (b >= 0) { Rl = kn.R; ol = kn.o; w = kn.V.n; vO = kn.V.f; qb = kn.qw; }
+                    else { qb = bq0; Rl = Rbase; ol = obase; w = mk(0.f, 0.f, 0.f); vO = mk(0.f, 0.f, 0.f); }
+                    const V3 pos = ol + mulc(Rl, m.link_p[idx][0], m.link_p[idx][1], m.link_p[idx][2]);
+                    const Quat qlk = {m.link_quat[idx][0], m.link_quat[idx][1], m.link_quat[idx][2], m.link_quat[idx][3]};
+                    const Quat qo = qmul(qb, qlk);
+                    const V3 vel = cross_add(vO, w, pos);
+                    dst[(size_t)(row + 0) * TK] = pos.x; dst[(size_t)(row + 1) * TK] = pos.y; dst[(size_t)(row + 2) * TK] = pos.z;
+                    dst[(size_t)(row + 3) * TK] = qo.x; dst[(size_t)(row + 4) * TK] = qo.y; dst[(size_t)(row + 5) * TK] = qo.z;
+                    dst[(size_t)(row + 6) * TK] = qo.w;
+                    dst[(size_t)(row + 7) * TK] = vel.x; dst[(size_t)(row + 8) * TK] = vel.y; dst[(size_t)(row + 9) * TK] = vel.z;
+                    dst[(size_t)(row + 10) * TK] = w.x; dst[(size_t)(row + 11) * TK] = w.y; dst[(size_t)(row + 12) * TK] = w.z;
+                }
+                row += 13;
+            } else if (kind == MPPIB_OBS_DOF_STATE) {
+                if (kval && bval) {
+                    dst[(size_t)(row + 2 * i) * TK] = q;
+                    dst[(size_t)(row + 2 * i + 1) * TK] = qd;
+                }
+                row += 2 * nb;
+            } else if (kind == MPPIB_OBS_FREE_STATE) {
+                const int fb = L.fb0 + idx * FBN;
+                for (int r = i; r < 13; r += G) if (kval) dst[(size_t)(row + r) * TK] = (CONTACT && idx < m.nfree) ? xs[fb + r] : 0.f;
+                row += 13;
+            } else {
+                for (int r = i; r < 3; r += G) if (kval) dst[(size_t)(row + r) * TK] = (CONTACT && idx < MPPIB_MAX_SLOTS) ? xs[L.net0 + 3 * idx + r] : 0.f;
+                row += 3;
+            }
+        }
+    };
+
+    Kin kn;
+    if (CONTACT) { kinematics<G, R>(bc, tr, q, qd, kn); shapes_world(kn, true); }
+    int pending = (obs != nullptr && nsteps == 0) ? t0 : -1;
+    float u0n = 0.f, u1n = 0.f, uv = 0.f, uw = 0.f;
+    auto load_u = [&](int t) {
+        u0n = __ldg(&actions[((size_t)t * nu + ci0) * K + k]);
+        u1n = __ldg(&actions[((size_t)t * nu + ci1) * K + k]);
+        if (planar) { uv = __ldg(&actions[((size_t)t * nu + 0) * K + k]); uw = __ldg(&actions[((size_t)t * nu + 1) * K + k]); }
+    };
+    if (nsteps > 0) load_u(t0);
+    const int nsub = p.substeps;
+#pragma unroll 1
+    for (int t = t0; t < t0 + nsteps; ++t) {
+        float tgt = cc0 * u0n + cc1 * u1n;
+        const float pv = p.u_scale * uv, pw = p.u_scale * uw;
+        if (t + 1 < t0 + nsteps) load_u(t + 1);
+#pragma unroll 1
+        for (int sub = 0; sub < nsub; ++sub) {
+            if (planar) {
+                // differential drive reduced to a planar base: body twist (v, omega) -> world-frame velocity targets of the three
+                // virtual joints; the forward axis turns with the current yaw (joint 2)
+                const float yaw = shfl_at<G>(q, 2);
+                float sy, cy; sincos_cw(yaw, &sy, &cy);
+                if (i == 0) tgt = pv * (m.fwd_axis[0] * cy - m.fwd_axis[1] * sy);
+                if (i == 1) tgt = pv * (m.fwd_axis[0] * sy + m.fwd_axis[1] * cy);
+                if (i == 2) tgt = pw;
+            }
+            kinematics<G, R>(bc, tr, q, qd, kn);
+            if (sub == 0 && pending >= 0) { write_obs(pending, kn); pending = -1; }
+            // ---- per-body terms about the world origin
+            const V3 cw = kn.o + mulc(kn.R, bc.cx, bc.cy, bc.cz);
+            const V3 hw = scale(bc.mass, cw);
+            S3 A;
+            {
+                const V3 r0 = mk(kn.R.m00, kn.R.m01, kn.R.m02), r1 = mk(kn.R.m10, kn.R.m11, kn.R.m12), r2 = mk(kn.R.m20, kn.R.m21, kn.R.m22);
+                const V3 t0v = mul(bc.Ic, r0), t1v = mul(bc.Ic, r1), t2v = mul(bc.Ic, r2);
+                const float d2 = dot(hw, cw);
+                A.xx = fmaf(-hw.x, cw.x, d2 + dot(r0, t0v)); A.yy = fmaf(-hw.y, cw.y, d2 + dot(r1, t1v)); A.zz = fmaf(-hw.z, cw.z, d2 + dot(r2, t2v));
+                A.xy = fmaf(-hw.x, cw.y, dot(r0, t1v)); A.xz = fmaf(-hw.x, cw.z, dot(r0, t2v)); A.yz = fmaf(-hw.y, cw.z, dot(r1, t2v));
+            }
+            const V3 w = kn.V.n, v = kn.V.f;
+            V6 fb6;
+            {
+                const V3 nn = cross_add(mul(A, w), hw, v);
+                const V3 ff = cross_add(scale(bc.mass, v), w, hw);
+                fb6.n = cross_add(cross(w, nn), v, ff);
+                fb6.f = cross(w, ff);
+            }
+            V6 a;
+            a.n = cross(w, kn.Vl.n);
+            a.f = cross_add(cross(w, kn.Vl.f), v, kn.Vl.n);
+            anc_add3<G, R>(a.n, tr); anc_add3<G, R>(a.f, tr);
+            a.f = mk(a.f.x + a0x, a.f.y + a0y, a.f.z + a0z);
+            fb6.n = cross_add(mul_add(fb6.n, A, a.n), hw, a.f);
+            fb6.f = cross_add(mk(fmaf(a.f.x, bc.mass, fb6.f.x), fmaf(a.f.y, bc.mass, fb6.f.y), fmaf(a.f.z, bc.mass, fb6.f.z)), a.n, hw);
+            // ---- composites: sums over the subtree
+            subtree_add<G, R>(A.xx, i, tr); subtree_add<G, R>(A.yy, i, tr); subtree_add<G, R>(A.zz, i, tr);
+            subtree_add<G, R>(A.xy, i, tr); subtree_add<G, R>(A.xz, i, tr); subtree_add<G, R>(A.yz, i, tr);
+            V3 hc = hw;
+            subtree_add3<G, R>(hc, i, tr);
+            subtree_add3<G, R>(fb6.n, i, tr); subtree_add3<G, R>(fb6.f, i, tr);
+            V6 Fj;
+            Fj.n = cross_add(mul(A, kn.S.n), hc, kn.S.f);
+            Fj.f = cross_add(scale(mc, kn.S.f), kn.S.n, hc);
+            const float bias = dot6(kn.S, fb6);
+            // ---- joint-space inertia, LEAF-FIRST elimination order (the pivots are then the articulated-body diagonals D_j the
+            // contact solve needs): virtual index v = NB - 1 - body.  Lane j owns column j of the LOWER triangle: M_rj = F_r . S_j for
+            // the descendants r of j (0 elsewhere); in virtual indices that is the upper-triangle column the solver below expects.
+            constexpr int VB = NB - 1;
+            const int vi = VB - i;                                           // virtual index of this lane (negative for lanes >= NB: never a pivot)
+            float mcol[NB];
+#pragma unroll
+            for (int vr = 0; vr < NB; ++vr) {
+                const int rb = VB - vr;                                      // body of virtual row vr
+                V6 Fr;
+                Fr.n.x = shfl_at<G>(Fj.n.x, rb); Fr.n.y = shfl_at<G>(Fj.n.y, rb); Fr.n.z = shfl_at<G>(Fj.n.z, rb);
+                Fr.f.x = shfl_at<G>(Fj.f.x, rb); Fr.f.y = shfl_at<G>(Fj.f.y, rb); Fr.f.z = shfl_at<G>(Fj.f.z, rb);
+                mcol[vr] = ((tr.desc >> rb) & 1u) ? dot6(Fr, kn.S) : 0.f;
+            }
+            float sat = 0.f, qdd = 0.f, invD = 1.f;
+#pragma unroll 1
+            for (int solve = 0; solve < 2; ++solve) {
+                float tau, dimp;
+                if (sat != 0.f) { tau = sat * bc.effort - bc.damp * qd; dimp = bc.dimp_sat; }
+                else if (vel_mode) { tau = bc.kd * (tgt - qd) - bc.damp * qd; dimp = bc.dimp_drive; }
+                else { tau = fminf(fmaxf(tgt, -bc.effort), bc.effort) - (bc.kd + bc.damp) * qd; dimp = bc.dimp_drive; }
+                float col[NB], lcol[NB];
+#pragma unroll
+                for (int r = 0; r < NB; ++r) { col[r] = mcol[r]; lcol[r] = 0.f; }
+                float invd = 1.f;
+                float y = tau - bias;
+#pragma unroll
+                for (int kk = 0; kk < NB; ++kk) {
+                    const int kb = VB - kk;                                  // body of the pivot
+                    const float dk = shfl_at<G>(col[kk] + dimp, kb);
+                    const float inv = rcp_approx(dk);
+                    const bool own = vi == kk;
+                    if (own) invd = inv;
+                    const float lk = col[kk] * inv;
+                    if (kk + 1 < NB) {
+                        const float yk = shfl_at<G>(y, kb);
+                        if (vi > kk) y = fmaf(-lk, yk, y);
+                    }
+#pragma unroll
+                    for (int r = kk + 1; r < NB; ++r) {
+                        const float lr = shfl_at<G>(lk, VB - r);
+                        col[r] = fmaf(-lr, col[kk], col[r]);
+                        if (own) lcol[r] = lr;
+                    }
+                }
+                y *= invd;
+#pragma unroll
+                for (int jj = NB - 1; jj >= 1; --jj) {
+                    const float xj = shfl_at<G>(y, VB - jj);
+                    if (vi >= 0 && vi < jj) y = fmaf(-lcol[jj], xj, y);
+                }
+                qdd = bval ? y : 0.f;
+                invD = invd;                                                 // 1 / D_j of the articulated-body recursion
+                bool newly = false;
+                if (solve == 0 && vel_mode && bval) {
+                    const float td = bc.kd * (tgt - (qd + h * qdd));
+                    if (fabsf(td) > bc.effort) { sat = td > 0.f ? 1.f : -1.f; newly = true; }
+                }
+                if (!__any_sync(FULL, newly)) break;
+            }
+            float vnew = qd + h * qdd;
+            if (CONTACT) {
+                // ---- contacts on the predicted velocities
+                float dq = 0.f;
+                shapes_world(kn, false);
+                detect();
+                if (i == 0) for (int f = 0; f < m.nfree; ++f) if (m.free_gravity[f]) {
+                    const int fb = L.fb0 + f * FBN;
+                    xs[fb + FB_V] += h * m.gravity[0]; xs[fb + FB_V + 1] += h * m.gravity[1]; xs[fb + FB_V + 2] += h * m.gravity[2];
+                }
+                __syncwarp();
+                const float invDc = bval ? fminf(invD, 1.0e6f) : 0.f;        // 1 / max(D_j, 1e-6)
+#ifdef MPPIB_DEBUG_K
+                if (k == MPPIB_DEBUG_K && kval) {
+                    if (i == 0) {
+                        printf("team t=%d sub=%d nc=%d\n", t, sub, nc);
+                        for (int c = 0; c < nc; ++c) {
+                            const int cb = L.ct0 + c * CTN; const int ids = __float_as_int(xs[cb + CT_IDS]);
+                            printf("  c%d A=%d B=%d p=(%.5f %.5f %.5f) n=(%.4f %.4f %.4f) d=%.6f mu=%.4f\n", c, (ids & 0xFF) - 2, ((ids >> 8) & 0xFF) - 2,
+                                   xs[cb], xs[cb + 1], xs[cb + 2], xs[cb + 3], xs[cb + 4], xs[cb + 5], xs[cb + 6], xs[cb + 7]);
+                        }
+                    }
+                    if (bval) printf("  j%d vp=%.6f invD=%.6f\n", i, vnew, invDc);
+                }
+#endif
+                solve_contacts(kn, bval ? vnew : 0.f, invDc, dq, sub == nsub - 1);
+#ifdef MPPIB_DEBUG_K
+                if (k == MPPIB_DEBUG_K && kval) {
+                    if (i == 0) for (int c = 0; c < nc; ++c) { const int cb = L.ct0 + c * CTN; printf("  c%d ln=%.6f lt1=%.6f lt2=%.6f ikn=%.5f\n", c, xs[cb + CT_LN], xs[cb + CT_LT1], xs[cb + CT_LT2], xs[cb + CT_KN]); }
+                    if (bval) printf("  j%d dq=%.6f\n", i, dq);
+                }
+#endif
+                vnew += dq;
+            }
+            // ---- integrate
+            {
+                float vn = fminf(fmaxf(vnew, -bc.qd_max), bc.qd_max);
+                float x = q + h * vn;
+                if (x < bc.q_lo) { x = bc.q_lo; if (vn < 0.f) vn = 0.f; }
+                if (x > bc.q_hi) { x = bc.q_hi; if (vn > 0.f) vn = 0.f; }
+                if (bval) { q = x; qd = vn; }
+            }
+            if (CONTACT) integrate_free();
+        }
+        if (obs != nullptr) pending = t;
+    }
+    if (pending >= 0) {
+        kinematics<G, R>(bc, tr, q, qd, kn);
+        write_obs(pending, kn);
+    }
+    if (state != nullptr && kval) {
+        if (bval) {
+            state[(size_t)i * K + k] = q;
+            state[(size_t)(nb + i) * K + k] = qd;
+        }
+        if (CONTACT) for (int f = 0; f < m.nfree; ++f)
+            for (int r = i; r < 13; r += G) state[(size_t)(2 * nb + 13 * f + r) * K + k] = xs[L.fb0 + f * FBN + r];
+    }
+}
+
+template <int G, int NB, bool CONTACT>
+int launch_team_t(MppibContext* c, const float* state0, const float* root0, float* state, const float* actions, int t0, int nsteps, float* obs, cudaStream_t s) {
+    const int K = c->params.K;
+    constexpr int RPW = 32 / G;
+    const TLayout L(c->model.nfree, c->model.nshapes, c->model.max_contacts);
+    const size_t smem = CONTACT ? sizeof(float) * (size_t)RPW * team_stride(L.total, G) : 0;
+    MPPIB_REQUIRE(smem <= 200 * 1024, "mppib_rollout: %zu bytes of shared memory per team CTA", smem);
+    static size_t smem_attr[64] = {0};
+    size_t& attr = smem_attr[c->device & 63];
+    if (smem > 48 * 1024 && smem > attr) {
+        MPPIB_CHECK_CUDA(cudaFuncSetAttribute(mppib_rollout_team_kernel<G, NB, CONTACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    const int ctas = (K + RPW - 1) / RPW;
+    mppib_rollout_team_kernel<G, NB, CONTACT><<<ctas, 32, smem, s>>>(c->model, c->params, state0, root0, state, actions, t0, nsteps, obs);
+    MPPIB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+// trees / contact scenes with at most 16 bodies in depth-first order (every subtree a contiguous index range) and depth < 16
+bool rollout_team_eligible(const MppibModel& m) {
+    if (m.nb > 16) return false;
+    for (int i = 0; i < m.nb; ++i) {
+        if (m.parent[i] >= i) return false;
+        int depth = 0;
+        for (int j = i; j >= 0; j = m.parent[j]) ++depth;
+        if (depth > (m.nb <= 8 ? 8 : 16)) return false;
+    }
+    // contiguity: body j > i is a descendant of i  <=>  j < end_i, where end_i = i + size of the subtree
+    for (int i = 0; i < m.nb; ++i) {
+        int size = 0, last = i;
+        for (int j = i; j < m.nb; ++j) {
+            bool desc = false;
+            for (int a = j; a >= 0; a = m.parent[a]) if (a == i) { desc = true; break; }
+            if (desc) { ++size; last = j; }
+        }
+        if (last != i + size - 1) return false;
+    }
+    if (m.planar_base && (m.nb < 3 || m.nu < 2)) return false;
+    return true;
+}
+
+int launch_rollout_team(MppibContext* c, const float* state0, const float* root0, float* state, const float* actions, int t0, int nsteps,
+                        float* obs, cudaStream_t s) {
+    const MppibModel& m = c->model;
+    const bool contact = m.nfree > 0 || m.nshapes > 0;
+    if (contact) MPPIB_REQUIRE(root0 != nullptr, "mppib_rollout: root0 is required for scenes with free bodies / collision shapes");
+#define TEAM_CASE(G, NB)                                                                                             \
+    return contact ? launch_team_t<G, NB, true>(c, state0, root0, state, actions, t0, nsteps, obs, s)                \
+                   : launch_team_t<G, NB, false>(c, state0, root0, state, actions, t0, nsteps, obs, s)
+    if (m.nb <= 4) { TEAM_CASE(8, 4); }
+    if (m.nb <= 8) { TEAM_CASE(8, 8); }
+    if (m.nb <= 12) { TEAM_CASE(16, 12); }
+    TEAM_CASE(16, 16);
+#undef TEAM_CASE
+}

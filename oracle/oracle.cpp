@@ -591,6 +591,10 @@ struct ContactWorld {
             }
         }
     }
+    // A contact row whose effective inverse mass is below K_ROW_MIN [1/kg] is dropped: e.g. a ground-parallel base pressed on from
+    // above, or the vertical friction direction of a wall contact of a planar robot.  (An exact `> 0` would make the row depend on
+    // whether an implementation's rotation arithmetic yields an exact 0 or 1e-9 for such a direction.)
+    static constexpr double K_ROW_MIN = 1e-9;
     void solve(const Articulation<S>& art, S h) {
         const S kp = (S)m->contact_kp, kd = (S)m->contact_kd;
         const S gamma = (S)1 / (h * (h * kp + kd)), beta = h * kp / (h * kp + kd);
@@ -599,7 +603,7 @@ struct ContactWorld {
         for (int i = 0; i < nc; ++i) { Contact<S>& c = ct[i]; c.kn = inv_mass(c, c.n, art); c.kt1 = inv_mass(c, c.t1, art); c.kt2 = inv_mass(c, c.t2, art); }
         for (int it = 0; it < m->contact_iters; ++it) for (int i = 0; i < nc; ++i) {
             Contact<S>& c = ct[i];
-            if (!(c.kn > 0)) continue;
+            if (!(c.kn > (S)K_ROW_MIN)) continue;                     // the bodies cannot move along the normal: no contact row at all
             // one visit = normal row + two friction rows solved from the SAME relative velocity, then one impulse application
             S va[3], vb[3], vr[3];
             point_velocity(c.refA, c.p, art, va); point_velocity(c.refB, c.p, art, vb);
@@ -610,8 +614,8 @@ struct ContactWorld {
             const S bias = c.d > 0 ? std::min(beta * c.d / h, (S)m->max_depen) : c.d / h;
             const S ln_new = std::max((S)0, c.ln + (-vn + bias - gamma * c.ln) / (c.kn + gamma));
             const S lim = c.mu * ln_new;
-            const S lt1_new = c.kt1 > 0 ? std::min(std::max(c.lt1 - vt1 / c.kt1, -lim), lim) : c.lt1;
-            const S lt2_new = c.kt2 > 0 ? std::min(std::max(c.lt2 - vt2 / c.kt2, -lim), lim) : c.lt2;
+            const S lt1_new = c.kt1 > (S)K_ROW_MIN ? std::min(std::max(c.lt1 - vt1 / c.kt1, -lim), lim) : c.lt1;
+            const S lt2_new = c.kt2 > (S)K_ROW_MIN ? std::min(std::max(c.lt2 - vt2 / c.kt2, -lim), lim) : c.lt2;
             S dP[3];
             for (int r = 0; r < 3; ++r) dP[r] = (ln_new - c.ln) * c.n[r] + (lt1_new - c.lt1) * c.t1[r] + (lt2_new - c.lt2) * c.t2[r];
             c.ln = ln_new; c.lt1 = lt1_new; c.lt2 = lt2_new;
