@@ -48,10 +48,14 @@ enum : int { FB_X = 0, FB_Q = 3, FB_V = 7, FB_W = 10, FB_MASS = 13, FB_HALF = 14
 enum : int { SH_R = 0, SH_C = 9, SH_HALF = 12, SH_MU = 15, SH_RAD = 16, SHN = 17 };
 enum : int { CT_P = 0, CT_N = 3, CT_D = 6, CT_MU = 7, CT_LN = 8, CT_LT1 = 9, CT_LT2 = 10, CT_IDS = 11, CT_KN = 12, CT_KT1 = 13, CT_KT2 = 14, CT_T1 = 15, CTN = 18 };
 constexpr float K_ROW_MIN = 1e-9f;     // contact rows with a smaller effective inverse mass [1/kg] are dropped (contact.cuh, oracle.cpp)
+constexpr int MAXS = 4;                 // generalised coordinates per lane in the contact solve: nb + 6 nfree <= G + 24 over G >= 8 lanes
 struct TLayout {
-    int fb0, sh0, ct0, net0, total;
-    __host__ __device__ TLayout(int nfree, int nshapes, int max_contacts) {
-        fb0 = 0; sh0 = fb0 + nfree * FBN; ct0 = sh0 + nshapes * SHN; net0 = ct0 + max_contacts * CTN; total = net0 + 3 * MPPIB_MAX_SLOTS;
+    int fb0, sh0, ct0, net0, rw0, ncs, total;
+    // rw0: contact rows [contact][coordinate slot][n, t1, t2][lane];  ncs: coordinate slots per lane = ceil((nb + 6 nfree) / G)
+    __host__ __device__ TLayout(int nb, int nfree, int nshapes, int max_contacts, int G) {
+        fb0 = 0; sh0 = fb0 + nfree * FBN; ct0 = sh0 + nshapes * SHN; net0 = ct0 + max_contacts * CTN; rw0 = net0 + 3 * MPPIB_MAX_SLOTS;
+        ncs = (nb + 6 * nfree + G - 1) / G;
+        total = rw0 + max_contacts * ncs * 3 * G;
     }
 };
 __host__ __device__ inline int team_stride(int total, int G) { return ((total + 31) & ~31) + G; }   // stride % 32 == G: the teams of a warp start G banks apart
@@ -216,7 +220,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
     const int ib = bval ? i : 0;
     const float h = p.dt / (float)p.substeps;
     const bool vel_mode = m.drive_mode == MPPIB_DRIVE_VELOCITY;
-    const TLayout L(m.nfree, m.nshapes, m.max_contacts);
+    const TLayout L(nb, m.nfree, m.nshapes, m.max_contacts, G);
     float* xs = sm_all + (size_t)team * team_stride(L.total, G);
 
     // ---- tree tables
@@ -300,6 +304,19 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
     // contact pipeline (team-parallel restatement of contact.cuh; the oracle's loop orders are kept)
     // =====================================================================================================================
     const uint32_t kg = p.k_offset + (uint32_t)k;
+    // generalised coordinates of the contact solve held by this lane: coordinate sl * G + i = joint (< nb), else component of a free body
+    const int ncs = L.ncs;
+    int ctype[MAXS], cfb[MAXS], ccomp[MAXS], cref[MAXS];     // 0 none / 1 joint / 2 linear / 3 angular (body axes); free body base, component, ref id
+#pragma unroll
+    for (int sl = 0; sl < MAXS; ++sl) {
+        const int c = sl * G + i;
+        ctype[sl] = 0; cfb[sl] = 0; ccomp[sl] = 0; cref[sl] = -99;
+        if (c < nb) ctype[sl] = 1;
+        else if (c - nb < 6 * m.nfree) {
+            const int f = (c - nb) / 6, comp = (c - nb) % 6;
+            ctype[sl] = comp < 3 ? 2 : 3; ccomp[sl] = comp % 3; cfb[sl] = L.fb0 + f * FBN; cref[sl] = REF_FREE0 + f;
+        }
+    }
     auto refresh_free = [&](int fb) {      // all lanes compute, lane 0 writes
         const Quat fq = {xs[fb + FB_Q], xs[fb + FB_Q + 1], xs[fb + FB_Q + 2], xs[fb + FB_Q + 3]};
         const M3 Rf = quat_to_R(fq);
@@ -543,37 +560,35 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
         }
         __syncwarp(tm);
     };
-    // joint-space row of this lane's joint for a contact on body `ref` at pt along d:  S.f . d + S.n . (pt x d)  if the joint is on
-    // the chain of the body, else 0; `sgn` = +1 on side A, -1 on side B
-    auto jrow = [&](const Kin& kn, float sgn_chain, V3 pt, V3 d) -> float {
-        return sgn_chain * (dot(kn.S.f, d) + dot(kn.S.n, cross(pt, d)));
-    };
+    // ---- Gauss-Seidel soft-constraint solve on the predicted velocities (contact.cuh solve, oracle.cpp ContactWorld::solve) over
+    // GENERALISED COORDINATES, one (or a few) per lane: the nb joints, then per free body its 3 linear velocity components (world) and its
+    // 3 angular velocity components IN BODY AXES -- there the inverse inertia is diagonal like the joints' 1 / D_j, so every coordinate
+    // has ONE scalar inverse inertia `minv` and a contact row is one number per coordinate: J_r (kept in shared memory for the
+    // sweeps).  A visit is then 3 loads + 3 products per coordinate, ONE butterfly all-reduce of the three row velocities, the row
+    // updates (replicated on every lane: no owner lane, no barrier) and 3 FMAs per coordinate.
     auto chain_sign = [&](int refA, int refB) -> float {
-        float s = 0.f;
-        if (refA >= 0 && refA < REF_FREE0 && ((s_anc[refA] >> i) & 1u) && bval) s = 1.f;
-        if (refB >= 0 && refB < REF_FREE0 && ((s_anc[refB] >> i) & 1u) && bval) s = -1.f;
-        return s;
+        float sg = 0.f;
+        if (refA >= 0 && refA < REF_FREE0 && ((s_anc[refA] >> i) & 1u)) sg = 1.f;
+        if (refB >= 0 && refB < REF_FREE0 && ((s_anc[refB] >> i) & 1u)) sg = -1.f;
+        return sg;
     };
-    // free-body part of the effective inverse mass / of the relative velocity (all lanes compute the same numbers)
-    auto free_inv_mass = [&](int ref, V3 pt, V3 dir) -> float {
-        if (ref < REF_FREE0) return 0.f;
-        const int fb = L.fb0 + (ref - REF_FREE0) * FBN;
-        const V3 r = pt - ld3(xs, fb + FB_X);
-        const V3 rxn = cross(r, dir);
-        const S3 Iw = {xs[fb + FB_IW], xs[fb + FB_IW + 1], xs[fb + FB_IW + 2], xs[fb + FB_IW + 3], xs[fb + FB_IW + 4], xs[fb + FB_IW + 5]};
-        return xs[fb + FB_MASS] + dot(cross(mul(Iw, rxn), r), dir);
-    };
-    auto free_velocity = [&](int ref, V3 pt) -> V3 {
-        if (ref < REF_FREE0) return mk(0.f, 0.f, 0.f);
-        const int fb = L.fb0 + (ref - REF_FREE0) * FBN;
-        return ld3(xs, fb + FB_V) + cross(ld3(xs, fb + FB_W), pt - ld3(xs, fb + FB_X));
-    };
-    // Gauss-Seidel soft-constraint solve on the predicted velocities (contact.cuh solve): vp = predicted qd of this lane's joint,
-    // dq = its velocity correction (in / out), invD = 1 / D_j
-    auto solve_contacts = [&](const Kin& kn, float vp, float invD, float& dq, bool last_substep) {
+    auto solve_contacts = [&](const Kin& kn, float& vjoint, float invD, bool last_substep) {
         const float kp = m.contact_kp, kdc = m.contact_kd;
         const float gamma = 1.0f / (h * (h * kp + kdc)), beta = h * kp / (h * kp + kdc), ih = 1.0f / h;
-        for (int c = 0; c < nc; ++c) {                       // per contact, once: tangent frame, inverse effective masses, bias velocity
+        float vel[MAXS], minv[MAXS];
+#pragma unroll
+        for (int sl = 0; sl < MAXS; ++sl) {
+            vel[sl] = 0.f; minv[sl] = 0.f;
+            if (sl >= ncs) continue;
+            if (ctype[sl] == 1) { vel[sl] = vjoint; minv[sl] = invD; }
+            else if (ctype[sl] == 2) { vel[sl] = xs[cfb[sl] + FB_V + ccomp[sl]]; minv[sl] = xs[cfb[sl] + FB_MASS]; }
+            else if (ctype[sl] == 3) {
+                const int fb = cfb[sl], cc = ccomp[sl];
+                vel[sl] = xs[fb + FB_R + cc] * xs[fb + FB_W] + xs[fb + FB_R + 3 + cc] * xs[fb + FB_W + 1] + xs[fb + FB_R + 6 + cc] * xs[fb + FB_W + 2];
+                minv[sl] = xs[fb + FB_IINV + cc];
+            }
+        }
+        for (int c = 0; c < nc; ++c) {                       // per contact, once: tangent frame, rows, inverse effective masses, bias velocity
             const int cb = L.ct0 + c * CTN;
             const int ids = __float_as_int(xs[cb + CT_IDS]);
             const int refA = (ids & 0xFF) - 2, refB = ((ids >> 8) & 0xFF) - 2;
@@ -582,12 +597,31 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             V3 t1 = cross(n, e);
             t1 = scale(rsqrtf(dot(t1, t1)), t1);
             const V3 t2 = cross(n, t1);
-            const float sg = chain_sign(refA, refB);
-            const float jn = jrow(kn, sg, pt, n), j1 = jrow(kn, sg, pt, t1), j2 = jrow(kn, sg, pt, t2);
-            float kn_ = team_sum<G>(jn * jn * invD, tm), kt1 = team_sum<G>(j1 * j1 * invD, tm), kt2 = team_sum<G>(j2 * j2 * invD, tm);
-            kn_ += free_inv_mass(refA, pt, n) + free_inv_mass(refB, pt, n);
-            kt1 += free_inv_mass(refA, pt, t1) + free_inv_mass(refB, pt, t1);
-            kt2 += free_inv_mass(refA, pt, t2) + free_inv_mass(refB, pt, t2);
+            float kn_ = 0.f, kt1 = 0.f, kt2 = 0.f;
+#pragma unroll
+            for (int sl = 0; sl < MAXS; ++sl) {
+                if (sl >= ncs) continue;
+                float jn = 0.f, j1 = 0.f, j2 = 0.f;
+                if (ctype[sl] == 1) {
+                    const float sg = chain_sign(refA, refB);
+                    const V3 mn = cross(pt, n), m1 = cross(pt, t1), m2 = cross(pt, t2);
+                    jn = sg * (dot(kn.S.f, n) + dot(kn.S.n, mn)); j1 = sg * (dot(kn.S.f, t1) + dot(kn.S.n, m1)); j2 = sg * (dot(kn.S.f, t2) + dot(kn.S.n, m2));
+                } else if (ctype[sl] >= 2) {
+                    const float sg = refA == cref[sl] ? 1.f : (refB == cref[sl] ? -1.f : 0.f);
+                    const int fb = cfb[sl], cc = ccomp[sl];
+                    if (ctype[sl] == 2) {
+                        jn = sg * (cc == 0 ? n.x : (cc == 1 ? n.y : n.z)); j1 = sg * (cc == 0 ? t1.x : (cc == 1 ? t1.y : t1.z)); j2 = sg * (cc == 0 ? t2.x : (cc == 1 ? t2.y : t2.z));
+                    } else {
+                        const V3 r = pt - ld3(xs, fb + FB_X);
+                        const V3 col = mk(xs[fb + FB_R + cc], xs[fb + FB_R + 3 + cc], xs[fb + FB_R + 6 + cc]);      // body axis cc in the world
+                        jn = sg * dot(col, cross(r, n)); j1 = sg * dot(col, cross(r, t1)); j2 = sg * dot(col, cross(r, t2));
+                    }
+                }
+                float* rw = xs + L.rw0 + ((c * ncs + sl) * 3) * G + i;
+                rw[0] = jn; rw[G] = j1; rw[2 * G] = j2;
+                kn_ = fmaf(jn * jn, minv[sl], kn_); kt1 = fmaf(j1 * j1, minv[sl], kt1); kt2 = fmaf(j2 * j2, minv[sl], kt2);
+            }
+            kn_ = team_sum<G>(kn_, tm); kt1 = team_sum<G>(kt1, tm); kt2 = team_sum<G>(kt2, tm);
             const float d = xs[cb + CT_D];
             __syncwarp(tm);
             if (i == 0) {
@@ -604,47 +638,51 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
                 const int cb = L.ct0 + c * CTN;
                 const float ikn = xs[cb + CT_KN];
                 if (!(ikn > 0.f)) continue;                  // team-uniform
-                const int ids = __float_as_int(xs[cb + CT_IDS]);
-                const int refA = (ids & 0xFF) - 2, refB = ((ids >> 8) & 0xFF) - 2;
-                const V3 pt = ld3(xs, cb + CT_P), n = ld3(xs, cb + CT_N), t1 = ld3(xs, cb + CT_T1);
-                const V3 t2 = cross(n, t1);
                 const float bias = xs[cb + CT_D], mu = xs[cb + CT_MU], ikt1 = xs[cb + CT_KT1], ikt2 = xs[cb + CT_KT2];
-                const float sg = chain_sign(refA, refB);
-                const float jn = jrow(kn, sg, pt, n), j1 = jrow(kn, sg, pt, t1), j2 = jrow(kn, sg, pt, t2);
-                const float vj = vp + dq;
-                // relative velocity along the contact frame: the joints' parts by an all-reduce, the free bodies' parts directly
-                const V3 vfree = free_velocity(refA, pt) - free_velocity(refB, pt);
-                const float vn = team_sum<G>(jn * vj, tm) + dot(vfree, n);
-                const float v1 = team_sum<G>(j1 * vj, tm) + dot(vfree, t1);
-                const float v2 = team_sum<G>(j2 * vj, tm) + dot(vfree, t2);
                 const float ln = xs[cb + CT_LN], lt1 = xs[cb + CT_LT1], lt2 = xs[cb + CT_LT2];
+                float jn[MAXS], j1[MAXS], j2[MAXS];
+                float vn = 0.f, v1 = 0.f, v2 = 0.f;
+#pragma unroll
+                for (int sl = 0; sl < MAXS; ++sl) {
+                    jn[sl] = j1[sl] = j2[sl] = 0.f;
+                    if (sl >= ncs) continue;
+                    const float* rw = xs + L.rw0 + ((c * ncs + sl) * 3) * G + i;
+                    jn[sl] = rw[0]; j1[sl] = rw[G]; j2[sl] = rw[2 * G];
+                    vn = fmaf(jn[sl], vel[sl], vn); v1 = fmaf(j1[sl], vel[sl], v1); v2 = fmaf(j2[sl], vel[sl], v2);
+                }
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) {        // relative velocity along the contact frame: one butterfly for the three rows
+                    vn += __shfl_xor_sync(tm, vn, o, G); v1 += __shfl_xor_sync(tm, v1, o, G); v2 += __shfl_xor_sync(tm, v2, o, G);
+                }
                 const float ln_new = fmaxf(0.f, ln + (-vn + bias - gamma * ln) * ikn);
                 const float lim = mu * ln_new;
                 const float lt1_new = ikt1 > 0.f ? fminf(fmaxf(lt1 - v1 * ikt1, -lim), lim) : lt1;
                 const float lt2_new = ikt2 > 0.f ? fminf(fmaxf(lt2 - v2 * ikt2, -lim), lim) : lt2;
                 const float dn = ln_new - ln, d1 = lt1_new - lt1, d2 = lt2_new - lt2;
-                dq += invD * (jn * dn + j1 * d1 + j2 * d2);  // this lane's joint (0 when it is not on the contact's chain)
-                __syncwarp(tm);                                // every lane has read the contact and the free bodies
-                if (i == 0) {
-                    xs[cb + CT_LN] = ln_new; xs[cb + CT_LT1] = lt1_new; xs[cb + CT_LT2] = lt2_new;
-                    const V3 P = scale(dn, n) + scale(d1, t1) + scale(d2, t2);
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int ref = e == 0 ? refA : refB;
-                        if (ref < REF_FREE0) continue;
-                        const float sgn = e == 0 ? 1.0f : -1.0f;
-                        const int fb = L.fb0 + (ref - REF_FREE0) * FBN;
-                        const V3 r = pt - ld3(xs, fb + FB_X);
-                        const float im = sgn * xs[fb + FB_MASS];
-                        xs[fb + FB_V] += im * P.x; xs[fb + FB_V + 1] += im * P.y; xs[fb + FB_V + 2] += im * P.z;
-                        const S3 Iw = {xs[fb + FB_IW], xs[fb + FB_IW + 1], xs[fb + FB_IW + 2], xs[fb + FB_IW + 3], xs[fb + FB_IW + 4], xs[fb + FB_IW + 5]};
-                        const V3 dw = mul(Iw, cross(r, P));
-                        xs[fb + FB_W] += sgn * dw.x; xs[fb + FB_W + 1] += sgn * dw.y; xs[fb + FB_W + 2] += sgn * dw.z;
-                    }
-                }
-                __syncwarp(tm);
+                for (int sl = 0; sl < MAXS; ++sl) if (sl < ncs) vel[sl] = fmaf(minv[sl], fmaf(jn[sl], dn, fmaf(j1[sl], d1, j2[sl] * d2)), vel[sl]);
+                // every lane stores the same three numbers and later reads back what it stored itself: no owner lane, no barrier
+                xs[cb + CT_LN] = ln_new; xs[cb + CT_LT1] = lt1_new; xs[cb + CT_LT2] = lt2_new;
             }
         }
+        // ---- back to the bodies: joints keep their lane's value; free bodies: linear components, then omega = R omega_body
+        __syncwarp(tm);
+#pragma unroll
+        for (int sl = 0; sl < MAXS; ++sl) {
+            if (sl >= ncs) continue;
+            if (ctype[sl] == 1) vjoint = vel[sl];
+            else if (ctype[sl] == 2) xs[cfb[sl] + FB_V + ccomp[sl]] = vel[sl];
+            else if (ctype[sl] == 3) xs[cfb[sl] + FB_W + ccomp[sl]] = vel[sl];       // (body axes for a moment)
+        }
+        __syncwarp(tm);
+        for (int f = 0; f < m.nfree; ++f) {
+            const int fb = L.fb0 + f * FBN;
+            const V3 wb = ld3(xs, fb + FB_W);
+            const M3 Rf = ldM3(xs, fb + FB_R);
+            __syncwarp(tm);
+            if (i == 0) st3(xs, fb + FB_W, mulM(Rf, wb));
+        }
+        __syncwarp(tm);
         if (last_substep) {                                  // net contact force per body = the last substep's impulses / h
             if (i == 0) {
                 for (int s = 0; s < 3 * MPPIB_MAX_SLOTS; ++s) xs[L.net0 + s] = 0.f;
@@ -851,7 +889,6 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             float vnew = qd + h * qdd;
             if (CONTACT) {
                 // ---- contacts on the predicted velocities
-                float dq = 0.f;
                 shapes_world(kn, false);
                 detect();
                 if (i == 0) for (int f = 0; f < m.nfree; ++f) if (m.free_gravity[f]) {
@@ -873,14 +910,14 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
                     if (bval) printf("  j%d vp=%.6f invD=%.6f\n", i, vnew, invDc);
                 }
 #endif
-                solve_contacts(kn, bval ? vnew : 0.f, invDc, dq, sub == nsub - 1);
+                if (!bval) vnew = 0.f;
+                solve_contacts(kn, vnew, invDc, sub == nsub - 1);
 #ifdef MPPIB_DEBUG_K
                 if (k == MPPIB_DEBUG_K && kval) {
                     if (i == 0) for (int c = 0; c < nc; ++c) { const int cb = L.ct0 + c * CTN; printf("  c%d ln=%.6f lt1=%.6f lt2=%.6f ikn=%.5f\n", c, xs[cb + CT_LN], xs[cb + CT_LT1], xs[cb + CT_LT2], xs[cb + CT_KN]); }
-                    if (bval) printf("  j%d dq=%.6f\n", i, dq);
+                    if (bval) printf("  j%d v=%.6f\n", i, vnew);
                 }
 #endif
-                vnew += dq;
             }
             // ---- integrate
             {
@@ -912,7 +949,7 @@ template <int G, int NB, bool CONTACT>
 int launch_team_t(MppibContext* c, const float* state0, const float* root0, float* state, const float* actions, int t0, int nsteps, float* obs, cudaStream_t s) {
     const int K = c->params.K;
     constexpr int RPW = 32 / G;
-    const TLayout L(c->model.nfree, c->model.nshapes, c->model.max_contacts);
+    const TLayout L(c->model.nb, c->model.nfree, c->model.nshapes, c->model.max_contacts, G);
     const size_t smem = CONTACT ? sizeof(float) * (size_t)RPW * team_stride(L.total, G) : 0;
     MPPIB_REQUIRE(smem <= 200 * 1024, "mppib_rollout: %zu bytes of shared memory per team CTA", smem);
     static size_t smem_attr[64] = {0};
