@@ -46,16 +46,17 @@ __device__ __forceinline__ M3 mulMM(const M3& a, const M3& b) {
 enum : int { REF_STATIC = -1, REF_FREE0 = 64 };
 enum : int { FB_X = 0, FB_Q = 3, FB_V = 7, FB_W = 10, FB_MASS = 13, FB_HALF = 14, FB_IINV = 17, FB_R = 20, FB_IW = 29, FBN = 35 };   // FB_MASS: inverse mass
 enum : int { SH_R = 0, SH_C = 9, SH_HALF = 12, SH_MU = 15, SH_RAD = 16, SHN = 17 };
-enum : int { CT_P = 0, CT_N = 3, CT_D = 6, CT_MU = 7, CT_LN = 8, CT_LT1 = 9, CT_LT2 = 10, CT_IDS = 11, CT_KN = 12, CT_KT1 = 13, CT_KT2 = 14, CT_T1 = 15, CTN = 18 };
+// contact record, 16-byte groups: [ln lt1 lt2 mu] the state of the sweeps | [bias 1/(kn+gamma) 1/kt1 1/kt2] their constants | [p ids] [n -] [t1 -]
+enum : int { CT_LN = 0, CT_LT1 = 1, CT_LT2 = 2, CT_MU = 3, CT_D = 4, CT_KN = 5, CT_KT1 = 6, CT_KT2 = 7, CT_P = 8, CT_IDS = 11, CT_N = 12, CT_T1 = 16, CTN = 20 };
 constexpr float K_ROW_MIN = 1e-9f;     // contact rows with a smaller effective inverse mass [1/kg] are dropped (contact.cuh, oracle.cpp)
-constexpr int MAXS = 4;                 // generalised coordinates per lane in the contact solve: nb + 6 nfree <= G + 24 over G >= 8 lanes
+constexpr int MAXS_ALL = 4;                 // generalised coordinates per lane in the contact solve: nb + 6 nfree <= G + 24 over G >= 8 lanes
 struct TLayout {
     int fb0, sh0, ct0, net0, rw0, ncs, total;
-    // rw0: contact rows [contact][coordinate slot][n, t1, t2][lane];  ncs: coordinate slots per lane = ceil((nb + 6 nfree) / G)
+    // rw0: contact rows [contact][coordinate] of float4 (n, t1, t2, -);  ncs: coordinate slots per lane = ceil((nb + 6 nfree) / G)
     __host__ __device__ TLayout(int nb, int nfree, int nshapes, int max_contacts, int G) {
-        fb0 = 0; sh0 = fb0 + nfree * FBN; ct0 = sh0 + nshapes * SHN; net0 = ct0 + max_contacts * CTN; rw0 = net0 + 3 * MPPIB_MAX_SLOTS;
+        fb0 = 0; sh0 = fb0 + nfree * FBN; ct0 = (sh0 + nshapes * SHN + 3) & ~3; net0 = ct0 + max_contacts * CTN; rw0 = net0 + 3 * MPPIB_MAX_SLOTS;
         ncs = (nb + 6 * nfree + G - 1) / G;
-        total = rw0 + max_contacts * ncs * 3 * G;
+        total = rw0 + max_contacts * (nb + 6 * nfree) * 4;
     }
 };
 __host__ __device__ inline int team_stride(int total, int G) { return ((total + 31) & ~31) + G; }   // stride % 32 == G: the teams of a warp start G banks apart
@@ -196,14 +197,15 @@ __device__ __forceinline__ void kinematics(const BodyConst& bc, const Tree<R>& t
 }
 
 // G lanes per rollout, NB >= nb joint-space rows (compile time), CONTACT: free bodies / collision shapes present
-template <int G, int NB, bool CONTACT>
+template <int G, int NB, bool CONTACT, int NCS>
 __global__ void __launch_bounds__(32)
 mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_constant__ MppibParams p,
                           const float* __restrict__ state0, const float* __restrict__ root0, float* __restrict__ state,
                           const float* __restrict__ actions, int t0, int nsteps, float* __restrict__ obs) {
     constexpr int RPW = 32 / G;
     constexpr int R = (G == 16) ? 4 : ((G == 8) ? 3 : 2);        // rounds of pointer jumping: depth < 2^R
-    extern __shared__ float sm_all[];
+    extern __shared__ float4 sm_all4[];
+    float* sm_all = reinterpret_cast<float*>(sm_all4);
     __shared__ uint32_t s_bmask[MPPIB_MAX_SHAPES];               // candidate partners of every shape
     __shared__ uint32_t s_anc[MPPIB_MAX_BODIES];                 // ancestor-or-self mask of every body (the chain of a contact's link)
     const int K = p.K, T = p.T, nu = m.nu, nb = m.nb;
@@ -305,7 +307,8 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
     // =====================================================================================================================
     const uint32_t kg = p.k_offset + (uint32_t)k;
     // generalised coordinates of the contact solve held by this lane: coordinate sl * G + i = joint (< nb), else component of a free body
-    const int ncs = L.ncs;
+    constexpr int MAXS = NCS;
+    constexpr int ncs = NCS;                                 // (== L.ncs, checked by the launcher)
     int ctype[MAXS], cfb[MAXS], ccomp[MAXS], cref[MAXS];     // 0 none / 1 joint / 2 linear / 3 angular (body axes); free body base, component, ref id
 #pragma unroll
     for (int sl = 0; sl < MAXS; ++sl) {
@@ -576,6 +579,8 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
         const float kp = m.contact_kp, kdc = m.contact_kd;
         const float gamma = 1.0f / (h * (h * kp + kdc)), beta = h * kp / (h * kp + kdc), ih = 1.0f / h;
         float vel[MAXS], minv[MAXS];
+        float4* rows = reinterpret_cast<float4*>(xs + L.rw0);
+        const int ncoord = nb + 6 * m.nfree;
 #pragma unroll
         for (int sl = 0; sl < MAXS; ++sl) {
             vel[sl] = 0.f; minv[sl] = 0.f;
@@ -617,8 +622,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
                         jn = sg * dot(col, cross(r, n)); j1 = sg * dot(col, cross(r, t1)); j2 = sg * dot(col, cross(r, t2));
                     }
                 }
-                float* rw = xs + L.rw0 + ((c * ncs + sl) * 3) * G + i;
-                rw[0] = jn; rw[G] = j1; rw[2 * G] = j2;
+                if (sl * G + i < ncoord) rows[c * ncoord + sl * G + i] = make_float4(jn, j1, j2, 0.f);
                 kn_ = fmaf(jn * jn, minv[sl], kn_); kt1 = fmaf(j1 * j1, minv[sl], kt1); kt2 = fmaf(j2 * j2, minv[sl], kt2);
             }
             kn_ = team_sum<G>(kn_, tm); kt1 = team_sum<G>(kt1, tm); kt2 = team_sum<G>(kt2, tm);
@@ -633,37 +637,48 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             }
         }
         __syncwarp(tm);
-        for (int it = 0; it < m.contact_iters; ++it) {
-            for (int c = 0; c < nc; ++c) {
-                const int cb = L.ct0 + c * CTN;
-                const float ikn = xs[cb + CT_KN];
-                if (!(ikn > 0.f)) continue;                  // team-uniform
-                const float bias = xs[cb + CT_D], mu = xs[cb + CT_MU], ikt1 = xs[cb + CT_KT1], ikt2 = xs[cb + CT_KT2];
-                const float ln = xs[cb + CT_LN], lt1 = xs[cb + CT_LT1], lt2 = xs[cb + CT_LT2];
-                float jn[MAXS], j1[MAXS], j2[MAXS];
+        // the sweeps: contact_iters x nc visits in one flat loop; the constants and rows of the NEXT visit are fetched while this one
+        // reduces (they do not change during the sweeps; the multipliers do and are loaded by the visit itself)
+        const int nvisit = nc > 0 ? m.contact_iters * nc : 0;
+        float4 Bc = make_float4(0.f, 0.f, 0.f, 0.f), Rc[MAXS];
+        if (nc > 0) {
+            Bc = *reinterpret_cast<const float4*>(xs + L.ct0 + CT_D);
+#pragma unroll
+            for (int sl = 0; sl < MAXS; ++sl) Rc[sl] = (sl + 1 < MAXS || sl * G + i < ncoord) ? rows[sl * G + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        int c = 0;
+#pragma unroll 1
+        for (int v = 0; v < nvisit; ++v) {
+            const int cb = L.ct0 + c * CTN;
+            const int cnx = c + 1 == nc ? 0 : c + 1;
+            const float4 Bn = *reinterpret_cast<const float4*>(xs + L.ct0 + cnx * CTN + CT_D);
+            float4 Rn[MAXS];
+#pragma unroll
+            for (int sl = 0; sl < MAXS; ++sl) Rn[sl] = (sl + 1 < MAXS || sl * G + i < ncoord) ? rows[cnx * ncoord + sl * G + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float bias = Bc.x, ikn = Bc.y, ikt1 = Bc.z, ikt2 = Bc.w;
+            if (ikn > 0.f) {                                 // team-uniform
+                const float4 A = *reinterpret_cast<const float4*>(xs + cb);              // ln lt1 lt2 mu
                 float vn = 0.f, v1 = 0.f, v2 = 0.f;
 #pragma unroll
-                for (int sl = 0; sl < MAXS; ++sl) {
-                    jn[sl] = j1[sl] = j2[sl] = 0.f;
-                    if (sl >= ncs) continue;
-                    const float* rw = xs + L.rw0 + ((c * ncs + sl) * 3) * G + i;
-                    jn[sl] = rw[0]; j1[sl] = rw[G]; j2[sl] = rw[2 * G];
-                    vn = fmaf(jn[sl], vel[sl], vn); v1 = fmaf(j1[sl], vel[sl], v1); v2 = fmaf(j2[sl], vel[sl], v2);
-                }
+                for (int sl = 0; sl < MAXS; ++sl) { vn = fmaf(Rc[sl].x, vel[sl], vn); v1 = fmaf(Rc[sl].y, vel[sl], v1); v2 = fmaf(Rc[sl].z, vel[sl], v2); }
 #pragma unroll
                 for (int o = G / 2; o > 0; o >>= 1) {        // relative velocity along the contact frame: one butterfly for the three rows
                     vn += __shfl_xor_sync(tm, vn, o, G); v1 += __shfl_xor_sync(tm, v1, o, G); v2 += __shfl_xor_sync(tm, v2, o, G);
                 }
-                const float ln_new = fmaxf(0.f, ln + (-vn + bias - gamma * ln) * ikn);
-                const float lim = mu * ln_new;
-                const float lt1_new = ikt1 > 0.f ? fminf(fmaxf(lt1 - v1 * ikt1, -lim), lim) : lt1;
-                const float lt2_new = ikt2 > 0.f ? fminf(fmaxf(lt2 - v2 * ikt2, -lim), lim) : lt2;
-                const float dn = ln_new - ln, d1 = lt1_new - lt1, d2 = lt2_new - lt2;
+                const float ln_new = fmaxf(0.f, A.x + (-vn + bias - gamma * A.x) * ikn);
+                const float lim = A.w * ln_new;
+                const float lt1_new = ikt1 > 0.f ? fminf(fmaxf(A.y - v1 * ikt1, -lim), lim) : A.y;
+                const float lt2_new = ikt2 > 0.f ? fminf(fmaxf(A.z - v2 * ikt2, -lim), lim) : A.z;
+                const float dn = ln_new - A.x, d1 = lt1_new - A.y, d2 = lt2_new - A.z;
 #pragma unroll
-                for (int sl = 0; sl < MAXS; ++sl) if (sl < ncs) vel[sl] = fmaf(minv[sl], fmaf(jn[sl], dn, fmaf(j1[sl], d1, j2[sl] * d2)), vel[sl]);
-                // every lane stores the same three numbers and later reads back what it stored itself: no owner lane, no barrier
-                xs[cb + CT_LN] = ln_new; xs[cb + CT_LT1] = lt1_new; xs[cb + CT_LT2] = lt2_new;
+                for (int sl = 0; sl < MAXS; ++sl) vel[sl] = fmaf(minv[sl], fmaf(Rc[sl].x, dn, fmaf(Rc[sl].y, d1, Rc[sl].z * d2)), vel[sl]);
+                // every lane stores the same numbers and later reads back what it stored itself: no owner lane, no barrier
+                *reinterpret_cast<float4*>(xs + cb) = make_float4(ln_new, lt1_new, lt2_new, A.w);
             }
+            Bc = Bn;
+#pragma unroll
+            for (int sl = 0; sl < MAXS; ++sl) Rc[sl] = Rn[sl];
+            c = cnx;
         }
         // ---- back to the bodies: joints keep their lane's value; free bodies: linear components, then omega = R omega_body
         __syncwarp(tm);
@@ -945,7 +960,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
     }
 }
 
-template <int G, int NB, bool CONTACT>
+template <int G, int NB, bool CONTACT, int NCS>
 int launch_team_t(MppibContext* c, const float* state0, const float* root0, float* state, const float* actions, int t0, int nsteps, float* obs, cudaStream_t s) {
     const int K = c->params.K;
     constexpr int RPW = 32 / G;
@@ -955,13 +970,28 @@ int launch_team_t(MppibContext* c, const float* state0, const float* root0, floa
     static size_t smem_attr[64] = {0};
     size_t& attr = smem_attr[c->device & 63];
     if (smem > 48 * 1024 && smem > attr) {
-        MPPIB_CHECK_CUDA(cudaFuncSetAttribute(mppib_rollout_team_kernel<G, NB, CONTACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MPPIB_CHECK_CUDA(cudaFuncSetAttribute(mppib_rollout_team_kernel<G, NB, CONTACT, NCS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
     const int ctas = (K + RPW - 1) / RPW;
-    mppib_rollout_team_kernel<G, NB, CONTACT><<<ctas, 32, smem, s>>>(c->model, c->params, state0, root0, state, actions, t0, nsteps, obs);
+    mppib_rollout_team_kernel<G, NB, CONTACT, NCS><<<ctas, 32, smem, s>>>(c->model, c->params, state0, root0, state, actions, t0, nsteps, obs);
     MPPIB_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+// coordinate slots per lane of the contact solve (compile time): ceil((nb + 6 nfree) / G)
+template <int G, int NB>
+int launch_team_g(MppibContext* c, bool contact, const float* state0, const float* root0, float* state, const float* actions, int t0, int nsteps, float* obs,
+                  cudaStream_t s) {
+    if (!contact) return launch_team_t<G, NB, false, 1>(c, state0, root0, state, actions, t0, nsteps, obs, s);
+    const int ncs = (c->model.nb + 6 * c->model.nfree + G - 1) / G;
+    switch (ncs) {
+        case 1: return launch_team_t<G, NB, true, 1>(c, state0, root0, state, actions, t0, nsteps, obs, s);
+        case 2: return launch_team_t<G, NB, true, 2>(c, state0, root0, state, actions, t0, nsteps, obs, s);
+        case 3: return launch_team_t<G, NB, true, 3>(c, state0, root0, state, actions, t0, nsteps, obs, s);
+        default: MPPIB_REQUIRE(ncs <= MAXS_ALL, "mppib_rollout: %d coordinate slots per lane", ncs);
+                 return launch_team_t<G, NB, true, 4>(c, state0, root0, state, actions, t0, nsteps, obs, s);
+    }
 }
 
 }  // namespace
@@ -994,9 +1024,7 @@ int launch_rollout_team(MppibContext* c, const float* state0, const float* root0
     const MppibModel& m = c->model;
     const bool contact = m.nfree > 0 || m.nshapes > 0;
     if (contact) MPPIB_REQUIRE(root0 != nullptr, "mppib_rollout: root0 is required for scenes with free bodies / collision shapes");
-#define TEAM_CASE(G, NB)                                                                                             \
-    return contact ? launch_team_t<G, NB, true>(c, state0, root0, state, actions, t0, nsteps, obs, s)                \
-                   : launch_team_t<G, NB, false>(c, state0, root0, state, actions, t0, nsteps, obs, s)
+#define TEAM_CASE(G, NB) return launch_team_g<G, NB>(c, contact, state0, root0, state, actions, t0, nsteps, obs, s)
     if (m.nb <= 4) { TEAM_CASE(8, 4); }
     if (m.nb <= 8) { TEAM_CASE(8, 8); }
     if (m.nb <= 12) { TEAM_CASE(16, 12); }
