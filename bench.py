@@ -571,7 +571,7 @@ def run_gpu_arm(args, rank, world, local_rank):
             "gpu_config": {"K_per_gpu": planner.sim.num_envs, "baseline_gpus": C["baseline_gpus"],
                            "exchange": "none" if world == 1 else ("peer-memory stores fused into K3 (NVLink), flags acquired by K4" if planner.mppi._peer_exchange else "NCCL all-gather"),
                            "cuda_graph": graph_on, "l2": "flushed (256 MiB write) before every timed plan",
-                           "k2_mapping": "lanes-per-rollout (rollout_lanes.cu)" if os.environ.get("MPPIB_K2_LANES", "1") != "0" and name == "c2" else "thread-per-rollout (rollout.cu)",
+                           "k2_mapping": planner.mppi.backend.rollout_mapping(),
                            "ms_per_step_p10_p50_p90_max": [float(np.percentile(per_step_ms, p)) for p in (10, 50, 90, 100)],
                            "slowest_steps": sorted(range(len(per_step_ms)), key=lambda i: -per_step_ms[i])[:3]},
             "e2e": e2e,

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MPPIB_ABI_VERSION 11
+#define MPPIB_ABI_VERSION 12
 
 #define MPPIB_MAX_BODIES 16   /* moving (1-DoF) bodies of the articulation            */
 #define MPPIB_MAX_LINKS  32   /* URDF links whose state can be observed               */
@@ -287,6 +287,15 @@ int32_t mppib_cost_pose(int64_t n, const float* a, int64_t a_si, int64_t a_sr, c
 /* Shared-memory bytes one 32-rollout CTA of mppib_rollout needs for this model (host-side arithmetic, no device access):
  * lets the model compiler size `max_contacts` to what fits an SM (226 KB usable) before a handle exists.                     */
 int64_t mppib_rollout_smem_bytes(const MppibModel* model_h);
+
+/* Which rollout kernel mppib_rollout launches for this handle's model and K (diagnostics / benchmark reporting; the result of the
+ * rollout does not depend on it beyond float32 rounding -- every mapping is tested against the same oracle):
+ * one thread per rollout, one articulation body per lane (serial chains without contacts), or a team of lanes per rollout
+ * (trees; contact scenes of small robots).  Environment MPPIB_K2_LANES=0, MPPIB_K2_TEAM=0|1 force a mapping.               */
+#define MPPIB_MAPPING_THREAD 0
+#define MPPIB_MAPPING_LANES  1
+#define MPPIB_MAPPING_TEAM   2
+int32_t mppib_rollout_mapping(MppibHandle h);
 
 /* Optional host mirror of the action: when set, mppib_finalize also stores action_out[0..nu) to `mirror` -- a pointer into
  * PINNED host memory (device-addressable under unified addressing), so the caller of the reference's compute_action* only

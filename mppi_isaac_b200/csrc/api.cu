@@ -92,8 +92,8 @@ int32_t mppib_create(const MppibModel* model_h, const MppibParams* params_h, int
     c->num_sms = prop.multiProcessorCount;
     c->k2_lanes = 1;
     if (const char* e = getenv("MPPIB_K2_LANES")) c->k2_lanes = atoi(e) != 0;   // read once per handle, not per launch
-    c->k2_team = 0;
-    if (const char* e = getenv("MPPIB_K2_TEAM")) c->k2_team = atoi(e) != 0;
+    c->k2_team = -1;
+    if (const char* e = getenv("MPPIB_K2_TEAM")) c->k2_team = atoi(e) < 0 ? -1 : (atoi(e) != 0);
     c->k2_pairs = -1;
     if (const char* e = getenv("MPPIB_K2_PAIRS")) c->k2_pairs = atoi(e) != 0;
     c->k3_variant = (getenv("MPPIB_K3_VARIANT") || getenv("MPPIB_K3_WIDE") || getenv("MPPIB_K3_GRID")) ? 1 : 0;
@@ -247,6 +247,11 @@ int32_t mppib_finalize(MppibHandle h, const float* partials, int32_t G, float* U
     }
     MPPIB_ON_DEVICE(h);
     return launch_finalize(h, partials, G, U, action_out, stats, (cudaStream_t)stream);
+}
+
+int32_t mppib_rollout_mapping(MppibHandle h) {
+    MPPIB_REQUIRE(h != nullptr, "null handle");
+    return rollout_mapping(h);
 }
 
 int64_t mppib_rollout_smem_bytes(const MppibModel* model_h) {

@@ -47,7 +47,8 @@ struct MppibContext {
     float* action_mirror;                      // pinned host mirror of the action written by K4 (nullable)
     int k3_variant;                            // 0 = warp-specialised K3 (default), 1 = block-synchronous K3 (MPPIB_K3_VARIANT / _WIDE / _GRID knobs)
     int k2_pairs;                              // lanes kernel: -1 = choose by K (default), 0 / 1 = force one / two rollouts per lane group (MPPIB_K2_PAIRS)
-    int k2_team;                               // K2 mapping for trees / contact scenes: 1 = a team of lanes per rollout (rollout_team.cu), 0 = one thread per rollout
+    int k2_team;                               // K2 mapping for trees / contact scenes: 1 = a team of lanes per rollout (rollout_team.cu), 0 = one thread per
+                                               // rollout, -1 = choose by scene and K (default; rollout_mapping())
     int k2_lanes;                              // K2 mapping for eligible scenes: 1 = one body per lane (default), 0 = one thread per rollout
 };
 
@@ -103,6 +104,8 @@ long long rollout_smem_bytes(const MppibModel& m);
 bool rollout_lanes_eligible(const MppibModel& m);
 // K2, team-of-lanes mapping for trees and scenes with contacts (rollout_team.cu)
 bool rollout_team_eligible(const MppibModel& m);
+// which kernel mppib_rollout launches for this handle: MPPIB_MAPPING_* (include/mppib.h)
+int rollout_mapping(const MppibContext* c);
 int launch_rollout_team(MppibContext* c, const float* state0, const float* root0, float* state, const float* actions, int t0, int nsteps,
                         float* obs, cudaStream_t s);
 int launch_rollout_lanes(MppibContext* c, const float* state0, float* state, const float* actions, int t0, int nsteps, float* obs,

@@ -585,15 +585,31 @@ int launch_t(MppibContext* c, const float* state0, const float* root0, float* st
 
 }  // namespace
 
+// Which kernel runs a scene.  Serial chains without contacts: one body per lane (rollout_lanes.cu).  Trees without contacts: a team of
+// lanes per rollout (rollout_team.cu; 1.4 - 4.5x the thread-per-rollout kernel, profiles/r2_team.md).  Scenes with contacts: the team
+// kernel where its Gauss-Seidel sweeps (a few rollouts per warp) beat the thread-per-rollout kernel (32 rollouts per warp, one warp
+// per SM): robots of up to 8 joints at the shard sizes of the BASELINE configs (K <= TEAM_CONTACT_MAX_K); the 9-joint panda_pick
+// scene and very large K stay on the thread-per-rollout kernel.  MPPIB_K2_LANES=0 / MPPIB_K2_TEAM=0|1 force a mapping (A/B runs).
+static constexpr int TEAM_CONTACT_MAX_K = 40000;
+int rollout_mapping(const MppibContext* c) {
+    const MppibModel& m = c->model;
+    const bool contact = m.nfree > 0 || m.nshapes > 0;
+    if (c->k2_lanes && rollout_lanes_eligible(m)) return MPPIB_MAPPING_LANES;
+    if (c->k2_team != 0 && rollout_team_eligible(m)) {
+        if (c->k2_team == 1) return MPPIB_MAPPING_TEAM;
+        if (!contact || (m.nb <= 8 && c->params.K <= TEAM_CONTACT_MAX_K)) return MPPIB_MAPPING_TEAM;
+    }
+    return MPPIB_MAPPING_THREAD;
+}
+
 int launch_rollout(MppibContext* c, const float* state0, const float* root0, float* state, const float* actions, int t0, int nsteps,
                    float* obs, cudaStream_t s) {
     const MppibModel& m = c->model;
     const bool chain = is_chain(m);
     const bool contact = m.nfree > 0 || m.nshapes > 0;
-    // serial chains without contacts: one body per lane (rollout_lanes.cu) unless MPPIB_K2_LANES=0 asks for the thread-per-rollout
-    // kernel (A/B measurements, tools/tune_rollout.py)
-    if (c->k2_lanes && rollout_lanes_eligible(m)) return launch_rollout_lanes(c, state0, state, actions, t0, nsteps, obs, s);
-    if (c->k2_team && rollout_team_eligible(m)) return launch_rollout_team(c, state0, root0, state, actions, t0, nsteps, obs, s);
+    const int mapping = rollout_mapping(c);
+    if (mapping == MPPIB_MAPPING_LANES) return launch_rollout_lanes(c, state0, state, actions, t0, nsteps, obs, s);
+    if (mapping == MPPIB_MAPPING_TEAM) return launch_rollout_team(c, state0, root0, state, actions, t0, nsteps, obs, s);
     if (contact) {
         MPPIB_REQUIRE(root0 != nullptr, "mppib_rollout: root0 is required for scenes with free bodies / collision boxes");
         if (chain) return launch_t<true, true>(c, state0, root0, state, actions, t0, nsteps, obs, s);
