@@ -120,14 +120,25 @@ __device__ __forceinline__ uint32_t partner_mask(const MppibModel& m, int a) {
 }
 
 // team-wide helpers: G lanes, lane-in-team i, `tb` = first lane of the team in the warp
-// (the contact phase runs team-divergent loops -- the teams of a warp see different numbers of contacts -- so every shuffle / ballot /
-// barrier in it names only the lanes of the team: `tm`)
-template <int G> __device__ __forceinline__ float team_sum(float v, uint32_t tm) {
+// The teams of a warp see different numbers of contacts, but the control flow of the contact phase is kept WARP-UNIFORM: loops run to the
+// largest trip count among the teams of the warp and a team past its own count is predicated off.  (The teams of a warp wait for each
+// other at the next full-warp shuffle anyway; with team-divergent loops every shuffle would need the team's lane mask in a register,
+// which costs a MATCH / REDUX / VOTE convergence check per shuffle group -- 8 of the 83 instructions of a Gauss-Seidel visit, and
+// 11 % of its stall samples, profiles/r2_team.md.)
+template <int G> __device__ __forceinline__ float team_sum(float v) {
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(tm, v, o, G);
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o, G);
     return v;
 }
-template <int G> __device__ __forceinline__ uint32_t team_ballot(bool pred, uint32_t tm, int tb) { return __ballot_sync(tm, pred) >> tb; }
+template <int G> __device__ __forceinline__ uint32_t team_ballot(bool pred, int tb) { return (__ballot_sync(FULL, pred) >> tb) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u)); }
+// the team bits of a warp ballot OR-ed over the teams of the warp
+template <int G> __device__ __forceinline__ uint32_t union_ballot(bool pred) {
+    uint32_t u = __ballot_sync(FULL, pred);
+    if (G <= 16) u |= u >> 16;
+    if (G <= 8) u |= u >> 8;
+    if (G <= 4) u |= u >> 4;
+    return u & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+}
 
 struct BodyConst {
     float tqx, tqy, tqz, tqw, tpx, tpy, tpz, tax, tay, taz, jrev;
@@ -212,7 +223,6 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
     const int lane = threadIdx.x & 31;
     const int i = lane & (G - 1);
     const int team = lane / G, tb = team * G;
-    const uint32_t tm = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << tb;      // the lanes of this team
     const int k_first = (int)blockIdx.x * RPW;
     if (k_first >= K) return;
     int k = k_first + team;
@@ -324,7 +334,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
         const Quat fq = {xs[fb + FB_Q], xs[fb + FB_Q + 1], xs[fb + FB_Q + 2], xs[fb + FB_Q + 3]};
         const M3 Rf = quat_to_R(fq);
         const float i0 = xs[fb + FB_IINV], i1 = xs[fb + FB_IINV + 1], i2 = xs[fb + FB_IINV + 2];
-        __syncwarp(tm);
+        __syncwarp();
         if (i == 0) {
             stM3(xs, fb + FB_R, Rf);
             xs[fb + FB_IW + 0] = Rf.m00 * i0 * Rf.m00 + Rf.m01 * i1 * Rf.m01 + Rf.m02 * i2 * Rf.m02;
@@ -334,7 +344,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             xs[fb + FB_IW + 4] = Rf.m00 * i0 * Rf.m20 + Rf.m01 * i1 * Rf.m21 + Rf.m02 * i2 * Rf.m22;
             xs[fb + FB_IW + 5] = Rf.m10 * i0 * Rf.m20 + Rf.m11 * i1 * Rf.m21 + Rf.m12 * i2 * Rf.m22;
         }
-        __syncwarp(tm);
+        __syncwarp();
     };
     if (CONTACT) {
         // one-time per rollout: randomised shape / body parameters (lane = shape / free body), initial free-body states
@@ -369,7 +379,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
                 xs[fb + r] = state0 ? root0[13 * m.free_actor[f] + r] : state[(size_t)(2 * nb + 13 * f + r) * K + k];
         }
         for (int s = i; s < 3 * MPPIB_MAX_SLOTS; s += G) xs[L.net0 + s] = 0.f;
-        __syncwarp(tm);
+        __syncwarp();
         for (int f = 0; f < m.nfree; ++f) refresh_free(L.fb0 + f * FBN);
     }
     // world poses of the shapes: `statics` once per rollout, links and free bodies in every substep (lane = shape; a link's frame comes
@@ -404,12 +414,12 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             stM3(xs, sb + SH_R, mulMM(Ro, quat_to_R(qlc)));
             st3(xs, sb + SH_C, po + mulc(Ro, m.shape_pos[s][0], m.shape_pos[s][1], m.shape_pos[s][2]));
         }
-        __syncwarp(tm);
+        __syncwarp();
     };
     int nc = 0;
     // append the contacts of the lanes that raise `hit`, in lane order (the oracle's sample-point order)
     auto append = [&](bool hit, int refA, int refB, int slotA, int slotB, V3 pt, V3 n, float d, float mu) {
-        const uint32_t bits = team_ballot<G>(hit, tm, tb);
+        const uint32_t bits = team_ballot<G>(hit, tb);
         const int slot = nc + __popc(bits & ((1u << i) - 1u));
         if (hit && slot < m.max_contacts) {
             const int cb = L.ct0 + slot * CTN;
@@ -420,7 +430,8 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
         nc = min(nc + __popc(bits), (int)m.max_contacts);
     };
     // sample points of box a inside box b (lane = sample point), `flip`: a is the B side of the pair
-    auto points_in_box = [&](int a, int b, bool flip) {
+    // (`on`: this team takes part -- the pair loop runs over the union of the teams' near pairs)
+    auto points_in_box = [&](int a, int b, bool flip, bool on) {
         const int sa = L.sh0 + a * SHN, sb = L.sh0 + b * SHN;
         const M3 Ra = ldM3(xs, sa + SH_R), Rb = ldM3(xs, sb + SH_R);
         const V3 ca = ld3(xs, sa + SH_C), cbv = ld3(xs, sb + SH_C);
@@ -433,7 +444,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
         const float mg = m.contact_margin;
         for (int i0 = 0; i0 < 27; i0 += G) {
             const int idx = i0 + i;
-            bool hit = idx < 27 && idx != 13;
+            bool hit = on && idx < 27 && idx != 13;
             const int ix = idx / 9 - 1, iy = (idx / 3) % 3 - 1, iz = idx % 3 - 1;
             const V3 pt = mulM(Ra, mk(ix * ha.x, iy * ha.y, iz * ha.z)) + ca;
             const V3 x = mulMT(Rb, pt - cbv);
@@ -451,7 +462,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
         }
     };
     // ONE contact of a sphere against a box or a sphere (contact.cuh sphere_contact); all lanes compute, lane 0 appends
-    auto sphere_contact = [&](int a, int b) {
+    auto sphere_contact = [&](int a, int b, bool on) {
         const int sa = L.sh0 + a * SHN, sb = L.sh0 + b * SHN;
         const float mu = 0.5f * (xs[sa + SH_MU] + xs[sb + SH_MU]), mg = m.contact_margin;
         const int refa = shape_ref(m, a), refb = shape_ref(m, b), slota = m.shape_slot[a], slotb = m.shape_slot[b];
@@ -494,7 +505,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             pt = cx + mulM(Rx, qq);
             if (!sphere_is_a) n = mk(-n.x, -n.y, -n.z);
         }
-        append(hit && i == 0, refa, refb, slota, slotb, pt, n, pen, mu);
+        append(on && hit && i == 0, refa, refb, slota, slotb, pt, n, pen, mu);
     };
     auto near_shapes = [&](int a, int b) -> bool {
         const int sa = L.sh0 + a * SHN, sb = L.sh0 + b * SHN;
@@ -523,18 +534,20 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
     // partners of shape a: the broad phase of up to G partners in parallel (lane = partner), then the near ones in ascending order
     auto pairs_of = [&](int a) {
         uint32_t mask = s_bmask[a];
-        while (mask) {                                       // team-uniform
+        while (mask) {                                       // warp-uniform
             uint32_t mine = mask; int b = -1;
             for (int j = 0; j <= i && mine; ++j) { b = __ffs(mine) - 1; mine &= mine - 1; }     // the (i+1)-th set bit, if there is one
             const int cnt = __popc(mask);
             const bool have = i < cnt;
             const bool nearb = have && near_shapes(a, b);
-            uint32_t nbits = team_ballot<G>(nearb, tm, tb);
-            while (nbits) {                                  // team-uniform: lanes in ascending partner order
-                const int ln = __ffs(nbits) - 1; nbits &= nbits - 1;
-                const int bb = __shfl_sync(tm, b, ln, G);
-                if (m.shape_type[a] == MPPIB_SHAPE_SPHERE || m.shape_type[bb] == MPPIB_SHAPE_SPHERE) sphere_contact(a, bb);
-                else { points_in_box(a, bb, false); points_in_box(bb, a, true); }
+            const uint32_t mybits = team_ballot<G>(nearb, tb);
+            uint32_t ubits = union_ballot<G>(nearb);         // near for ANY team of the warp: warp-uniform loop, lanes in ascending partner order
+            while (ubits) {
+                const int ln = __ffs(ubits) - 1; ubits &= ubits - 1;
+                const int bb = __shfl_sync(FULL, b, ln, G);  // (the same shape for every team: b depends on the lane only)
+                const bool on = (mybits >> ln) & 1u;
+                if (m.shape_type[a] == MPPIB_SHAPE_SPHERE || m.shape_type[bb] == MPPIB_SHAPE_SPHERE) sphere_contact(a, bb, on);
+                else { points_in_box(a, bb, false, on); points_in_box(bb, a, true, on); }
             }
             for (int j = 0; j < G && mask; ++j) mask &= mask - 1;                               // drop the partners just handled
         }
@@ -561,7 +574,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             if (m.shape_owner_kind[a] != MPPIB_OWNER_LINK) continue;
             pairs_of(a);
         }
-        __syncwarp(tm);
+        __syncwarp();
     };
     // ---- Gauss-Seidel soft-constraint solve on the predicted velocities (contact.cuh solve, oracle.cpp ContactWorld::solve) over
     // GENERALISED COORDINATES, one (or a few) per lane: the nb joints, then per free body its 3 linear velocity components (world) and its
@@ -593,9 +606,11 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
                 minv[sl] = xs[fb + FB_IINV + cc];
             }
         }
-        for (int c = 0; c < nc; ++c) {                       // per contact, once: tangent frame, rows, inverse effective masses, bias velocity
+        const int nc_warp = __reduce_max_sync(FULL, nc);     // contacts of the busiest team of the warp
+        for (int c = 0; c < nc_warp; ++c) {                  // per contact, once: tangent frame, rows, inverse effective masses, bias velocity
+            const bool act = c < nc;                         // (a team past its own contacts computes on stale records and stores nothing)
             const int cb = L.ct0 + c * CTN;
-            const int ids = __float_as_int(xs[cb + CT_IDS]);
+            const int ids = act ? __float_as_int(xs[cb + CT_IDS]) : 0;
             const int refA = (ids & 0xFF) - 2, refB = ((ids >> 8) & 0xFF) - 2;
             const V3 pt = ld3(xs, cb + CT_P), n = ld3(xs, cb + CT_N);
             const V3 e = fabsf(n.x) < 0.9f ? mk(1.f, 0.f, 0.f) : mk(0.f, 1.f, 0.f);
@@ -622,66 +637,71 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
                         jn = sg * dot(col, cross(r, n)); j1 = sg * dot(col, cross(r, t1)); j2 = sg * dot(col, cross(r, t2));
                     }
                 }
-                if (sl * G + i < ncoord) rows[c * ncoord + sl * G + i] = make_float4(jn, j1, j2, 0.f);
+                if (act && sl * G + i < ncoord) rows[c * ncoord + sl * G + i] = make_float4(jn, j1, j2, 0.f);
                 kn_ = fmaf(jn * jn, minv[sl], kn_); kt1 = fmaf(j1 * j1, minv[sl], kt1); kt2 = fmaf(j2 * j2, minv[sl], kt2);
             }
-            kn_ = team_sum<G>(kn_, tm); kt1 = team_sum<G>(kt1, tm); kt2 = team_sum<G>(kt2, tm);
+            kn_ = team_sum<G>(kn_); kt1 = team_sum<G>(kt1); kt2 = team_sum<G>(kt2);
             const float d = xs[cb + CT_D];
-            __syncwarp(tm);
-            if (i == 0) {
-                xs[cb + CT_KN] = kn_ > K_ROW_MIN ? 1.0f / (kn_ + gamma) : 0.f;
-                xs[cb + CT_KT1] = kt1 > K_ROW_MIN ? 1.0f / kt1 : 0.f;
-                xs[cb + CT_KT2] = kt2 > K_ROW_MIN ? 1.0f / kt2 : 0.f;
+            __syncwarp();
+            if (i == 0 && act) {
+                xs[cb + CT_KN] = kn_ > K_ROW_MIN ? rcp_approx(kn_ + gamma) : 0.f;
+                xs[cb + CT_KT1] = kt1 > K_ROW_MIN ? rcp_approx(kt1) : 0.f;
+                xs[cb + CT_KT2] = kt2 > K_ROW_MIN ? rcp_approx(kt2) : 0.f;
                 st3(xs, cb + CT_T1, t1);
                 xs[cb + CT_D] = d > 0.f ? fminf(beta * d * ih, m.max_depen) : d * ih;
             }
         }
-        __syncwarp(tm);
+        __syncwarp();
         // the sweeps: contact_iters x nc visits in one flat loop; the constants and rows of the NEXT visit are fetched while this one
         // reduces (they do not change during the sweeps; the multipliers do and are loaded by the visit itself)
-        const int nvisit = nc > 0 ? m.contact_iters * nc : 0;
-        float4 Bc = make_float4(0.f, 0.f, 0.f, 0.f), Rc[MAXS];
+        const int nvisit = m.contact_iters * nc;
+        const int nvisit_warp = m.contact_iters * nc_warp;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 Bc = zero4, Rc[MAXS];
+#pragma unroll
+        for (int sl = 0; sl < MAXS; ++sl) Rc[sl] = zero4;
         if (nc > 0) {
             Bc = *reinterpret_cast<const float4*>(xs + L.ct0 + CT_D);
 #pragma unroll
-            for (int sl = 0; sl < MAXS; ++sl) Rc[sl] = (sl + 1 < MAXS || sl * G + i < ncoord) ? rows[sl * G + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int sl = 0; sl < MAXS; ++sl) if (sl + 1 < MAXS || sl * G + i < ncoord) Rc[sl] = rows[sl * G + i];
         }
         int c = 0;
 #pragma unroll 1
-        for (int v = 0; v < nvisit; ++v) {
+        for (int v = 0; v < nvisit_warp; ++v) {
             const int cb = L.ct0 + c * CTN;
-            const int cnx = c + 1 == nc ? 0 : c + 1;
-            const float4 Bn = *reinterpret_cast<const float4*>(xs + L.ct0 + cnx * CTN + CT_D);
-            float4 Rn[MAXS];
+            const int cnx = c + 1 >= nc ? 0 : c + 1;
+            const bool act_next = v + 1 < nvisit;
+            float4 Bn = zero4, Rn[MAXS];
+            if (act_next) Bn = *reinterpret_cast<const float4*>(xs + L.ct0 + cnx * CTN + CT_D);
 #pragma unroll
-            for (int sl = 0; sl < MAXS; ++sl) Rn[sl] = (sl + 1 < MAXS || sl * G + i < ncoord) ? rows[cnx * ncoord + sl * G + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int sl = 0; sl < MAXS; ++sl) { Rn[sl] = zero4; if (act_next && (sl + 1 < MAXS || sl * G + i < ncoord)) Rn[sl] = rows[cnx * ncoord + sl * G + i]; }
             const float bias = Bc.x, ikn = Bc.y, ikt1 = Bc.z, ikt2 = Bc.w;
-            if (ikn > 0.f) {                                 // team-uniform
-                const float4 A = *reinterpret_cast<const float4*>(xs + cb);              // ln lt1 lt2 mu
-                float vn = 0.f, v1 = 0.f, v2 = 0.f;
+            const bool upd = ikn > 0.f;                      // (false for a disabled row and for a team past its visits: Bc = 0)
+            float4 A = zero4;                                // ln lt1 lt2 mu
+            if (upd) A = *reinterpret_cast<const float4*>(xs + cb);
+            float vn = 0.f, v1 = 0.f, v2 = 0.f;
 #pragma unroll
-                for (int sl = 0; sl < MAXS; ++sl) { vn = fmaf(Rc[sl].x, vel[sl], vn); v1 = fmaf(Rc[sl].y, vel[sl], v1); v2 = fmaf(Rc[sl].z, vel[sl], v2); }
+            for (int sl = 0; sl < MAXS; ++sl) { vn = fmaf(Rc[sl].x, vel[sl], vn); v1 = fmaf(Rc[sl].y, vel[sl], v1); v2 = fmaf(Rc[sl].z, vel[sl], v2); }
 #pragma unroll
-                for (int o = G / 2; o > 0; o >>= 1) {        // relative velocity along the contact frame: one butterfly for the three rows
-                    vn += __shfl_xor_sync(tm, vn, o, G); v1 += __shfl_xor_sync(tm, v1, o, G); v2 += __shfl_xor_sync(tm, v2, o, G);
-                }
-                const float ln_new = fmaxf(0.f, A.x + (-vn + bias - gamma * A.x) * ikn);
-                const float lim = A.w * ln_new;
-                const float lt1_new = ikt1 > 0.f ? fminf(fmaxf(A.y - v1 * ikt1, -lim), lim) : A.y;
-                const float lt2_new = ikt2 > 0.f ? fminf(fmaxf(A.z - v2 * ikt2, -lim), lim) : A.z;
-                const float dn = ln_new - A.x, d1 = lt1_new - A.y, d2 = lt2_new - A.z;
-#pragma unroll
-                for (int sl = 0; sl < MAXS; ++sl) vel[sl] = fmaf(minv[sl], fmaf(Rc[sl].x, dn, fmaf(Rc[sl].y, d1, Rc[sl].z * d2)), vel[sl]);
-                // every lane stores the same numbers and later reads back what it stored itself: no owner lane, no barrier
-                *reinterpret_cast<float4*>(xs + cb) = make_float4(ln_new, lt1_new, lt2_new, A.w);
+            for (int o = G / 2; o > 0; o >>= 1) {            // relative velocity along the contact frame: one butterfly for the three rows
+                vn += __shfl_xor_sync(FULL, vn, o, G); v1 += __shfl_xor_sync(FULL, v1, o, G); v2 += __shfl_xor_sync(FULL, v2, o, G);
             }
+            const float ln_new = fmaxf(0.f, A.x + (-vn + bias - gamma * A.x) * ikn);
+            const float lim = A.w * ln_new;
+            const float lt1_new = ikt1 > 0.f ? fminf(fmaxf(A.y - v1 * ikt1, -lim), lim) : A.y;
+            const float lt2_new = ikt2 > 0.f ? fminf(fmaxf(A.z - v2 * ikt2, -lim), lim) : A.z;
+            const float dn = upd ? ln_new - A.x : 0.f, d1 = upd ? lt1_new - A.y : 0.f, d2 = upd ? lt2_new - A.z : 0.f;
+#pragma unroll
+            for (int sl = 0; sl < MAXS; ++sl) vel[sl] = fmaf(minv[sl], fmaf(Rc[sl].x, dn, fmaf(Rc[sl].y, d1, Rc[sl].z * d2)), vel[sl]);
+            // every lane stores the same numbers and later reads back what it stored itself: no owner lane, no barrier
+            if (upd) *reinterpret_cast<float4*>(xs + cb) = make_float4(ln_new, lt1_new, lt2_new, A.w);
             Bc = Bn;
 #pragma unroll
             for (int sl = 0; sl < MAXS; ++sl) Rc[sl] = Rn[sl];
             c = cnx;
         }
         // ---- back to the bodies: joints keep their lane's value; free bodies: linear components, then omega = R omega_body
-        __syncwarp(tm);
+        __syncwarp();
 #pragma unroll
         for (int sl = 0; sl < MAXS; ++sl) {
             if (sl >= ncs) continue;
@@ -689,15 +709,15 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             else if (ctype[sl] == 2) xs[cfb[sl] + FB_V + ccomp[sl]] = vel[sl];
             else if (ctype[sl] == 3) xs[cfb[sl] + FB_W + ccomp[sl]] = vel[sl];       // (body axes for a moment)
         }
-        __syncwarp(tm);
+        __syncwarp();
         for (int f = 0; f < m.nfree; ++f) {
             const int fb = L.fb0 + f * FBN;
             const V3 wb = ld3(xs, fb + FB_W);
             const M3 Rf = ldM3(xs, fb + FB_R);
-            __syncwarp(tm);
+            __syncwarp();
             if (i == 0) st3(xs, fb + FB_W, mulM(Rf, wb));
         }
-        __syncwarp(tm);
+        __syncwarp();
         if (last_substep) {                                  // net contact force per body = the last substep's impulses / h
             if (i == 0) {
                 for (int s = 0; s < 3 * MPPIB_MAX_SLOTS; ++s) xs[L.net0 + s] = 0.f;
@@ -713,7 +733,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
                     if (slotB >= 0) { xs[L.net0 + 3 * slotB] -= F.x; xs[L.net0 + 3 * slotB + 1] -= F.y; xs[L.net0 + 3 * slotB + 2] -= F.z; }
                 }
             }
-            __syncwarp(tm);
+            __syncwarp();
         }
     };
     auto integrate_free = [&]() {
@@ -725,12 +745,12 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             const Quat dqq = qmul(wq, fq);
             Quat r = {fq.x + 0.5f * h * dqq.x, fq.y + 0.5f * h * dqq.y, fq.z + 0.5f * h * dqq.z, fq.w + 0.5f * h * dqq.w};
             const float il = rsqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
-            __syncwarp(tm);
+            __syncwarp();
             if (i == 0) {
                 xs[fb + FB_X] = x.x + h * v.x; xs[fb + FB_X + 1] = x.y + h * v.y; xs[fb + FB_X + 2] = x.z + h * v.z;
                 xs[fb + FB_Q] = r.x * il; xs[fb + FB_Q + 1] = r.y * il; xs[fb + FB_Q + 2] = r.z * il; xs[fb + FB_Q + 3] = r.w * il;
             }
-            __syncwarp(tm);
+            __syncwarp();
             refresh_free(fb);
         }
     };

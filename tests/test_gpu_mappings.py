@@ -30,14 +30,14 @@ def test_forced_mapping_is_what_runs(mapping):
 
 
 def test_default_mapping_by_scene_and_size(monkeypatch):
-    """without the knob: trees -> team; contact scenes of small robots -> team up to the shard sizes, thread-per-rollout beyond"""
+    """without the knob: trees -> team; contact scenes of robots with up to 8 joints -> team; the 9-joint pick scene -> thread-per-rollout"""
     monkeypatch.delenv("MPPIB_K2_TEAM", raising=False)
     sc, p, _ = gripper_setup(K=64, T=5)
     assert "team" in S.gpu_backend(sc, p).rollout_mapping()
     sc, p, _ = push_setup(K=4000, T=5)
     assert "team" in S.gpu_backend(sc, p).rollout_mapping()
-    sc, p, _ = push_setup(K=65536, T=5)
-    assert "thread" in S.gpu_backend(sc, p).rollout_mapping()
+    sc, p, _ = boxer_setup(K=4000, T=5)
+    assert "team" in S.gpu_backend(sc, p).rollout_mapping()
     sc, p, _ = S._pick_scene(256, 10)
     assert "thread" in S.gpu_backend(sc, p).rollout_mapping()
 
