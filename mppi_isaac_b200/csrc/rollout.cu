@@ -507,30 +507,12 @@ mppib_rollout_kernel(const __grid_constant__ MppibModel m, const __grid_constant
                 for (int i = 0; i < nb; ++i) { xs[(L.jv0 + 2 * nb + i) * 32 + lane] = SM(i, F_QD) + h * SM(i, F_QDD); xs[(L.jv0 + i) * 32 + lane] = 0.f; }
                 contact::shapes_world<NSLOT>(m, L, sm, xs, lane, base.R, base.o, root0, false);
                 const int nc = contact::detect(m, L, xs, lane, s_bmask);
-#ifdef MPPIB_DEBUG_K
-                if (k == MPPIB_DEBUG_K) {
-                    printf("thread t=%d sub=%d nc=%d\n", t, sub, nc);
-                    for (int c = 0; c < nc; ++c) {
-                        const int cb = L.ct0 + c * contact::CTN; const int ids = __float_as_int(xs[(cb + contact::CT_IDS) * 32 + lane]);
-                        printf("  c%d A=%d B=%d p=(%.5f %.5f %.5f) n=(%.4f %.4f %.4f) d=%.6f mu=%.4f\n", c, (ids & 0xFF) - 2, ((ids >> 8) & 0xFF) - 2,
-                               xs[(cb + 0) * 32 + lane], xs[(cb + 1) * 32 + lane], xs[(cb + 2) * 32 + lane], xs[(cb + 3) * 32 + lane], xs[(cb + 4) * 32 + lane],
-                               xs[(cb + 5) * 32 + lane], xs[(cb + 6) * 32 + lane], xs[(cb + 7) * 32 + lane]);
-                    }
-                    for (int i = 0; i < nb; ++i) printf("  j%d vp=%.6f invD=%.6f\n", i, xs[(L.jv0 + 2 * nb + i) * 32 + lane], xs[(L.jv0 + nb + i) * 32 + lane]);
-                }
-#endif
                 for (int f = 0; f < m.nfree; ++f) if (m.free_gravity[f]) {
                     const int fb = L.fb0 + f * contact::FBN;
                     xs[(fb + contact::FB_V) * 32 + lane] += h * m.gravity[0]; xs[(fb + contact::FB_V + 1) * 32 + lane] += h * m.gravity[1];
                     xs[(fb + contact::FB_V + 2) * 32 + lane] += h * m.gravity[2];
                 }
                 contact::solve<NSLOT, CHAIN>(m, L, sm, xs, lane, nc, h);
-#ifdef MPPIB_DEBUG_K
-                if (k == MPPIB_DEBUG_K) {
-                    for (int c = 0; c < nc; ++c) { const int cb = L.ct0 + c * contact::CTN; printf("  c%d ln=%.6f lt1=%.6f lt2=%.6f ikn=%.5f\n", c, xs[(cb + contact::CT_LN) * 32 + lane], xs[(cb + contact::CT_LT1) * 32 + lane], xs[(cb + contact::CT_LT2) * 32 + lane], xs[(cb + contact::CT_KN) * 32 + lane]); }
-                    for (int i = 0; i < nb; ++i) printf("  j%d dq=%.6f\n", i, xs[(L.jv0 + i) * 32 + lane]);
-                }
-#endif
             }
             // ------------------------------------------------------------------ integrate
             for (int i = 0; i < nb; ++i) {

@@ -48,15 +48,18 @@ enum : int { FB_X = 0, FB_Q = 3, FB_V = 7, FB_W = 10, FB_MASS = 13, FB_HALF = 14
 enum : int { SH_R = 0, SH_C = 9, SH_HALF = 12, SH_MU = 15, SH_RAD = 16, SHN = 17 };
 // contact record, 16-byte groups: [ln lt1 lt2 mu] the state of the sweeps | [bias 1/(kn+gamma) 1/kt1 1/kt2] their constants | [p ids] [n -] [t1 -]
 enum : int { CT_LN = 0, CT_LT1 = 1, CT_LT2 = 2, CT_MU = 3, CT_D = 4, CT_KN = 5, CT_KT1 = 6, CT_KT2 = 7, CT_P = 8, CT_IDS = 11, CT_N = 12, CT_T1 = 16, CTN = 20 };
+enum : int { JB_R = 0, JB_O = 9, JB_SN = 12, JB_SF = 15, JB_VP = 18, JB_INVD = 19, JBN = 20 };
 constexpr float K_ROW_MIN = 1e-9f;     // contact rows with a smaller effective inverse mass [1/kg] are dropped (contact.cuh, oracle.cpp)
-constexpr int MAXS_ALL = 4;                 // generalised coordinates per lane in the contact solve: nb + 6 nfree <= G + 24 over G >= 8 lanes
+constexpr int MAXS_ALL = 5;                 // generalised coordinates per lane in the contact solve: nb + 6 nfree <= G + 24 over G >= 8 lanes
 struct TLayout {
-    int fb0, sh0, ct0, net0, rw0, ncs, total;
-    // rw0: contact rows [contact][coordinate] of float4 (n, t1, t2, -);  ncs: coordinate slots per lane = ceil((nb + 6 nfree) / G)
-    __host__ __device__ TLayout(int nb, int nfree, int nshapes, int max_contacts, int G) {
+    int fb0, sh0, ct0, net0, rw0, jb0, ncs, total;
+    // rw0: contact rows [contact][coordinate] of float4 (n, t1, t2, -);  ncs: coordinate slots per lane = ceil((nb + 6 nfree) / GC);
+    // jb0: what the articulation phase hands to the contact phase and back, per body: frame, motion subspace, predicted velocity, 1 / D_j
+    __host__ __device__ TLayout(int nb, int nfree, int nshapes, int max_contacts, int GC) {
         fb0 = 0; sh0 = fb0 + nfree * FBN; ct0 = (sh0 + nshapes * SHN + 3) & ~3; net0 = ct0 + max_contacts * CTN; rw0 = net0 + 3 * MPPIB_MAX_SLOTS;
-        ncs = (nb + 6 * nfree + G - 1) / G;
-        total = rw0 + max_contacts * (nb + 6 * nfree) * 4;
+        ncs = (nb + 6 * nfree + GC - 1) / GC;
+        jb0 = rw0 + max_contacts * (nb + 6 * nfree) * 4;
+        total = jb0 + nb * JBN;
     }
 };
 __host__ __device__ inline int team_stride(int total, int G) { return ((total + 31) & ~31) + G; }   // stride % 32 == G: the teams of a warp start G banks apart
@@ -207,13 +210,19 @@ __device__ __forceinline__ void kinematics(const BodyConst& bc, const Tree<R>& t
     anc_add3<G, R>(kn.V.n, tr); anc_add3<G, R>(kn.V.f, tr);
 }
 
-// G lanes per rollout, NB >= nb joint-space rows (compile time), CONTACT: free bodies / collision shapes present
-template <int G, int NB, bool CONTACT, int NCS>
+// G lanes per rollout in the ARTICULATION phase (one body per lane), NB >= nb joint-space rows (compile time); CONTACT: free bodies /
+// collision shapes present -> the CONTACT phase runs with GC <= G lanes per rollout over NCS coordinate slots per lane.  A warp owns
+// RPW = 32 / GC rollouts; with GC < G (the 9-joint panda_pick scene: G = 16, GC = 8) the articulation runs in G / GC passes over them --
+// it is a few per cent of the work -- so that the Gauss-Seidel sweeps, which are 3/4 of the work and whose cost per visit hardly depends
+// on the team width, serve four rollouts per warp instead of two.  The two phases talk through the joint block in shared memory.
+template <int G, int NB, bool CONTACT, int NCS, int GC>
 __global__ void __launch_bounds__(32)
 mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_constant__ MppibParams p,
                           const float* __restrict__ state0, const float* __restrict__ root0, float* __restrict__ state,
                           const float* __restrict__ actions, int t0, int nsteps, float* __restrict__ obs) {
-    constexpr int RPW = 32 / G;
+    constexpr int RPW = 32 / GC;                                 // rollouts per warp
+    constexpr int NP = G / GC;                                   // articulation passes
+    constexpr int APP = 32 / G;                                  // rollouts per articulation pass
     constexpr int R = (G == 16) ? 4 : ((G == 8) ? 3 : 2);        // rounds of pointer jumping: depth < 2^R
     extern __shared__ float4 sm_all4[];
     float* sm_all = reinterpret_cast<float*>(sm_all4);
@@ -221,19 +230,31 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
     __shared__ uint32_t s_anc[MPPIB_MAX_BODIES];                 // ancestor-or-self mask of every body (the chain of a contact's link)
     const int K = p.K, T = p.T, nu = m.nu, nb = m.nb;
     const int lane = threadIdx.x & 31;
-    const int i = lane & (G - 1);
-    const int team = lane / G, tb = team * G;
+    const int i = lane & (G - 1);                                // articulation phase: body of this lane
+    const int team = lane / G;
     const int k_first = (int)blockIdx.x * RPW;
     if (k_first >= K) return;
-    int k = k_first + team;
-    const bool kval = k < K;
-    if (!kval) k = K - 1;
+    const TLayout L(nb, m.nfree, m.nshapes, m.max_contacts, GC);
+    const int xstride = team_stride(L.total, GC);
+    int ka[NP]; bool kvala[NP]; float* xsa[NP];                  // rollout of this lane in articulation pass pp, its shared-memory block
+#pragma unroll
+    for (int pp = 0; pp < NP; ++pp) {
+        const int r = pp * APP + team;
+        ka[pp] = k_first + r; kvala[pp] = ka[pp] < K;
+        if (!kvala[pp]) ka[pp] = K - 1;
+        xsa[pp] = sm_all + (size_t)r * xstride;
+    }
+    // contact phase: GC lanes per rollout
+    const int ic = lane & (GC - 1);
+    const int tbc = (lane / GC) * GC;
+    int kc = k_first + lane / GC;
+    const bool kvalc = kc < K;
+    if (!kvalc) kc = K - 1;
+    float* xs = sm_all + (size_t)(lane / GC) * xstride;
     const bool bval = i < nb;
     const int ib = bval ? i : 0;
     const float h = p.dt / (float)p.substeps;
     const bool vel_mode = m.drive_mode == MPPIB_DRIVE_VELOCITY;
-    const TLayout L(nb, m.nfree, m.nshapes, m.max_contacts, G);
-    float* xs = sm_all + (size_t)team * team_stride(L.total, G);
 
     // ---- tree tables
     Tree<R> tr;
@@ -306,23 +327,27 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
     const M3 Rbase = quat_to_R(bq0);
     const V3 obase = mk(m.base_pos[0], m.base_pos[1], m.base_pos[2]);
 
-    float q = 0.f, qd = 0.f;
-    if (bval) {
-        q = state0 ? state0[i] : state[(size_t)i * K + k];
-        qd = state0 ? state0[nb + i] : state[(size_t)(nb + i) * K + k];
+    float q[NP], qd[NP];
+#pragma unroll
+    for (int pp = 0; pp < NP; ++pp) {
+        q[pp] = 0.f; qd[pp] = 0.f;
+        if (bval) {
+            q[pp] = state0 ? state0[i] : state[(size_t)i * K + ka[pp]];
+            qd[pp] = state0 ? state0[nb + i] : state[(size_t)(nb + i) * K + ka[pp]];
+        }
     }
 
     // =====================================================================================================================
     // contact pipeline (team-parallel restatement of contact.cuh; the oracle's loop orders are kept)
     // =====================================================================================================================
-    const uint32_t kg = p.k_offset + (uint32_t)k;
-    // generalised coordinates of the contact solve held by this lane: coordinate sl * G + i = joint (< nb), else component of a free body
+    const uint32_t kg = p.k_offset + (uint32_t)kc;
+    // generalised coordinates of the contact solve held by this lane: coordinate sl * GC + ic = joint (< nb), else component of a free body
     constexpr int MAXS = NCS;
     constexpr int ncs = NCS;                                 // (== L.ncs, checked by the launcher)
     int ctype[MAXS], cfb[MAXS], ccomp[MAXS], cref[MAXS];     // 0 none / 1 joint / 2 linear / 3 angular (body axes); free body base, component, ref id
 #pragma unroll
     for (int sl = 0; sl < MAXS; ++sl) {
-        const int c = sl * G + i;
+        const int c = sl * GC + ic;
         ctype[sl] = 0; cfb[sl] = 0; ccomp[sl] = 0; cref[sl] = -99;
         if (c < nb) ctype[sl] = 1;
         else if (c - nb < 6 * m.nfree) {
@@ -335,7 +360,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
         const M3 Rf = quat_to_R(fq);
         const float i0 = xs[fb + FB_IINV], i1 = xs[fb + FB_IINV + 1], i2 = xs[fb + FB_IINV + 2];
         __syncwarp();
-        if (i == 0) {
+        if (ic == 0) {
             stM3(xs, fb + FB_R, Rf);
             xs[fb + FB_IW + 0] = Rf.m00 * i0 * Rf.m00 + Rf.m01 * i1 * Rf.m01 + Rf.m02 * i2 * Rf.m02;
             xs[fb + FB_IW + 1] = Rf.m10 * i0 * Rf.m10 + Rf.m11 * i1 * Rf.m11 + Rf.m12 * i2 * Rf.m12;
@@ -348,7 +373,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
     };
     if (CONTACT) {
         // one-time per rollout: randomised shape / body parameters (lane = shape / free body), initial free-body states
-        for (int s = i; s < m.nshapes; s += G) {
+        for (int s = ic; s < m.nshapes; s += GC) {
             V3 half = mk(m.shape_half[s][0], m.shape_half[s][1], m.shape_half[s][2]);
             float mu = m.shape_friction[s];
             if (m.shape_actor[s] >= 0) {
@@ -361,7 +386,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             xs[sb + SH_MU] = mu;
             xs[sb + SH_RAD] = m.shape_type[s] == MPPIB_SHAPE_SPHERE ? half.x : sqrtf(dot(half, half));
         }
-        for (int f = i; f < m.nfree; f += G) {
+        for (int f = ic; f < m.nfree; f += GC) {
             const int fb = L.fb0 + f * FBN;
             V3 ns; float um, uf; actor_noise(p, kg, m.free_actor[f], ns, um, uf);
             const float mass = m.free_mass[f] * (1.0f + m.free_mass_pct[f] * um);
@@ -376,35 +401,28 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             xs[fb + FB_IINV + 1] = 1.0f / (m3 * (half.x * half.x + half.z * half.z));
             xs[fb + FB_IINV + 2] = 1.0f / (m3 * (half.x * half.x + half.y * half.y));
             for (int r = 0; r < 13; ++r)
-                xs[fb + r] = state0 ? root0[13 * m.free_actor[f] + r] : state[(size_t)(2 * nb + 13 * f + r) * K + k];
+                xs[fb + r] = state0 ? root0[13 * m.free_actor[f] + r] : state[(size_t)(2 * nb + 13 * f + r) * K + kc];
         }
-        for (int s = i; s < 3 * MPPIB_MAX_SLOTS; s += G) xs[L.net0 + s] = 0.f;
+        for (int s = ic; s < 3 * MPPIB_MAX_SLOTS; s += GC) xs[L.net0 + s] = 0.f;
         __syncwarp();
         for (int f = 0; f < m.nfree; ++f) refresh_free(L.fb0 + f * FBN);
     }
     // world poses of the shapes: `statics` once per rollout, links and free bodies in every substep (lane = shape; a link's frame comes
-    // from the lane that owns the body)
-    auto shapes_world = [&](const Kin& kn, bool statics) {
+    // from the joint block the articulation phase wrote)
+    auto shapes_world = [&](bool statics) {
         const int ns = m.nshapes;
-        for (int s0 = 0; s0 < ns; s0 += G) {
-            const int s = s0 + i;
-            const bool act = s < ns;
-            const int sc = act ? s : 0;
-            const int kind = m.shape_owner_kind[sc];
-            const int own = m.shape_owner[sc];
-            const int src = (kind == MPPIB_OWNER_LINK && own >= 0) ? own : i;
+        for (int s = ic; s < ns; s += GC) {
+            const int kind = m.shape_owner_kind[s];
+            const int own = m.shape_owner[s];
+            if ((kind == MPPIB_OWNER_STATIC) != statics) continue;
             M3 Ro; V3 po;
-            Ro.m00 = shfl_at<G>(kn.R.m00, src); Ro.m01 = shfl_at<G>(kn.R.m01, src); Ro.m02 = shfl_at<G>(kn.R.m02, src);
-            Ro.m10 = shfl_at<G>(kn.R.m10, src); Ro.m11 = shfl_at<G>(kn.R.m11, src); Ro.m12 = shfl_at<G>(kn.R.m12, src);
-            Ro.m20 = shfl_at<G>(kn.R.m20, src); Ro.m21 = shfl_at<G>(kn.R.m21, src); Ro.m22 = shfl_at<G>(kn.R.m22, src);
-            po.x = shfl_at<G>(kn.o.x, src); po.y = shfl_at<G>(kn.o.y, src); po.z = shfl_at<G>(kn.o.z, src);
-            if (!act || (kind == MPPIB_OWNER_STATIC) != statics) continue;
             if (kind == MPPIB_OWNER_STATIC) {
                 const float* rs = root0 + 13 * m.shape_actor[s];
                 const Quat qs = {rs[3], rs[4], rs[5], rs[6]};
                 Ro = quat_to_R(qs); po = mk(rs[0], rs[1], rs[2]);
             } else if (kind == MPPIB_OWNER_LINK) {
                 if (own < 0) { Ro = Rbase; po = obase; }
+                else { const int jb = L.jb0 + own * JBN; Ro = ldM3(xs, jb + JB_R); po = ld3(xs, jb + JB_O); }
             } else {
                 const int fb = L.fb0 + own * FBN;
                 Ro = ldM3(xs, fb + FB_R); po = ld3(xs, fb + FB_X);
@@ -419,8 +437,8 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
     int nc = 0;
     // append the contacts of the lanes that raise `hit`, in lane order (the oracle's sample-point order)
     auto append = [&](bool hit, int refA, int refB, int slotA, int slotB, V3 pt, V3 n, float d, float mu) {
-        const uint32_t bits = team_ballot<G>(hit, tb);
-        const int slot = nc + __popc(bits & ((1u << i) - 1u));
+        const uint32_t bits = team_ballot<GC>(hit, tbc);
+        const int slot = nc + __popc(bits & ((1u << ic) - 1u));
         if (hit && slot < m.max_contacts) {
             const int cb = L.ct0 + slot * CTN;
             st3(xs, cb + CT_P, pt); st3(xs, cb + CT_N, n);
@@ -442,8 +460,8 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
         bool c0 = fabsf(cl.x) > hb.x, c1 = fabsf(cl.y) > hb.y, c2 = fabsf(cl.z) > hb.z;
         if (!(c0 || c1 || c2)) c0 = c1 = c2 = true;
         const float mg = m.contact_margin;
-        for (int i0 = 0; i0 < 27; i0 += G) {
-            const int idx = i0 + i;
+        for (int i0 = 0; i0 < 27; i0 += GC) {
+            const int idx = i0 + ic;
             bool hit = on && idx < 27 && idx != 13;
             const int ix = idx / 9 - 1, iy = (idx / 3) % 3 - 1, iz = idx % 3 - 1;
             const V3 pt = mulM(Ra, mk(ix * ha.x, iy * ha.y, iz * ha.z)) + ca;
@@ -505,7 +523,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             pt = cx + mulM(Rx, qq);
             if (!sphere_is_a) n = mk(-n.x, -n.y, -n.z);
         }
-        append(on && hit && i == 0, refa, refb, slota, slotb, pt, n, pen, mu);
+        append(on && hit && ic == 0, refa, refb, slota, slotb, pt, n, pen, mu);
     };
     auto near_shapes = [&](int a, int b) -> bool {
         const int sa = L.sh0 + a * SHN, sb = L.sh0 + b * SHN;
@@ -531,25 +549,25 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
         if (fabsf(ta.z) > ha.z + c02 * hb.x + c12 * hb.y + c22 * hb.z + mg) return false;
         return true;
     };
-    // partners of shape a: the broad phase of up to G partners in parallel (lane = partner), then the near ones in ascending order
+    // partners of shape a: the broad phase of up to GC partners in parallel (lane = partner), then the near ones in ascending order
     auto pairs_of = [&](int a) {
         uint32_t mask = s_bmask[a];
         while (mask) {                                       // warp-uniform
             uint32_t mine = mask; int b = -1;
-            for (int j = 0; j <= i && mine; ++j) { b = __ffs(mine) - 1; mine &= mine - 1; }     // the (i+1)-th set bit, if there is one
+            for (int j = 0; j <= ic && mine; ++j) { b = __ffs(mine) - 1; mine &= mine - 1; }     // the (ic+1)-th set bit, if there is one
             const int cnt = __popc(mask);
-            const bool have = i < cnt;
+            const bool have = ic < cnt;
             const bool nearb = have && near_shapes(a, b);
-            const uint32_t mybits = team_ballot<G>(nearb, tb);
-            uint32_t ubits = union_ballot<G>(nearb);         // near for ANY team of the warp: warp-uniform loop, lanes in ascending partner order
+            const uint32_t mybits = team_ballot<GC>(nearb, tbc);
+            uint32_t ubits = union_ballot<GC>(nearb);         // near for ANY team of the warp: warp-uniform loop, lanes in ascending partner order
             while (ubits) {
                 const int ln = __ffs(ubits) - 1; ubits &= ubits - 1;
-                const int bb = __shfl_sync(FULL, b, ln, G);  // (the same shape for every team: b depends on the lane only)
+                const int bb = __shfl_sync(FULL, b, ln, GC);  // (the same shape for every team: b depends on the lane only)
                 const bool on = (mybits >> ln) & 1u;
                 if (m.shape_type[a] == MPPIB_SHAPE_SPHERE || m.shape_type[bb] == MPPIB_SHAPE_SPHERE) sphere_contact(a, bb, on);
                 else { points_in_box(a, bb, false, on); points_in_box(bb, a, true, on); }
             }
-            for (int j = 0; j < G && mask; ++j) mask &= mask - 1;                               // drop the partners just handled
+            for (int j = 0; j < GC && mask; ++j) mask &= mask - 1;                               // drop the partners just handled
         }
     };
     auto detect = [&]() {
@@ -561,8 +579,8 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             if (m.ground_plane) {
                 const M3 Ra = ldM3(xs, sa + SH_R); const V3 ca = ld3(xs, sa + SH_C), ha = ld3(xs, sa + SH_HALF);
                 const float mu = 0.5f * (xs[sa + SH_MU] + m.ground_friction);
-                for (int i0 = 0; i0 < 8; i0 += G) {
-                    const int idx = i0 + i;
+                for (int i0 = 0; i0 < 8; i0 += GC) {
+                    const int idx = i0 + ic;
                     const int ix = (idx >> 2) * 2 - 1, iy = ((idx >> 1) & 1) * 2 - 1, iz = (idx & 1) * 2 - 1;
                     const V3 pt = mulM(Ra, mk(ix * ha.x, iy * ha.y, iz * ha.z)) + ca;
                     append(idx < 8 && pt.z < m.ground_margin, shape_ref(m, a), REF_STATIC, m.shape_slot[a], -1, pt, mk(0.f, 0.f, 1.f), -pt.z, mu);
@@ -582,13 +600,13 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
     // has ONE scalar inverse inertia `minv` and a contact row is one number per coordinate: J_r (kept in shared memory for the
     // sweeps).  A visit is then 3 loads + 3 products per coordinate, ONE butterfly all-reduce of the three row velocities, the row
     // updates (replicated on every lane: no owner lane, no barrier) and 3 FMAs per coordinate.
-    auto chain_sign = [&](int refA, int refB) -> float {
+    auto chain_sign = [&](int joint, int refA, int refB) -> float {      // +1 / -1: the joint moves side A / side B of the contact
         float sg = 0.f;
-        if (refA >= 0 && refA < REF_FREE0 && ((s_anc[refA] >> i) & 1u)) sg = 1.f;
-        if (refB >= 0 && refB < REF_FREE0 && ((s_anc[refB] >> i) & 1u)) sg = -1.f;
+        if (refA >= 0 && refA < REF_FREE0 && ((s_anc[refA] >> joint) & 1u)) sg = 1.f;
+        if (refB >= 0 && refB < REF_FREE0 && ((s_anc[refB] >> joint) & 1u)) sg = -1.f;
         return sg;
     };
-    auto solve_contacts = [&](const Kin& kn, float& vjoint, float invD, bool last_substep) {
+    auto solve_contacts = [&](bool last_substep) {
         const float kp = m.contact_kp, kdc = m.contact_kd;
         const float gamma = 1.0f / (h * (h * kp + kdc)), beta = h * kp / (h * kp + kdc), ih = 1.0f / h;
         float vel[MAXS], minv[MAXS];
@@ -598,7 +616,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
         for (int sl = 0; sl < MAXS; ++sl) {
             vel[sl] = 0.f; minv[sl] = 0.f;
             if (sl >= ncs) continue;
-            if (ctype[sl] == 1) { vel[sl] = vjoint; minv[sl] = invD; }
+            if (ctype[sl] == 1) { const int jb = L.jb0 + (sl * GC + ic) * JBN; vel[sl] = xs[jb + JB_VP]; minv[sl] = xs[jb + JB_INVD]; }
             else if (ctype[sl] == 2) { vel[sl] = xs[cfb[sl] + FB_V + ccomp[sl]]; minv[sl] = xs[cfb[sl] + FB_MASS]; }
             else if (ctype[sl] == 3) {
                 const int fb = cfb[sl], cc = ccomp[sl];
@@ -623,9 +641,11 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
                 if (sl >= ncs) continue;
                 float jn = 0.f, j1 = 0.f, j2 = 0.f;
                 if (ctype[sl] == 1) {
-                    const float sg = chain_sign(refA, refB);
+                    const int jb = L.jb0 + (sl * GC + ic) * JBN;
+                    const float sg = chain_sign(sl * GC + ic, refA, refB);
+                    const V3 Sn = ld3(xs, jb + JB_SN), Sf = ld3(xs, jb + JB_SF);
                     const V3 mn = cross(pt, n), m1 = cross(pt, t1), m2 = cross(pt, t2);
-                    jn = sg * (dot(kn.S.f, n) + dot(kn.S.n, mn)); j1 = sg * (dot(kn.S.f, t1) + dot(kn.S.n, m1)); j2 = sg * (dot(kn.S.f, t2) + dot(kn.S.n, m2));
+                    jn = sg * (dot(Sf, n) + dot(Sn, mn)); j1 = sg * (dot(Sf, t1) + dot(Sn, m1)); j2 = sg * (dot(Sf, t2) + dot(Sn, m2));
                 } else if (ctype[sl] >= 2) {
                     const float sg = refA == cref[sl] ? 1.f : (refB == cref[sl] ? -1.f : 0.f);
                     const int fb = cfb[sl], cc = ccomp[sl];
@@ -637,13 +657,13 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
                         jn = sg * dot(col, cross(r, n)); j1 = sg * dot(col, cross(r, t1)); j2 = sg * dot(col, cross(r, t2));
                     }
                 }
-                if (act && sl * G + i < ncoord) rows[c * ncoord + sl * G + i] = make_float4(jn, j1, j2, 0.f);
+                if (act && sl * GC + ic < ncoord) rows[c * ncoord + sl * GC + ic] = make_float4(jn, j1, j2, 0.f);
                 kn_ = fmaf(jn * jn, minv[sl], kn_); kt1 = fmaf(j1 * j1, minv[sl], kt1); kt2 = fmaf(j2 * j2, minv[sl], kt2);
             }
-            kn_ = team_sum<G>(kn_); kt1 = team_sum<G>(kt1); kt2 = team_sum<G>(kt2);
+            kn_ = team_sum<GC>(kn_); kt1 = team_sum<GC>(kt1); kt2 = team_sum<GC>(kt2);
             const float d = xs[cb + CT_D];
             __syncwarp();
-            if (i == 0 && act) {
+            if (ic == 0 && act) {
                 xs[cb + CT_KN] = kn_ > K_ROW_MIN ? rcp_approx(kn_ + gamma) : 0.f;
                 xs[cb + CT_KT1] = kt1 > K_ROW_MIN ? rcp_approx(kt1) : 0.f;
                 xs[cb + CT_KT2] = kt2 > K_ROW_MIN ? rcp_approx(kt2) : 0.f;
@@ -663,7 +683,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
         if (nc > 0) {
             Bc = *reinterpret_cast<const float4*>(xs + L.ct0 + CT_D);
 #pragma unroll
-            for (int sl = 0; sl < MAXS; ++sl) if (sl + 1 < MAXS || sl * G + i < ncoord) Rc[sl] = rows[sl * G + i];
+            for (int sl = 0; sl < MAXS; ++sl) if (sl + 1 < MAXS || sl * GC + ic < ncoord) Rc[sl] = rows[sl * GC + ic];
         }
         int c = 0;
 #pragma unroll 1
@@ -674,7 +694,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             float4 Bn = zero4, Rn[MAXS];
             if (act_next) Bn = *reinterpret_cast<const float4*>(xs + L.ct0 + cnx * CTN + CT_D);
 #pragma unroll
-            for (int sl = 0; sl < MAXS; ++sl) { Rn[sl] = zero4; if (act_next && (sl + 1 < MAXS || sl * G + i < ncoord)) Rn[sl] = rows[cnx * ncoord + sl * G + i]; }
+            for (int sl = 0; sl < MAXS; ++sl) { Rn[sl] = zero4; if (act_next && (sl + 1 < MAXS || sl * GC + ic < ncoord)) Rn[sl] = rows[cnx * ncoord + sl * GC + ic]; }
             const float bias = Bc.x, ikn = Bc.y, ikt1 = Bc.z, ikt2 = Bc.w;
             const bool upd = ikn > 0.f;                      // (false for a disabled row and for a team past its visits: Bc = 0)
             float4 A = zero4;                                // ln lt1 lt2 mu
@@ -683,8 +703,8 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
 #pragma unroll
             for (int sl = 0; sl < MAXS; ++sl) { vn = fmaf(Rc[sl].x, vel[sl], vn); v1 = fmaf(Rc[sl].y, vel[sl], v1); v2 = fmaf(Rc[sl].z, vel[sl], v2); }
 #pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) {            // relative velocity along the contact frame: one butterfly for the three rows
-                vn += __shfl_xor_sync(FULL, vn, o, G); v1 += __shfl_xor_sync(FULL, v1, o, G); v2 += __shfl_xor_sync(FULL, v2, o, G);
+            for (int o = GC / 2; o > 0; o >>= 1) {            // relative velocity along the contact frame: one butterfly for the three rows
+                vn += __shfl_xor_sync(FULL, vn, o, GC); v1 += __shfl_xor_sync(FULL, v1, o, GC); v2 += __shfl_xor_sync(FULL, v2, o, GC);
             }
             const float ln_new = fmaxf(0.f, A.x + (-vn + bias - gamma * A.x) * ikn);
             const float lim = A.w * ln_new;
@@ -705,7 +725,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
 #pragma unroll
         for (int sl = 0; sl < MAXS; ++sl) {
             if (sl >= ncs) continue;
-            if (ctype[sl] == 1) vjoint = vel[sl];
+            if (ctype[sl] == 1) xs[L.jb0 + (sl * GC + ic) * JBN + JB_VP] = vel[sl];
             else if (ctype[sl] == 2) xs[cfb[sl] + FB_V + ccomp[sl]] = vel[sl];
             else if (ctype[sl] == 3) xs[cfb[sl] + FB_W + ccomp[sl]] = vel[sl];       // (body axes for a moment)
         }
@@ -715,11 +735,11 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             const V3 wb = ld3(xs, fb + FB_W);
             const M3 Rf = ldM3(xs, fb + FB_R);
             __syncwarp();
-            if (i == 0) st3(xs, fb + FB_W, mulM(Rf, wb));
+            if (ic == 0) st3(xs, fb + FB_W, mulM(Rf, wb));
         }
         __syncwarp();
         if (last_substep) {                                  // net contact force per body = the last substep's impulses / h
-            if (i == 0) {
+            if (ic == 0) {
                 for (int s = 0; s < 3 * MPPIB_MAX_SLOTS; ++s) xs[L.net0 + s] = 0.f;
                 for (int c = 0; c < nc; ++c) {
                     const int cb = L.ct0 + c * CTN;
@@ -746,7 +766,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             Quat r = {fq.x + 0.5f * h * dqq.x, fq.y + 0.5f * h * dqq.y, fq.z + 0.5f * h * dqq.z, fq.w + 0.5f * h * dqq.w};
             const float il = rsqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
             __syncwarp();
-            if (i == 0) {
+            if (ic == 0) {
                 xs[fb + FB_X] = x.x + h * v.x; xs[fb + FB_X + 1] = x.y + h * v.y; xs[fb + FB_X + 2] = x.z + h * v.z;
                 xs[fb + FB_Q] = r.x * il; xs[fb + FB_Q + 1] = r.y * il; xs[fb + FB_Q + 2] = r.z * il; xs[fb + FB_Q + 3] = r.w * il;
             }
@@ -756,9 +776,11 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
     };
 
     // ---- observation rows of model step t from the frames of the CURRENT state
-    auto write_obs = [&](int t, const Kin& kn) {
+    auto write_obs = [&](int t, const Kin& kn, int pp) {
         const size_t TK = (size_t)T * K;
-        float* dst = obs + (size_t)t * K + k;
+        const bool kval = kvala[pp];
+        const float* xo = xsa[pp];
+        float* dst = obs + (size_t)t * K + ka[pp];
         int row = 0;
         for (int oi = 0; oi < p.nobs; ++oi) {
             const int kind = p.obs[oi].kind, idx = p.obs[oi].index;
@@ -781,50 +803,24 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
                 row += 13;
             } else if (kind == MPPIB_OBS_DOF_STATE) {
                 if (kval && bval) {
-                    dst[(size_t)(row + 2 * i) * TK] = q;
-                    dst[(size_t)(row + 2 * i + 1) * TK] = qd;
+                    dst[(size_t)(row + 2 * i) * TK] = q[pp];
+                    dst[(size_t)(row + 2 * i + 1) * TK] = qd[pp];
                 }
                 row += 2 * nb;
             } else if (kind == MPPIB_OBS_FREE_STATE) {
                 const int fb = L.fb0 + idx * FBN;
-                for (int r = i; r < 13; r += G) if (kval) dst[(size_t)(row + r) * TK] = (CONTACT && idx < m.nfree) ? xs[fb + r] : 0.f;
+                for (int r = i; r < 13; r += G) if (kval) dst[(size_t)(row + r) * TK] = (CONTACT && idx < m.nfree) ? xo[fb + r] : 0.f;
                 row += 13;
             } else {
-                for (int r = i; r < 3; r += G) if (kval) dst[(size_t)(row + r) * TK] = (CONTACT && idx < MPPIB_MAX_SLOTS) ? xs[L.net0 + 3 * idx + r] : 0.f;
+                for (int r = i; r < 3; r += G) if (kval) dst[(size_t)(row + r) * TK] = (CONTACT && idx < MPPIB_MAX_SLOTS) ? xo[L.net0 + 3 * idx + r] : 0.f;
                 row += 3;
             }
         }
     };
 
-    Kin kn;
-    if (CONTACT) { kinematics<G, R>(bc, tr, q, qd, kn); shapes_world(kn, true); }
-    int pending = (obs != nullptr && nsteps == 0) ? t0 : -1;
-    float u0n = 0.f, u1n = 0.f, uv = 0.f, uw = 0.f;
-    auto load_u = [&](int t) {
-        u0n = __ldg(&actions[((size_t)t * nu + ci0) * K + k]);
-        u1n = __ldg(&actions[((size_t)t * nu + ci1) * K + k]);
-        if (planar) { uv = __ldg(&actions[((size_t)t * nu + 0) * K + k]); uw = __ldg(&actions[((size_t)t * nu + 1) * K + k]); }
-    };
-    if (nsteps > 0) load_u(t0);
-    const int nsub = p.substeps;
-#pragma unroll 1
-    for (int t = t0; t < t0 + nsteps; ++t) {
-        float tgt = cc0 * u0n + cc1 * u1n;
-        const float pv = p.u_scale * uv, pw = p.u_scale * uw;
-        if (t + 1 < t0 + nsteps) load_u(t + 1);
-#pragma unroll 1
-        for (int sub = 0; sub < nsub; ++sub) {
-            if (planar) {
-                // differential drive reduced to a planar base: body twist (v, omega) -> world-frame velocity targets of the three
-                // virtual joints; the forward axis turns with the current yaw (joint 2)
-                const float yaw = shfl_at<G>(q, 2);
-                float sy, cy; sincos_cw(yaw, &sy, &cy);
-                if (i == 0) tgt = pv * (m.fwd_axis[0] * cy - m.fwd_axis[1] * sy);
-                if (i == 1) tgt = pv * (m.fwd_axis[0] * sy + m.fwd_axis[1] * cy);
-                if (i == 2) tgt = pw;
-            }
-            kinematics<G, R>(bc, tr, q, qd, kn);
-            if (sub == 0 && pending >= 0) { write_obs(pending, kn); pending = -1; }
+    // ---- one articulation substep of one rollout: composite-rigid-body terms, joint-space LDL^T; returns the predicted velocity of this
+    // lane's joint, `invD_out` = 1 / D_j of the articulated-body recursion (the joint's compliance in the contact solve)
+    auto articulation = [&](const Kin& kn, float q, float qd, float tgt, float& invD_out) -> float {
             // ---- per-body terms about the world origin
             const V3 cw = kn.o + mulc(kn.R, bc.cx, bc.cy, bc.cz);
             const V3 hw = scale(bc.mass, cw);
@@ -921,96 +917,136 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
                 }
                 if (!__any_sync(FULL, newly)) break;
             }
-            float vnew = qd + h * qdd;
+            invD_out = invD;
+            return qd + h * qdd;
+    };
+    Kin kn;
+    if (CONTACT) shapes_world(true);
+    int pending = (obs != nullptr && nsteps == 0) ? t0 : -1;
+    float u0n[NP], u1n[NP], uv[NP], uw[NP];
+#pragma unroll
+    for (int pp = 0; pp < NP; ++pp) { u0n[pp] = u1n[pp] = uv[pp] = uw[pp] = 0.f; }
+    auto load_u = [&](int t) {
+#pragma unroll
+        for (int pp = 0; pp < NP; ++pp) {
+            u0n[pp] = __ldg(&actions[((size_t)t * nu + ci0) * K + ka[pp]]);
+            u1n[pp] = __ldg(&actions[((size_t)t * nu + ci1) * K + ka[pp]]);
+            if (planar) { uv[pp] = __ldg(&actions[((size_t)t * nu + 0) * K + ka[pp]]); uw[pp] = __ldg(&actions[((size_t)t * nu + 1) * K + ka[pp]]); }
+        }
+    };
+    if (nsteps > 0) load_u(t0);
+    const int nsub = p.substeps;
+#pragma unroll 1
+    for (int t = t0; t < t0 + nsteps; ++t) {
+        float tgt0[NP], pv[NP], pw[NP];
+#pragma unroll
+        for (int pp = 0; pp < NP; ++pp) { tgt0[pp] = cc0 * u0n[pp] + cc1 * u1n[pp]; pv[pp] = p.u_scale * uv[pp]; pw[pp] = p.u_scale * uw[pp]; }
+        if (t + 1 < t0 + nsteps) load_u(t + 1);
+#pragma unroll 1
+        for (int sub = 0; sub < nsub; ++sub) {
+            float vnew[NP];
+#pragma unroll
+            for (int pp = 0; pp < NP; ++pp) {
+                float tgt = tgt0[pp];
+                if (planar) {
+                    // differential drive reduced to a planar base: body twist (v, omega) -> world-frame velocity targets of the three
+                    // virtual joints; the forward axis turns with the current yaw (joint 2)
+                    const float yaw = shfl_at<G>(q[pp], 2);
+                    float sy, cy; sincos_cw(yaw, &sy, &cy);
+                    if (i == 0) tgt = pv[pp] * (m.fwd_axis[0] * cy - m.fwd_axis[1] * sy);
+                    if (i == 1) tgt = pv[pp] * (m.fwd_axis[0] * sy + m.fwd_axis[1] * cy);
+                    if (i == 2) tgt = pw[pp];
+                }
+                kinematics<G, R>(bc, tr, q[pp], qd[pp], kn);
+                if (sub == 0 && pending >= 0) write_obs(pending, kn, pp);
+                float invD;
+                vnew[pp] = articulation(kn, q[pp], qd[pp], tgt, invD);
+                if (CONTACT && bval) {                       // hand-over to the contact phase
+                    float* xa = xsa[pp] + L.jb0 + i * JBN;
+                    stM3(xa, JB_R, kn.R); st3(xa, JB_O, kn.o); st3(xa, JB_SN, kn.S.n); st3(xa, JB_SF, kn.S.f);
+                    xa[JB_VP] = vnew[pp]; xa[JB_INVD] = fminf(invD, 1.0e6f);       // 1 / max(D_j, 1e-6)
+                }
+            }
+            if (sub == 0) pending = -1;
             if (CONTACT) {
                 // ---- contacts on the predicted velocities
-                shapes_world(kn, false);
+                __syncwarp();
+                shapes_world(false);
                 detect();
-                if (i == 0) for (int f = 0; f < m.nfree; ++f) if (m.free_gravity[f]) {
+                if (ic == 0) for (int f = 0; f < m.nfree; ++f) if (m.free_gravity[f]) {
                     const int fb = L.fb0 + f * FBN;
                     xs[fb + FB_V] += h * m.gravity[0]; xs[fb + FB_V + 1] += h * m.gravity[1]; xs[fb + FB_V + 2] += h * m.gravity[2];
                 }
                 __syncwarp();
-                const float invDc = bval ? fminf(invD, 1.0e6f) : 0.f;        // 1 / max(D_j, 1e-6)
-#ifdef MPPIB_DEBUG_K
-                if (k == MPPIB_DEBUG_K && kval) {
-                    if (i == 0) {
-                        printf("team t=%d sub=%d nc=%d\n", t, sub, nc);
-                        for (int c = 0; c < nc; ++c) {
-                            const int cb = L.ct0 + c * CTN; const int ids = __float_as_int(xs[cb + CT_IDS]);
-                            printf("  c%d A=%d B=%d p=(%.5f %.5f %.5f) n=(%.4f %.4f %.4f) d=%.6f mu=%.4f\n", c, (ids & 0xFF) - 2, ((ids >> 8) & 0xFF) - 2,
-                                   xs[cb], xs[cb + 1], xs[cb + 2], xs[cb + 3], xs[cb + 4], xs[cb + 5], xs[cb + 6], xs[cb + 7]);
-                        }
-                    }
-                    if (bval) printf("  j%d vp=%.6f invD=%.6f\n", i, vnew, invDc);
-                }
-#endif
-                if (!bval) vnew = 0.f;
-                solve_contacts(kn, vnew, invDc, sub == nsub - 1);
-#ifdef MPPIB_DEBUG_K
-                if (k == MPPIB_DEBUG_K && kval) {
-                    if (i == 0) for (int c = 0; c < nc; ++c) { const int cb = L.ct0 + c * CTN; printf("  c%d ln=%.6f lt1=%.6f lt2=%.6f ikn=%.5f\n", c, xs[cb + CT_LN], xs[cb + CT_LT1], xs[cb + CT_LT2], xs[cb + CT_KN]); }
-                    if (bval) printf("  j%d v=%.6f\n", i, vnew);
-                }
-#endif
+                solve_contacts(sub == nsub - 1);
+                __syncwarp();
             }
             // ---- integrate
-            {
-                float vn = fminf(fmaxf(vnew, -bc.qd_max), bc.qd_max);
-                float x = q + h * vn;
+#pragma unroll
+            for (int pp = 0; pp < NP; ++pp) {
+                float vj = vnew[pp];
+                if (CONTACT && bval) vj = xsa[pp][L.jb0 + i * JBN + JB_VP];
+                float vn = fminf(fmaxf(vj, -bc.qd_max), bc.qd_max);
+                float x = q[pp] + h * vn;
                 if (x < bc.q_lo) { x = bc.q_lo; if (vn < 0.f) vn = 0.f; }
                 if (x > bc.q_hi) { x = bc.q_hi; if (vn > 0.f) vn = 0.f; }
-                if (bval) { q = x; qd = vn; }
+                if (bval) { q[pp] = x; qd[pp] = vn; }
             }
             if (CONTACT) integrate_free();
         }
         if (obs != nullptr) pending = t;
     }
     if (pending >= 0) {
-        kinematics<G, R>(bc, tr, q, qd, kn);
-        write_obs(pending, kn);
-    }
-    if (state != nullptr && kval) {
-        if (bval) {
-            state[(size_t)i * K + k] = q;
-            state[(size_t)(nb + i) * K + k] = qd;
+#pragma unroll
+        for (int pp = 0; pp < NP; ++pp) {
+            kinematics<G, R>(bc, tr, q[pp], qd[pp], kn);
+            write_obs(pending, kn, pp);
         }
-        if (CONTACT) for (int f = 0; f < m.nfree; ++f)
-            for (int r = i; r < 13; r += G) state[(size_t)(2 * nb + 13 * f + r) * K + k] = xs[L.fb0 + f * FBN + r];
+    }
+    if (state != nullptr) {
+#pragma unroll
+        for (int pp = 0; pp < NP; ++pp) if (kvala[pp] && bval) {
+            state[(size_t)i * K + ka[pp]] = q[pp];
+            state[(size_t)(nb + i) * K + ka[pp]] = qd[pp];
+        }
+        if (CONTACT && kvalc) for (int f = 0; f < m.nfree; ++f)
+            for (int r = ic; r < 13; r += GC) state[(size_t)(2 * nb + 13 * f + r) * K + kc] = xs[L.fb0 + f * FBN + r];
     }
 }
 
-template <int G, int NB, bool CONTACT, int NCS>
+template <int G, int NB, bool CONTACT, int NCS, int GC>
 int launch_team_t(MppibContext* c, const float* state0, const float* root0, float* state, const float* actions, int t0, int nsteps, float* obs, cudaStream_t s) {
     const int K = c->params.K;
-    constexpr int RPW = 32 / G;
-    const TLayout L(c->model.nb, c->model.nfree, c->model.nshapes, c->model.max_contacts, G);
-    const size_t smem = CONTACT ? sizeof(float) * (size_t)RPW * team_stride(L.total, G) : 0;
+    constexpr int RPW = 32 / GC;
+    const TLayout L(c->model.nb, c->model.nfree, c->model.nshapes, c->model.max_contacts, GC);
+    const size_t smem = CONTACT ? sizeof(float) * (size_t)RPW * team_stride(L.total, GC) : 0;
     MPPIB_REQUIRE(smem <= 200 * 1024, "mppib_rollout: %zu bytes of shared memory per team CTA", smem);
     static size_t smem_attr[64] = {0};
     size_t& attr = smem_attr[c->device & 63];
     if (smem > 48 * 1024 && smem > attr) {
-        MPPIB_CHECK_CUDA(cudaFuncSetAttribute(mppib_rollout_team_kernel<G, NB, CONTACT, NCS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MPPIB_CHECK_CUDA(cudaFuncSetAttribute(mppib_rollout_team_kernel<G, NB, CONTACT, NCS, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
     const int ctas = (K + RPW - 1) / RPW;
-    mppib_rollout_team_kernel<G, NB, CONTACT, NCS><<<ctas, 32, smem, s>>>(c->model, c->params, state0, root0, state, actions, t0, nsteps, obs);
+    mppib_rollout_team_kernel<G, NB, CONTACT, NCS, GC><<<ctas, 32, smem, s>>>(c->model, c->params, state0, root0, state, actions, t0, nsteps, obs);
     MPPIB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-// coordinate slots per lane of the contact solve (compile time): ceil((nb + 6 nfree) / G)
+// contact scenes: 8 lanes per rollout in the contact phase; coordinate slots per lane (compile time) = ceil((nb + 6 nfree) / 8)
 template <int G, int NB>
 int launch_team_g(MppibContext* c, bool contact, const float* state0, const float* root0, float* state, const float* actions, int t0, int nsteps, float* obs,
                   cudaStream_t s) {
-    if (!contact) return launch_team_t<G, NB, false, 1>(c, state0, root0, state, actions, t0, nsteps, obs, s);
-    const int ncs = (c->model.nb + 6 * c->model.nfree + G - 1) / G;
+    if (!contact) return launch_team_t<G, NB, false, 1, G>(c, state0, root0, state, actions, t0, nsteps, obs, s);
+    constexpr int GC = 8;
+    const int ncs = (c->model.nb + 6 * c->model.nfree + GC - 1) / GC;
     switch (ncs) {
-        case 1: return launch_team_t<G, NB, true, 1>(c, state0, root0, state, actions, t0, nsteps, obs, s);
-        case 2: return launch_team_t<G, NB, true, 2>(c, state0, root0, state, actions, t0, nsteps, obs, s);
-        case 3: return launch_team_t<G, NB, true, 3>(c, state0, root0, state, actions, t0, nsteps, obs, s);
+        case 1: return launch_team_t<G, NB, true, 1, GC>(c, state0, root0, state, actions, t0, nsteps, obs, s);
+        case 2: return launch_team_t<G, NB, true, 2, GC>(c, state0, root0, state, actions, t0, nsteps, obs, s);
+        case 3: return launch_team_t<G, NB, true, 3, GC>(c, state0, root0, state, actions, t0, nsteps, obs, s);
+        case 4: return launch_team_t<G, NB, true, 4, GC>(c, state0, root0, state, actions, t0, nsteps, obs, s);
         default: MPPIB_REQUIRE(ncs <= MAXS_ALL, "mppib_rollout: %d coordinate slots per lane", ncs);
-                 return launch_team_t<G, NB, true, 4>(c, state0, root0, state, actions, t0, nsteps, obs, s);
+                 return launch_team_t<G, NB, true, 5, GC>(c, state0, root0, state, actions, t0, nsteps, obs, s);
     }
 }
 

@@ -59,11 +59,8 @@ for f, actor in enumerate(free_rows):
 obs_r = torch.zeros((ref.obs_size(), T, K), device=DEV)
 obs_t = torch.zeros((ref.obs_size(), T, K), device=DEV)
 np.set_printoptions(precision=5, suppress=True, linewidth=200)
-ONLY = int(os.environ.get("DEBUG_STEP", "-1"))
 for t in range(T):
     sr, st = dev(state), dev(state)
-    if ONLY >= 0 and t != ONLY:      # (a debug build prints inside the kernels: keep the other steps quiet by running the oracle-free thread kernel only)
-        os.environ["MPPIB_QUIET"] = "1"
     ref.rollout(None, sr, a_d, t, 1, obs_r, root0=root_d)
     team.rollout(None, st, a_d, t, 1, obs_t, root0=root_d)
     torch.cuda.synchronize()
