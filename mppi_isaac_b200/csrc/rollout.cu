@@ -569,16 +569,18 @@ int launch_t(MppibContext* c, const float* state0, const float* root0, float* st
 
 // Which kernel runs a scene.  Serial chains without contacts: one body per lane (rollout_lanes.cu).  Trees without contacts: a team of
 // lanes per rollout (rollout_team.cu; 1.4 - 4.5x the thread-per-rollout kernel, profiles/r2_team.md).  Scenes with contacts: the team
-// kernel where its Gauss-Seidel sweeps (4 rollouts per warp) beat the thread-per-rollout kernel (32 rollouts per warp, one warp per
-// SM): robots of up to 8 joints (2.0x at the shard sizes of BASELINE C3 / C4, 1.04x at K = 65 536); the 9-joint panda_pick scene
-// (2 rollouts per warp, 0.97x) stays on the thread-per-rollout kernel.  MPPIB_K2_LANES=0 / MPPIB_K2_TEAM=0|1 force a mapping (A/B runs).
+// kernel (4 rollouts per warp in the contact phase) where it beats the thread-per-rollout kernel (32 rollouts per warp, one warp per
+// SM): robots of up to 8 joints at every K (2.0 - 2.4x at the shard sizes of BASELINE C3 / C4, 1.4x at K = 16 000); the 9-joint
+// panda_pick scene up to TEAM_PICK_MAX_K samples per GPU (1.17x at the K = 8 192 shard of BASELINE C5, 0.99x at K = 65 536, where the
+// thread-per-rollout kernel stays).  MPPIB_K2_LANES=0 / MPPIB_K2_TEAM=0|1 force a mapping (A/B runs).
+static constexpr int TEAM_PICK_MAX_K = 16384;
 int rollout_mapping(const MppibContext* c) {
     const MppibModel& m = c->model;
     const bool contact = m.nfree > 0 || m.nshapes > 0;
     if (c->k2_lanes && rollout_lanes_eligible(m)) return MPPIB_MAPPING_LANES;
     if (c->k2_team != 0 && rollout_team_eligible(m)) {
         if (c->k2_team == 1) return MPPIB_MAPPING_TEAM;
-        if (!contact || m.nb <= 8) return MPPIB_MAPPING_TEAM;
+        if (!contact || m.nb <= 8 || c->params.K <= TEAM_PICK_MAX_K) return MPPIB_MAPPING_TEAM;
     }
     return MPPIB_MAPPING_THREAD;
 }

@@ -46,24 +46,36 @@ __device__ __forceinline__ M3 mulMM(const M3& a, const M3& b) {
 enum : int { REF_STATIC = -1, REF_FREE0 = 64 };
 enum : int { FB_X = 0, FB_Q = 3, FB_V = 7, FB_W = 10, FB_MASS = 13, FB_HALF = 14, FB_IINV = 17, FB_R = 20, FB_IW = 29, FBN = 35 };   // FB_MASS: inverse mass
 enum : int { SH_R = 0, SH_C = 9, SH_HALF = 12, SH_MU = 15, SH_RAD = 16, SHN = 17 };
-// contact record, 16-byte groups: [ln lt1 lt2 mu] the state of the sweeps | [bias 1/(kn+gamma) 1/kt1 1/kt2] their constants | [p ids] [n -] [t1 -]
-enum : int { CT_LN = 0, CT_LT1 = 1, CT_LT2 = 2, CT_MU = 3, CT_D = 4, CT_KN = 5, CT_KT1 = 6, CT_KT2 = 7, CT_P = 8, CT_IDS = 11, CT_N = 12, CT_T1 = 16, CTN = 20 };
+// contact record, 16-byte groups: [ln lt1 lt2 mu] the state of the sweeps | [bias 1/(kn+gamma) 1/kt1 1/kt2] their constants | [p ids] [n -]
+// and, in the roomy layout, [t1 -] (compact: the tangents are recomputed from n, tangent_frame()).
+// Two layouts of the per-rollout block.  ROOMY (robots of up to 8 joints): 20-float contact records, contact rows as one float4 per
+// coordinate -- one LDS.128 per coordinate slot and visit; these kernels run latency-bound with every CTA resident.  COMPACT (9 - 16
+// joints, e.g. panda_pick: 15 coordinates x 24 contacts of rows): 16-float records, rows as three planes of floats -- 20 % less shared
+// memory per rollout = 7 instead of 5 resident CTAs per SM, worth 1.25x there and a loss of 12 % on the small robots.
+enum : int { CT_LN = 0, CT_LT1 = 1, CT_LT2 = 2, CT_MU = 3, CT_D = 4, CT_KN = 5, CT_KT1 = 6, CT_KT2 = 7, CT_P = 8, CT_IDS = 11, CT_N = 12, CT_T1 = 16 };
 enum : int { JB_R = 0, JB_O = 9, JB_SN = 12, JB_SF = 15, JB_VP = 18, JB_INVD = 19, JBN = 20 };
 constexpr float K_ROW_MIN = 1e-9f;     // contact rows with a smaller effective inverse mass [1/kg] are dropped (contact.cuh, oracle.cpp)
 constexpr int MAXS_ALL = 5;                 // generalised coordinates per lane in the contact solve: nb + 6 nfree <= G + 24 over G >= 8 lanes
 struct TLayout {
-    int fb0, sh0, ct0, net0, rw0, jb0, ncs, total;
-    // rw0: contact rows [contact][coordinate] of float4 (n, t1, t2, -);  ncs: coordinate slots per lane = ceil((nb + 6 nfree) / GC);
+    int fb0, sh0, ct0, net0, rw0, jb0, ncs, ctn, total;
+    // rw0: contact rows [contact][n, t1, t2][coordinate];  ncs: coordinate slots per lane = ceil((nb + 6 nfree) / GC);
     // jb0: what the articulation phase hands to the contact phase and back, per body: frame, motion subspace, predicted velocity, 1 / D_j
-    __host__ __device__ TLayout(int nb, int nfree, int nshapes, int max_contacts, int GC) {
-        fb0 = 0; sh0 = fb0 + nfree * FBN; ct0 = (sh0 + nshapes * SHN + 3) & ~3; net0 = ct0 + max_contacts * CTN; rw0 = net0 + 3 * MPPIB_MAX_SLOTS;
+    __host__ __device__ TLayout(int nb, int nfree, int nshapes, int max_contacts, int GC, bool compact) {
+        ctn = compact ? 16 : 20;
+        fb0 = 0; sh0 = fb0 + nfree * FBN; ct0 = (sh0 + nshapes * SHN + 3) & ~3; net0 = ct0 + max_contacts * ctn; rw0 = net0 + 3 * MPPIB_MAX_SLOTS;
         ncs = (nb + 6 * nfree + GC - 1) / GC;
-        jb0 = rw0 + max_contacts * (nb + 6 * nfree) * 4;
+        jb0 = (rw0 + max_contacts * (nb + 6 * nfree) * (compact ? 3 : 4) + 3) & ~3;
         total = jb0 + nb * JBN;
     }
 };
 __host__ __device__ inline int team_stride(int total, int G) { return ((total + 31) & ~31) + G; }   // stride % 32 == G: the teams of a warp start G banks apart
 
+__device__ __forceinline__ void tangent_frame(V3 n, V3& t1, V3& t2) {
+    const V3 e = fabsf(n.x) < 0.9f ? mk(1.f, 0.f, 0.f) : mk(0.f, 1.f, 0.f);
+    t1 = cross(n, e);
+    t1 = scale(rsqrtf(dot(t1, t1)), t1);
+    t2 = cross(n, t1);
+}
 __device__ __forceinline__ V3 ld3(const float* xs, int b) { return mk(xs[b], xs[b + 1], xs[b + 2]); }
 __device__ __forceinline__ void st3(float* xs, int b, V3 v) { xs[b] = v.x; xs[b + 1] = v.y; xs[b + 2] = v.z; }
 __device__ __forceinline__ M3 ldM3(const float* xs, int b) {
@@ -234,7 +246,9 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
     const int team = lane / G;
     const int k_first = (int)blockIdx.x * RPW;
     if (k_first >= K) return;
-    const TLayout L(nb, m.nfree, m.nshapes, m.max_contacts, GC);
+    constexpr bool COMPACT = G > 8;                             // layout of the per-rollout block (see CT_*)
+    constexpr int CTN = COMPACT ? 16 : 20;
+    const TLayout L(nb, m.nfree, m.nshapes, m.max_contacts, GC, COMPACT);
     const int xstride = team_stride(L.total, GC);
     int ka[NP]; bool kvala[NP]; float* xsa[NP];                  // rollout of this lane in articulation pass pp, its shared-memory block
 #pragma unroll
@@ -610,8 +624,16 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
         const float kp = m.contact_kp, kdc = m.contact_kd;
         const float gamma = 1.0f / (h * (h * kp + kdc)), beta = h * kp / (h * kp + kdc), ih = 1.0f / h;
         float vel[MAXS], minv[MAXS];
-        float4* rows = reinterpret_cast<float4*>(xs + L.rw0);
+        float* rows = xs + L.rw0;
         const int ncoord = nb + 6 * m.nfree;
+        auto load_row = [&](int c, int sl) -> float4 {       // (n, t1, t2) entries of this lane's coordinate in slot sl; the last slot may be ragged
+            if (sl + 1 < MAXS || sl * GC + ic < ncoord) {
+                if (!COMPACT) return reinterpret_cast<const float4*>(rows)[c * ncoord + sl * GC + ic];
+                const float* rw = rows + c * 3 * ncoord + sl * GC + ic;
+                return make_float4(rw[0], rw[ncoord], rw[2 * ncoord], 0.f);
+            }
+            return make_float4(0.f, 0.f, 0.f, 0.f);
+        };
 #pragma unroll
         for (int sl = 0; sl < MAXS; ++sl) {
             vel[sl] = 0.f; minv[sl] = 0.f;
@@ -631,10 +653,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             const int ids = act ? __float_as_int(xs[cb + CT_IDS]) : 0;
             const int refA = (ids & 0xFF) - 2, refB = ((ids >> 8) & 0xFF) - 2;
             const V3 pt = ld3(xs, cb + CT_P), n = ld3(xs, cb + CT_N);
-            const V3 e = fabsf(n.x) < 0.9f ? mk(1.f, 0.f, 0.f) : mk(0.f, 1.f, 0.f);
-            V3 t1 = cross(n, e);
-            t1 = scale(rsqrtf(dot(t1, t1)), t1);
-            const V3 t2 = cross(n, t1);
+            V3 t1, t2; tangent_frame(n, t1, t2);
             float kn_ = 0.f, kt1 = 0.f, kt2 = 0.f;
 #pragma unroll
             for (int sl = 0; sl < MAXS; ++sl) {
@@ -657,7 +676,10 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
                         jn = sg * dot(col, cross(r, n)); j1 = sg * dot(col, cross(r, t1)); j2 = sg * dot(col, cross(r, t2));
                     }
                 }
-                if (act && sl * GC + ic < ncoord) rows[c * ncoord + sl * GC + ic] = make_float4(jn, j1, j2, 0.f);
+                if (act && sl * GC + ic < ncoord) {
+                    if (COMPACT) { float* rw = rows + c * 3 * ncoord + sl * GC + ic; rw[0] = jn; rw[ncoord] = j1; rw[2 * ncoord] = j2; }
+                    else reinterpret_cast<float4*>(rows)[c * ncoord + sl * GC + ic] = make_float4(jn, j1, j2, 0.f);
+                }
                 kn_ = fmaf(jn * jn, minv[sl], kn_); kt1 = fmaf(j1 * j1, minv[sl], kt1); kt2 = fmaf(j2 * j2, minv[sl], kt2);
             }
             kn_ = team_sum<GC>(kn_); kt1 = team_sum<GC>(kt1); kt2 = team_sum<GC>(kt2);
@@ -667,7 +689,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
                 xs[cb + CT_KN] = kn_ > K_ROW_MIN ? rcp_approx(kn_ + gamma) : 0.f;
                 xs[cb + CT_KT1] = kt1 > K_ROW_MIN ? rcp_approx(kt1) : 0.f;
                 xs[cb + CT_KT2] = kt2 > K_ROW_MIN ? rcp_approx(kt2) : 0.f;
-                st3(xs, cb + CT_T1, t1);
+                if (!COMPACT) st3(xs, cb + CT_T1, t1);
                 xs[cb + CT_D] = d > 0.f ? fminf(beta * d * ih, m.max_depen) : d * ih;
             }
         }
@@ -683,7 +705,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
         if (nc > 0) {
             Bc = *reinterpret_cast<const float4*>(xs + L.ct0 + CT_D);
 #pragma unroll
-            for (int sl = 0; sl < MAXS; ++sl) if (sl + 1 < MAXS || sl * GC + ic < ncoord) Rc[sl] = rows[sl * GC + ic];
+            for (int sl = 0; sl < MAXS; ++sl) Rc[sl] = load_row(0, sl);
         }
         int c = 0;
 #pragma unroll 1
@@ -694,7 +716,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             float4 Bn = zero4, Rn[MAXS];
             if (act_next) Bn = *reinterpret_cast<const float4*>(xs + L.ct0 + cnx * CTN + CT_D);
 #pragma unroll
-            for (int sl = 0; sl < MAXS; ++sl) { Rn[sl] = zero4; if (act_next && (sl + 1 < MAXS || sl * GC + ic < ncoord)) Rn[sl] = rows[cnx * ncoord + sl * GC + ic]; }
+            for (int sl = 0; sl < MAXS; ++sl) { Rn[sl] = zero4; if (act_next) Rn[sl] = load_row(cnx, sl); }
             const float bias = Bc.x, ikn = Bc.y, ikt1 = Bc.z, ikt2 = Bc.w;
             const bool upd = ikn > 0.f;                      // (false for a disabled row and for a team past its visits: Bc = 0)
             float4 A = zero4;                                // ln lt1 lt2 mu
@@ -746,8 +768,10 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
                     const int ids = __float_as_int(xs[cb + CT_IDS]);
                     const int slotA = ((ids >> 16) & 0xFF) - 1, slotB = ((ids >> 24) & 0xFF) - 1;
                     if (slotA < 0 && slotB < 0) continue;
-                    const V3 n = ld3(xs, cb + CT_N), t1 = ld3(xs, cb + CT_T1);
-                    const V3 t2 = cross(n, t1);
+                    const V3 n = ld3(xs, cb + CT_N);
+                    V3 t1, t2;
+                    if (COMPACT) tangent_frame(n, t1, t2);
+                    else { t1 = ld3(xs, cb + CT_T1); t2 = cross(n, t1); }
                     const V3 F = scale(ih, scale(xs[cb + CT_LN], n) + scale(xs[cb + CT_LT1], t1) + scale(xs[cb + CT_LT2], t2));
                     if (slotA >= 0) { xs[L.net0 + 3 * slotA] += F.x; xs[L.net0 + 3 * slotA + 1] += F.y; xs[L.net0 + 3 * slotA + 2] += F.z; }
                     if (slotB >= 0) { xs[L.net0 + 3 * slotB] -= F.x; xs[L.net0 + 3 * slotB + 1] -= F.y; xs[L.net0 + 3 * slotB + 2] -= F.z; }
@@ -1018,7 +1042,7 @@ template <int G, int NB, bool CONTACT, int NCS, int GC>
 int launch_team_t(MppibContext* c, const float* state0, const float* root0, float* state, const float* actions, int t0, int nsteps, float* obs, cudaStream_t s) {
     const int K = c->params.K;
     constexpr int RPW = 32 / GC;
-    const TLayout L(c->model.nb, c->model.nfree, c->model.nshapes, c->model.max_contacts, GC);
+    const TLayout L(c->model.nb, c->model.nfree, c->model.nshapes, c->model.max_contacts, GC, G > 8);
     const size_t smem = CONTACT ? sizeof(float) * (size_t)RPW * team_stride(L.total, GC) : 0;
     MPPIB_REQUIRE(smem <= 200 * 1024, "mppib_rollout: %zu bytes of shared memory per team CTA", smem);
     static size_t smem_attr[64] = {0};

@@ -30,7 +30,8 @@ def test_forced_mapping_is_what_runs(mapping):
 
 
 def test_default_mapping_by_scene_and_size(monkeypatch):
-    """without the knob: trees -> team; contact scenes of robots with up to 8 joints -> team; the 9-joint pick scene -> thread-per-rollout"""
+    """without the knob: trees -> team; contact scenes of robots with up to 8 joints -> team; the 9-joint pick scene -> team at the
+    shard sizes, thread-per-rollout at the full K = 65 536 on one GPU"""
     monkeypatch.delenv("MPPIB_K2_TEAM", raising=False)
     sc, p, _ = gripper_setup(K=64, T=5)
     assert "team" in S.gpu_backend(sc, p).rollout_mapping()
@@ -38,7 +39,9 @@ def test_default_mapping_by_scene_and_size(monkeypatch):
     assert "team" in S.gpu_backend(sc, p).rollout_mapping()
     sc, p, _ = boxer_setup(K=4000, T=5)
     assert "team" in S.gpu_backend(sc, p).rollout_mapping()
-    sc, p, _ = S._pick_scene(256, 10)
+    sc, p, _ = S._pick_scene(8192, 10)
+    assert "team" in S.gpu_backend(sc, p).rollout_mapping()
+    sc, p, _ = S._pick_scene(65536, 10)
     assert "thread" in S.gpu_backend(sc, p).rollout_mapping()
 
 

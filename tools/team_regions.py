@@ -18,12 +18,12 @@ def find(pat):
     raise KeyError(pat)
 
 
-marks = [(find("auto refresh_free"), "helpers (ld/st, team_sum, philox)"), (find("auto shapes_world"), "init / refresh_free"), (find("auto append"), "shapes_world"),
+marks = [(find("auto refresh_free"), "helpers (ld/st, team_sum, philox), kernel prologue"), (find("auto shapes_world"), "init / refresh_free"), (find("auto append"), "shapes_world"),
          (find("auto detect ="), "detect geometry (points / sphere / near / pairs)"), (find("auto chain_sign"), "detect loop"), (find("auto solve_contacts"), "chain_sign"),
          (find("// per contact, once"), "solve: coordinate velocities"), (find("// the sweeps:"), "solve: rows + effective masses"),
          (find("// ---- back to the bodies"), "solve: GS visits"), (find("auto integrate_free"), "solve: write-back / net force"),
-         (find("auto write_obs"), "integrate_free"), (find("Kin kn;"), "write_obs"), (find("// ---- per-body terms about the world origin"), "step head"),
-         (find("constexpr int VB"), "articulation per-body terms"), (find("float vnew = qd + h * qdd"), "joint-space LDL"), (10 ** 6, "contact call / integrate / tail")]
+         (find("auto write_obs"), "integrate_free"), (find("auto articulation ="), "write_obs"), (find("constexpr int VB"), "articulation: per-body terms, composites"),
+         (find("Kin kn;"), "articulation: joint-space LDL"), (10 ** 6, "main loop: targets, hand-over, integrate, stores")]
 out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), sys.argv[1], "2000"], capture_output=True, text=True).stdout
 tot, smp = collections.Counter(), collections.Counter()
 for l in out.splitlines():
