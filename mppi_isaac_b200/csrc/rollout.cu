@@ -567,20 +567,18 @@ int launch_t(MppibContext* c, const float* state0, const float* root0, float* st
 
 }  // namespace
 
-// Which kernel runs a scene.  Serial chains without contacts: one body per lane (rollout_lanes.cu).  Trees without contacts: a team of
-// lanes per rollout (rollout_team.cu; 1.4 - 4.5x the thread-per-rollout kernel, profiles/r2_team.md).  Scenes with contacts: the team
-// kernel (4 rollouts per warp in the contact phase) where it beats the thread-per-rollout kernel (32 rollouts per warp, one warp per
-// SM): robots of up to 8 joints at every K (2.0 - 2.4x at the shard sizes of BASELINE C3 / C4, 1.4x at K = 16 000); the 9-joint
-// panda_pick scene up to TEAM_PICK_MAX_K samples per GPU (1.17x at the K = 8 192 shard of BASELINE C5, 0.99x at K = 65 536, where the
-// thread-per-rollout kernel stays).  MPPIB_K2_LANES=0 / MPPIB_K2_TEAM=0|1 force a mapping (A/B runs).
-static constexpr int TEAM_PICK_MAX_K = 16384;
+// Which kernel runs a scene.  Serial chains without contacts: one body per lane (rollout_lanes.cu).  Everything else the team kernel
+// can take (trees of up to 16 bodies in depth-first order, with or without contacts): a team of lanes per rollout (rollout_team.cu) --
+// 1.4 - 4.5x the thread-per-rollout kernel on contact-free trees, 2.0 - 2.4x on the contact scenes of robots with up to 8 joints at the
+// shard sizes of BASELINE C3 / C4 (1.4x at K = 16 000), 1.17x on the K = 8 192 shard of the 9-joint panda_pick scene (BASELINE C5) and
+// 0.99x at its full K = 65 536 (profiles/r2_team.md).  The choice does not depend on K, so a shard of a multi-GPU job runs the same
+// arithmetic as the single-GPU job (bit-identical rollouts, tests/test_gpu_sizes.py).  The thread-per-rollout kernel below remains for
+// scenes the team kernel does not take and as the A/B reference: MPPIB_K2_LANES=0 / MPPIB_K2_TEAM=0|1 force a mapping.
 int rollout_mapping(const MppibContext* c) {
     const MppibModel& m = c->model;
-    const bool contact = m.nfree > 0 || m.nshapes > 0;
     if (c->k2_lanes && rollout_lanes_eligible(m)) return MPPIB_MAPPING_LANES;
     if (c->k2_team != 0 && rollout_team_eligible(m)) {
-        if (c->k2_team == 1) return MPPIB_MAPPING_TEAM;
-        if (!contact || m.nb <= 8 || c->params.K <= TEAM_PICK_MAX_K) return MPPIB_MAPPING_TEAM;
+        return MPPIB_MAPPING_TEAM;
     }
     return MPPIB_MAPPING_THREAD;
 }

@@ -29,20 +29,19 @@ def test_forced_mapping_is_what_runs(mapping):
     assert "lanes" in S.gpu_backend(sc, p).rollout_mapping()
 
 
-def test_default_mapping_by_scene_and_size(monkeypatch):
-    """without the knob: trees -> team; contact scenes of robots with up to 8 joints -> team; the 9-joint pick scene -> team at the
-    shard sizes, thread-per-rollout at the full K = 65 536 on one GPU"""
+def test_default_mapping_by_scene(monkeypatch):
+    """without the knob: serial chains -> lanes, every other scene the team kernel can take -> team, at every K (a shard of a multi-GPU
+    job must run the same arithmetic as the single-GPU job)"""
     monkeypatch.delenv("MPPIB_K2_TEAM", raising=False)
     sc, p, _ = gripper_setup(K=64, T=5)
     assert "team" in S.gpu_backend(sc, p).rollout_mapping()
-    sc, p, _ = push_setup(K=4000, T=5)
-    assert "team" in S.gpu_backend(sc, p).rollout_mapping()
+    for K in (4000, 65536):
+        sc, p, _ = push_setup(K=K, T=5)
+        assert "team" in S.gpu_backend(sc, p).rollout_mapping()
+        sc, p, _ = S._pick_scene(K, 10)
+        assert "team" in S.gpu_backend(sc, p).rollout_mapping()
     sc, p, _ = boxer_setup(K=4000, T=5)
     assert "team" in S.gpu_backend(sc, p).rollout_mapping()
-    sc, p, _ = S._pick_scene(8192, 10)
-    assert "team" in S.gpu_backend(sc, p).rollout_mapping()
-    sc, p, _ = S._pick_scene(65536, 10)
-    assert "thread" in S.gpu_backend(sc, p).rollout_mapping()
 
 
 def test_trees_free_running(oracle, mapping):
