@@ -735,7 +735,10 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             const float dn = upd ? ln_new - A.x : 0.f, d1 = upd ? lt1_new - A.y : 0.f, d2 = upd ? lt2_new - A.z : 0.f;
 #pragma unroll
             for (int sl = 0; sl < MAXS; ++sl) vel[sl] = fmaf(minv[sl], fmaf(Rc[sl].x, dn, fmaf(Rc[sl].y, d1, Rc[sl].z * d2)), vel[sl]);
-            // every lane stores the same numbers and later reads back what it stored itself: no owner lane, no barrier
+            // every lane stores the same numbers and later reads back what it stored itself: no owner lane.  (The barrier orders this
+            // visit's loads of the record before any lane's store for the tools -- compute-sanitizer racecheck -- and costs one issue slot;
+            // the shuffles above have already brought the lanes together.)
+            __syncwarp();
             if (upd) *reinterpret_cast<float4*>(xs + cb) = make_float4(ln_new, lt1_new, lt2_new, A.w);
             Bc = Bn;
 #pragma unroll
