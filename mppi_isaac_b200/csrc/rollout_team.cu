@@ -228,7 +228,7 @@ __device__ __forceinline__ void kinematics(const BodyConst& bc, const Tree<R>& t
 // it is a few per cent of the work -- so that the Gauss-Seidel sweeps, which are 3/4 of the work and whose cost per visit hardly depends
 // on the team width, serve four rollouts per warp instead of two.  The two phases talk through the joint block in shared memory.
 template <int G, int NB, bool CONTACT, int NCS, int GC>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, (CONTACT && G > 8) ? 8 : 12)   // compact-layout contact kernels: shared memory allows 7 CTAs per SM -> up to 255 registers, no spills (5 % there)
 mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_constant__ MppibParams p,
                           const float* __restrict__ state0, const float* __restrict__ root0, float* __restrict__ state,
                           const float* __restrict__ actions, int t0, int nsteps, float* __restrict__ obs) {
