@@ -240,6 +240,7 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
     float* sm_all = reinterpret_cast<float*>(sm_all4);
     __shared__ uint32_t s_bmask[MPPIB_MAX_SHAPES];               // candidate partners of every shape
     __shared__ uint32_t s_anc[MPPIB_MAX_BODIES];                 // ancestor-or-self mask of every body (the chain of a contact's link)
+    __shared__ uint8_t s_link[MPPIB_MAX_SHAPES];                 // the collision shapes of moving links, ascending
     const int K = p.K, T = p.T, nu = m.nu, nb = m.nb;
     const int lane = threadIdx.x & 31;
     const int i = lane & (G - 1);                                // articulation phase: body of this lane
@@ -290,7 +291,10 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
         tr.desc = desc;
         tr.end = bval ? i + __popc(desc) : G;
         if (team == 0 && bval) s_anc[i] = anc;
-        if (CONTACT) for (int s = lane; s < m.nshapes; s += 32) s_bmask[s] = partner_mask(m, s);
+        if (CONTACT) {
+            for (int s = lane; s < m.nshapes; s += 32) s_bmask[s] = partner_mask(m, s);
+            if (lane == 0) { int n = 0; for (int s = 0; s < m.nshapes; ++s) if (m.shape_owner_kind[s] == MPPIB_OWNER_LINK && shape_ref(m, s) != REF_STATIC) s_link[n++] = (uint8_t)s; }
+        }
         __syncwarp();
     }
 
@@ -368,6 +372,11 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             const int f = (c - nb) / 6, comp = (c - nb) % 6;
             ctype[sl] = comp < 3 ? 2 : 3; ccomp[sl] = comp % 3; cfb[sl] = L.fb0 + f * FBN; cref[sl] = REF_FREE0 + f;
         }
+    }
+    int nlink = 0; uint32_t static_mask = 0;
+    if (CONTACT) for (int s = 0; s < m.nshapes; ++s) {
+        if (m.shape_owner_kind[s] == MPPIB_OWNER_STATIC) static_mask |= 1u << s;
+        else if (m.shape_owner_kind[s] == MPPIB_OWNER_LINK && shape_ref(m, s) != REF_STATIC) ++nlink;
     }
     auto refresh_free = [&](int fb) {      // all lanes compute, lane 0 writes
         const Quat fq = {xs[fb + FB_Q], xs[fb + FB_Q + 1], xs[fb + FB_Q + 2], xs[fb + FB_Q + 3]};
@@ -602,9 +611,30 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             }
             pairs_of(a);
         }
-        for (int a = 0; a < ns; ++a) {   // articulation link vs static shape
-            if (m.shape_owner_kind[a] != MPPIB_OWNER_LINK) continue;
-            pairs_of(a);
+        // articulation link vs static shape.  A link shape has few partners (the static shapes: one table), so the broad phase runs with
+        // lane = LINK SHAPE against one static shape at a time; the near pairs are then visited in the oracle's order (link shape
+        // ascending, static shape ascending within it)
+        for (int l0 = 0; l0 < nlink; l0 += GC) {
+            const bool have = l0 + ic < nlink;
+            const int a = have ? s_link[l0 + ic] : 0;
+            uint32_t mymask = 0;
+            for (uint32_t sm = static_mask; sm; sm &= sm - 1) { const int b = __ffs(sm) - 1; if (have && near_shapes(a, b)) mymask |= 1u << b; }
+            if (!__any_sync(FULL, mymask != 0u)) continue;                   // (the arm is away from the table: the usual case)
+            const int nl = min(GC, nlink - l0);
+            for (int ln = 0; ln < nl; ++ln) {
+                const int aa = s_link[l0 + ln];
+                const uint32_t ma = __shfl_sync(FULL, mymask, ln, GC);       // this team's near static shapes of link shape aa
+                uint32_t ub = ma;                                            // ... of any team of the warp: warp-uniform loop
+                if (GC <= 16) ub |= __shfl_xor_sync(FULL, ub, 16);
+                if (GC <= 8) ub |= __shfl_xor_sync(FULL, ub, 8);
+                if (GC <= 4) ub |= __shfl_xor_sync(FULL, ub, 4);
+                for (; ub; ub &= ub - 1) {
+                    const int b = __ffs(ub) - 1;
+                    const bool on = (ma >> b) & 1u;
+                    if (m.shape_type[aa] == MPPIB_SHAPE_SPHERE || m.shape_type[b] == MPPIB_SHAPE_SPHERE) sphere_contact(aa, b, on);
+                    else { points_in_box(aa, b, false, on); points_in_box(b, aa, true, on); }
+                }
+            }
         }
         __syncwarp();
     };
