@@ -738,22 +738,22 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             for (int sl = 0; sl < MAXS; ++sl) Rc[sl] = load_row(0, sl);
         }
         int c = 0;
-#pragma unroll 1
-        for (int v = 0; v < nvisit_warp; ++v) {
+        // one visit: contact c with its constants Bcur / rows Rcur in registers; fetches those of the next visit into Bnxt / Rnxt
+        auto visit = [&](int v, const float4& Bcur, const float4 (&Rcur)[MAXS], float4& Bnxt, float4 (&Rnxt)[MAXS]) {
             const int cb = L.ct0 + c * CTN;
             const int cnx = c + 1 >= nc ? 0 : c + 1;
             const bool act_next = v + 1 < nvisit;
-            float4 Bn = zero4, Rn[MAXS];
-            if (act_next) Bn = *reinterpret_cast<const float4*>(xs + L.ct0 + cnx * CTN + CT_D);
+            Bnxt = zero4;
+            if (act_next) Bnxt = *reinterpret_cast<const float4*>(xs + L.ct0 + cnx * CTN + CT_D);
 #pragma unroll
-            for (int sl = 0; sl < MAXS; ++sl) { Rn[sl] = zero4; if (act_next) Rn[sl] = load_row(cnx, sl); }
-            const float bias = Bc.x, ikn = Bc.y, ikt1 = Bc.z, ikt2 = Bc.w;
-            const bool upd = ikn > 0.f;                      // (false for a disabled row and for a team past its visits: Bc = 0)
+            for (int sl = 0; sl < MAXS; ++sl) { Rnxt[sl] = zero4; if (act_next) Rnxt[sl] = load_row(cnx, sl); }
+            const float bias = Bcur.x, ikn = Bcur.y, ikt1 = Bcur.z, ikt2 = Bcur.w;
+            const bool upd = ikn > 0.f;                      // (false for a disabled row and for a team past its visits: Bcur = 0)
             float4 A = zero4;                                // ln lt1 lt2 mu
             if (upd) A = *reinterpret_cast<const float4*>(xs + cb);
             float vn = 0.f, v1 = 0.f, v2 = 0.f;
 #pragma unroll
-            for (int sl = 0; sl < MAXS; ++sl) { vn = fmaf(Rc[sl].x, vel[sl], vn); v1 = fmaf(Rc[sl].y, vel[sl], v1); v2 = fmaf(Rc[sl].z, vel[sl], v2); }
+            for (int sl = 0; sl < MAXS; ++sl) { vn = fmaf(Rcur[sl].x, vel[sl], vn); v1 = fmaf(Rcur[sl].y, vel[sl], v1); v2 = fmaf(Rcur[sl].z, vel[sl], v2); }
 #pragma unroll
             for (int o = GC / 2; o > 0; o >>= 1) {            // relative velocity along the contact frame: one butterfly for the three rows
                 vn += __shfl_xor_sync(FULL, vn, o, GC); v1 += __shfl_xor_sync(FULL, v1, o, GC); v2 += __shfl_xor_sync(FULL, v2, o, GC);
@@ -764,16 +764,19 @@ mppib_rollout_team_kernel(const __grid_constant__ MppibModel m, const __grid_con
             const float lt2_new = ikt2 > 0.f ? fminf(fmaxf(A.z - v2 * ikt2, -lim), lim) : A.z;
             const float dn = upd ? ln_new - A.x : 0.f, d1 = upd ? lt1_new - A.y : 0.f, d2 = upd ? lt2_new - A.z : 0.f;
 #pragma unroll
-            for (int sl = 0; sl < MAXS; ++sl) vel[sl] = fmaf(minv[sl], fmaf(Rc[sl].x, dn, fmaf(Rc[sl].y, d1, Rc[sl].z * d2)), vel[sl]);
+            for (int sl = 0; sl < MAXS; ++sl) vel[sl] = fmaf(minv[sl], fmaf(Rcur[sl].x, dn, fmaf(Rcur[sl].y, d1, Rcur[sl].z * d2)), vel[sl]);
             // every lane stores the same numbers and later reads back what it stored itself: no owner lane.  (The barrier orders this
             // visit's loads of the record before any lane's store for the tools -- compute-sanitizer racecheck -- and costs one issue slot;
             // the shuffles above have already brought the lanes together.)
             __syncwarp();
             if (upd) *reinterpret_cast<float4*>(xs + cb) = make_float4(ln_new, lt1_new, lt2_new, A.w);
-            Bc = Bn;
-#pragma unroll
-            for (int sl = 0; sl < MAXS; ++sl) Rc[sl] = Rn[sl];
             c = cnx;
+        };
+        float4 Bd, Rd[MAXS];                                 // two register sets, used alternately: no hand-over copies
+#pragma unroll 1
+        for (int v = 0; v < nvisit_warp; v += 2) {
+            visit(v, Bc, Rc, Bd, Rd);
+            if (v + 1 < nvisit_warp) visit(v + 1, Bd, Rd, Bc, Rc);
         }
         // ---- back to the bodies: joints keep their lane's value; free bodies: linear components, then omega = R omega_body
         __syncwarp();
