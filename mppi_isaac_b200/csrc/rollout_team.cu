@@ -1,21 +1,24 @@
-// rollout_team.cu -- K2 for TREES and for every scene WITH CONTACTS: a TEAM of G lanes per rollout (one articulation body per
-// lane; the same lanes become sample points, shape pairs and joints of a contact's chain in the contact phase).  Replaces
-// gym.simulate() / IsaacGymWrapper.step on the MPPI path (mppiisaac/planner/isaacgym_wrapper.py:524-572, :639-655) for the scenes
-// rollout_lanes.cu does not cover: panda + gripper, omnipanda, the planar differential-drive bases (boxer, albert, jackal), and
-// BASELINE C3 / C4 / C5 (boxer_push, heijn_push, panda_pick).  Same spec as rollout.cu + contact.cuh (the thread-per-rollout kernel,
-// kept as the A/B reference: MPPIB_K2_TEAM=0) and as oracle/oracle.cpp; tested against the same oracle.
+// rollout_team.cu -- K2 for TREES and for every scene WITH CONTACTS: a TEAM of lanes per rollout.  Replaces gym.simulate() /
+// IsaacGymWrapper.step on the MPPI path (mppiisaac/planner/isaacgym_wrapper.py:524-572, :639-655) for the scenes rollout_lanes.cu does
+// not cover: panda + gripper, omnipanda, the planar differential-drive bases (boxer, albert, jackal), and BASELINE C3 / C4 / C5
+// (boxer_push, heijn_push, panda_pick).  Same spec as rollout.cu + contact.cuh (the thread-per-rollout kernel, kept for scenes outside
+// this kernel's limits and as the A/B reference: MPPIB_K2_TEAM=0) and as oracle/oracle.cpp; tested against the same oracle under
+// both mappings (tests/test_gpu_mappings.py).  Measurements and ncu: profiles/r2_team.md.
 //
 // Why.  The thread-per-rollout contact kernels are ONE warp per SM walking a data-dependent stream of 23 - 32 k instructions per
 // (sub)step at CPI 3.7 (profiles/r2_contact.md): at the BASELINE shard sizes every CTA is resident at once, so their time is the
-// latency of a single warp, and 98 % of the machine idles.  A team shortens that stream: the articulation is the composite-rigid-body /
-// joint-space LDL^T formulation of rollout_lanes.cu generalised to trees (ancestor sums by pointer jumping, subtree sums as
-// differences of suffix sums in depth-first order), the 26 sample points of a box pair are tested by the lanes in parallel (appended
-// in the oracle's order by ballot + prefix popcount), and a Gauss-Seidel visit is three dot products per lane -- the lane's own
-// joint against the contact frame -- plus one butterfly all-reduce instead of three walks along the kinematic chain.
-//
-// Per-rollout data that several lanes need lives in shared memory, one contiguous block per rollout ([slot], not interleaved):
-// free bodies, world shapes, contacts, net forces -- ~0.7 k floats for panda_pick (the thread kernel: 1.6 k slots x 32 lanes per CTA).
-// Per-body data (q, qd, frame, motion subspace, 1 / D_j, velocity correction) stays in the registers of the body's lane.
+// latency of a single warp, and 98 % of the machine idles.  Here:
+//   * ARTICULATION PHASE, G = 8 / 16 lanes per rollout, one body per lane: the composite-rigid-body / joint-space LDL^T formulation of
+//     rollout_lanes.cu generalised to trees (ancestor sums by pointer jumping, subtree sums as differences of suffix sums in depth-first
+//     order, leaves-first elimination so that the pivots are the articulated-body diagonals D_j);
+//   * CONTACT PHASE, GC = 8 lanes per rollout (4 rollouts per warp): lane = shape / candidate partner / sample point in detection
+//     (contacts appended in the oracle's order by ballot + prefix popcount), lane = generalised coordinate in the Gauss-Seidel sweeps
+//     (the joints, and per free body 3 linear + 3 body-axis angular velocity components: one scalar inverse inertia each, one number
+//     per coordinate and contact row, one butterfly all-reduce per visit).
+// Per-rollout data of the contact phase lives in shared memory, one contiguous block per rollout (TLayout: free bodies, world shapes,
+// contact records, net forces, contact rows, and the joint block through which the two phases talk): 1.3 - 2 k floats, 7 - 8 one-warp
+// CTAs per SM (the thread-per-rollout kernel: 1.3 - 1.8 k slots x 32 lanes = one CTA per SM).  Per-body data of the articulation
+// phase (q, qd, frame, motion subspace) stays in the registers of the body's lane.
 #include "common.cuh"
 #include "lanes_math.cuh"
 
