@@ -1,0 +1,32 @@
+"""CPU (no GPU): the formulation of the K2 team kernel's articulation phase (csrc/rollout_team.cu) -- frames and spatial velocities by
+pointer jumping over the ancestors, composite rigid bodies as differences of suffix sums over the depth-first body order, joint-space
+LDL^T with the leaves eliminated first -- restated in float64 numpy (tools/proto_team.py) and checked against the oracle's body-frame
+articulated-body algorithm on the tree robots of conf/actors, incl. a rollout driven far beyond the effort limits (saturation
+re-solve) and the planar differential-drive bases.  Also pinned here: the pivots of the leaves-first elimination ARE the
+articulated-body diagonals D_j, which the contact solve uses as the joints' compliance."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools"))
+import proto_team  # noqa: E402
+
+
+@pytest.mark.parametrize("robot", ["panda_gripper", "omnipanda", "albert", "jackal", "boxer"])
+def test_tree_formulation_matches_the_oracle(oracle, robot):
+    assert proto_team.check(names=(robot,), K=2, T=4, verbose=False) < 5e-5
+
+
+def test_tree_tables_of_a_branching_robot():
+    """panda + gripper: 7 arm bodies in a chain, two fingers on the hand (body 6)"""
+    parent = [-1, 0, 1, 2, 3, 4, 5, 6, 6]
+    jump, desc, end = proto_team.tree_tables(parent, 16)
+    assert jump[0] == parent and jump[1][8] == 5 and jump[2][8] == 3 and jump[3][8] == -1
+    assert desc[6] == {6, 7, 8} and desc[7] == {7} and end == [9, 9, 9, 9, 9, 9, 9, 8, 9]
+    x = [np.array([float(i + 1)]) for i in range(9)]
+    assert [float(v[0]) for v in proto_team.anc_sum(x, jump)] == [1, 3, 6, 10, 15, 21, 28, 36, 37]
+    assert [float(v[0]) for v in proto_team.subtree_sum(x, end)] == [45, 44, 42, 39, 35, 30, 24, 8, 9]
+    with pytest.raises(AssertionError):
+        proto_team.tree_tables([-1, 0, 0, 1], 8)          # body 3 hangs below body 1 but is numbered after body 2: not depth first
