@@ -5,7 +5,7 @@ MPPIB_K2_TEAM=1 timeout 600 python -m pytest tests -m gpu -q --timeout 300 2>&1 
 MPPIB_K2_TEAM=0 timeout 600 python -m pytest tests -m gpu -q -x --timeout 300 2>&1 | tail -5 > gpurun_out/team/tests_thread.log
 for cfg in c3 c4 c5; do
   for team in 0 1; do
-    MPPIB_K2_TEAM=$team BENCH_NO_CPU=1 timeout 300 python bench.py --config $cfg --steps 10 --warmup 3 > gpurun_out/team/bench_${cfg}_team${team}.json 2> gpurun_out/team/bench_${cfg}_team${team}.err
+    MPPIB_K2_TEAM=$team timeout 300 python bench.py --config $cfg --steps 10 --warmup 3 > gpurun_out/team/bench_${cfg}_team${team}.json 2> gpurun_out/team/bench_${cfg}_team${team}.err
   done
 done
 tail -15 gpurun_out/team/tests_team.log; tail -3 gpurun_out/team/tests_thread.log
