@@ -30,3 +30,9 @@ def test_tree_tables_of_a_branching_robot():
     assert [float(v[0]) for v in proto_team.subtree_sum(x, end)] == [45, 44, 42, 39, 35, 30, 24, 8, 9]
     with pytest.raises(AssertionError):
         proto_team.tree_tables([-1, 0, 0, 1], 8)          # body 3 hangs below body 1 but is numbered after body 2: not depth first
+
+
+def test_generalised_coordinate_contact_solve_matches_the_oracle(oracle):
+    """a tilted, spinning free box on the ground, one model step: Gauss-Seidel over [v (world); omega (body axes)] with one scalar inverse
+    inertia per coordinate and rows cached per contact (the team kernel's formulation) == the oracle's world-frame solve"""
+    assert proto_team.check_free_box(verbose=False) < 5e-6

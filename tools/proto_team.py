@@ -2,7 +2,9 @@
 """float64 numpy restatement of the ARTICULATION substep of csrc/rollout_team.cu for TREES, written the way the kernel computes it --
 world frames / velocities / accelerations by pointer jumping over the ancestors, composites as differences of suffix sums over the
 depth-first body order, joint-space LDL^T with the leaves eliminated first -- and checked against the oracle (body-frame ABA with
-dense 6x6 transforms) on the host.  A formulation check that needs no GPU (tests/test_proto_team.py runs it):
+dense 6x6 transforms) on the host; and of its contact solve over generalised coordinates (a free box on the ground: linear + BODY-axis
+angular velocity components with scalar inverse inertias, cached rows) against the oracle's world-frame solve.  Formulation checks
+that need no GPU (tests/test_proto_team.py runs them):
 
     python tools/proto_team.py
 """
@@ -254,5 +256,107 @@ def _one_substep(p):
     return p1
 
 
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# The contact solve of rollout_team.cu in GENERALISED COORDINATES, for the part that is new against the oracle: a free body's three
+# linear velocity components (world) and three angular velocity components IN BODY AXES, one scalar inverse inertia each, contact rows
+# cached once per substep.  Case: a free box on the ground plane (up to 8 corner contacts), one model step of the heijn_push scene with
+# the robot far away -- the oracle solves it with world-frame inverse inertia tensors and point velocities.
+def free_box_step(m, p, box_state, f=0):
+    """One model step of free body f alone on the ground (no other contact partner in reach); box_state = its 13 root-state numbers.
+    Returns the 13 numbers after the step."""
+    h = p.dt / p.substeps
+    x, qt, v, w = (np.array(box_state[0:3], float), np.array(box_state[3:7], float), np.array(box_state[7:10], float),
+                   np.array(box_state[10:13], float))
+    shape = next(s for s in range(m.nshapes) if m.shape_owner_kind[s] == 2 and m.shape_owner[s] == f)
+    half = np.array(m.free_half[f][:], float)
+    mass = float(m.free_mass[f])
+    Iinv = 1.0 / (mass / 3.0 * np.array([half[1] ** 2 + half[2] ** 2, half[0] ** 2 + half[2] ** 2, half[0] ** 2 + half[1] ** 2]))
+    minv = np.concatenate([np.full(3, 1.0 / mass), Iinv])                      # one scalar inverse inertia per coordinate
+    kp, kd = float(m.contact_kp), float(m.contact_kd)
+    gamma, beta = 1.0 / (h * (h * kp + kd)), h * kp / (h * kp + kd)
+    mu = 0.5 * (float(m.shape_friction[shape]) + float(m.ground_friction))
+    g = np.array(m.gravity[:], float)
+    for _ in range(p.substeps):
+        R = q2R(qt)
+        sq, sp = np.array(m.shape_quat[shape][:], float), np.array(m.shape_pos[shape][:], float)
+        Rs, cs = R @ q2R(sq), x + R @ sp
+        contacts = []
+        for ix in (-1, 1):
+            for iy in (-1, 1):
+                for iz in (-1, 1):
+                    pt = Rs @ (np.array([ix, iy, iz]) * half) + cs
+                    if pt[2] < float(m.ground_margin):
+                        contacts.append((pt, -pt[2]))
+        if m.free_gravity[f]:
+            v = v + h * g
+        u = np.concatenate([v, R.T @ w])                                       # generalised velocities: world linear, BODY-axis angular
+        n = np.array([0.0, 0.0, 1.0])
+        e = np.array([1.0, 0, 0]) if abs(n[0]) < 0.9 else np.array([0, 1.0, 0])
+        t1 = np.cross(n, e); t1 /= np.linalg.norm(t1); t2 = np.cross(n, t1)
+        rows, consts, lam = [], [], []
+        for pt, d in contacts:                                                 # once per contact: rows, inverse effective masses, bias
+            r = pt - x
+            J = [np.concatenate([dr, R.T @ np.cross(r, dr)]) for dr in (n, t1, t2)]
+            k = [float((Jr * Jr) @ minv) for Jr in J]
+            bias = min(beta * d / h, float(m.max_depen)) if d > 0 else d / h
+            rows.append(J)
+            consts.append((bias, 1.0 / (k[0] + gamma) if k[0] > 1e-9 else 0.0, 1.0 / k[1] if k[1] > 1e-9 else 0.0, 1.0 / k[2] if k[2] > 1e-9 else 0.0))
+            lam.append(np.zeros(3))
+        for _it in range(m.contact_iters):
+            for c, J in enumerate(rows):
+                bias, ikn, ikt1, ikt2 = consts[c]
+                if not ikn > 0:
+                    continue
+                vn, v1, v2 = (float(Jr @ u) for Jr in J)
+                ln, lt1, lt2 = lam[c]
+                ln_new = max(0.0, ln + (-vn + bias - gamma * ln) * ikn)
+                lim = mu * ln_new
+                lt1_new = min(max(lt1 - v1 * ikt1, -lim), lim) if ikt1 > 0 else lt1
+                lt2_new = min(max(lt2 - v2 * ikt2, -lim), lim) if ikt2 > 0 else lt2
+                u = u + minv * (J[0] * (ln_new - ln) + J[1] * (lt1_new - lt1) + J[2] * (lt2_new - lt2))
+                lam[c] = np.array([ln_new, lt1_new, lt2_new])
+        v, w = u[:3], R @ u[3:]
+        x = x + h * v
+        wq = np.array([w[0], w[1], w[2], 0.0])
+        qt = qt + 0.5 * h * qmul(wq, qt)
+        qt = qt / np.linalg.norm(qt)
+    return np.concatenate([x, qt, v, w])
+
+
+def check_free_box(verbose=True):
+    from oracle import oracle as orc
+    from scenes import push_setup
+    sc, p, s0 = push_setup(K=4, T=2, obstacles=False, block_pos=(3.0, -2.0, 0.1), robot_pos=(0.0, 1.5, 0.05))
+    m = sc.model
+    nd2 = 2 * sc.ndof
+    NS = orc.lib().oracle_state_size(__import__("ctypes").byref(m))
+    rng = np.random.default_rng(12)
+    worst = 0.0
+    for trial in range(6):
+        ang = rng.uniform(-0.04, 0.04, 3)                                      # a slightly tilted box, some corners in the ground, some above it
+        qt = np.array([np.sin(ang[0] / 2), 0, 0, np.cos(ang[0] / 2)])
+        qt = qmul(np.array([0, np.sin(ang[1] / 2), 0, np.cos(ang[1] / 2)]), qt)
+        qt = qmul(np.array([0, 0, np.sin(0.7 + ang[2]), np.cos(0.7 + ang[2])]), qt)
+        half = np.array(m.free_half[0][:], float)
+        box = np.concatenate([[3.0, -2.0, half[2] - 0.002 * trial], qt, rng.uniform(-0.5, 0.5, 3) * [1, 1, 0.2], rng.uniform(-1.0, 1.0, 3)])
+        state = np.zeros((NS, p.K), np.float32)
+        state[:nd2] = s0[:, None]
+        state[nd2:nd2 + 13] = box.astype(np.float32)[:, None]
+        box32 = state[nd2:nd2 + 13, 0].astype(float)                          # (the state rows are float32: start both from the same numbers)
+        ref, _ = orc.rollout(m, p, None, np.zeros((p.T, sc.nu, p.K), np.float32), 0, 1, state=state.copy(), root0=sc.root_state0, want_obs=False, use_double=True)
+        mine = free_box_step(m, p, box32)
+        err = np.abs(mine - ref[nd2:nd2 + 13, 0]).max()
+        moved = np.abs(ref[nd2 + 7:nd2 + 13, 0] - box32[7:13]).max()
+        assert moved > 1e-2, "the contacts must have done something"
+        worst = max(worst, err)
+    if verbose:
+        print(f"free box on the ground, generalised-coordinate Gauss-Seidel vs the oracle's world-frame solve, 6 poses: max |state difference| = {worst:.2e}")
+    assert worst < 5e-6, worst
+    return worst
+
+
 if __name__ == "__main__":
     check()
+    check_free_box()
