@@ -36,3 +36,12 @@ def test_generalised_coordinate_contact_solve_matches_the_oracle(oracle):
     """a tilted, spinning free box on the ground, one model step: Gauss-Seidel over [v (world); omega (body axes)] with one scalar inverse
     inertia per coordinate and rows cached per contact (the team kernel's formulation) == the oracle's world-frame solve"""
     assert proto_team.check_free_box(verbose=False) < 5e-6
+
+
+@pytest.mark.parametrize("scene,steps", [("heijn", (0, 3, 6, 9)), ("boxer", (0, 4, 7, 9))])
+def test_whole_contact_step_matches_the_oracle(oracle, scene, steps):
+    """the team kernel's whole step restated in float64 -- tree articulation, contacts in the oracle's order up to the contact
+    capacity, Gauss-Seidel over joints + free-body components -- in lock-step with the oracle on the C4 / C3 push scenes while the
+    robot pushes the block (up to 24 contacts per substep)"""
+    wx, wv = proto_team.check_push_scene(scene, verbose=False, steps=steps)
+    assert wx < 2e-6 and wv < 2e-5

@@ -3,8 +3,9 @@
 world frames / velocities / accelerations by pointer jumping over the ancestors, composites as differences of suffix sums over the
 depth-first body order, joint-space LDL^T with the leaves eliminated first -- and checked against the oracle (body-frame ABA with
 dense 6x6 transforms) on the host; and of its contact solve over generalised coordinates (a free box on the ground: linear + BODY-axis
-angular velocity components with scalar inverse inertias, cached rows) against the oracle's world-frame solve.  Formulation checks
-that need no GPU (tests/test_proto_team.py runs them):
+angular velocity components with scalar inverse inertias, cached rows) against the oracle's world-frame solve; and of the WHOLE step of
+the push scenes (articulation + contacts in the oracle's order up to the capacity + Gauss-Seidel over joints and free-body components)
+in lock-step with the oracle.  Formulation checks that need no GPU (tests/test_proto_team.py runs them):
 
     python tools/proto_team.py
 """
@@ -54,8 +55,10 @@ def subtree_sum(x, end):
     return [P[i] - (P[end[i]] if end[i] < len(x) else 0.0) for i in range(len(x))]
 
 
-def rollout(m, p, state0, actions_k, want_pivots=False):
-    """actions_k: (T, nu) of ONE rollout; returns (q, qd) after T steps [and the LDL pivots of the last substep]."""
+def rollout(m, p, state0, actions_k, want_pivots=False, contact_cb=None):
+    """actions_k: (T, nu) of ONE rollout; returns (q, qd) after T steps [and the LDL pivots of the last substep].
+    contact_cb(R, origins, Sn, Sf, vp, pivots, h) -> corrected joint velocities: the contact phase, called once per substep with what
+    the articulation phase hands over (frames, motion subspaces, predicted velocities, the articulated-body diagonals)."""
     nb, T = m.nb, p.T
     G = 8 if nb <= 8 else 16
     h = p.dt / p.substeps
@@ -165,8 +168,11 @@ def rollout(m, p, state0, actions_k, want_pivots=False):
                     sat = np.where(newly, np.sign(td), 0.0)
                 else:
                     break
+            vj = qd + h * qdd
+            if contact_cb is not None:
+                vj = contact_cb(R, pl, Sn, Sf, vj, pivots, h)
             for i in range(nb):
-                vn = min(max(qd[i] + h * qdd[i], -m.qd_max[i]), m.qd_max[i])
+                vn = min(max(vj[i], -m.qd_max[i]), m.qd_max[i])
                 x = q[i] + h * vn
                 if x < m.q_lo[i]:
                     x = m.q_lo[i]; vn = max(vn, 0.0)
@@ -357,6 +363,222 @@ def check_free_box(verbose=True):
     return worst
 
 
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# The WHOLE step of a contact scene the way rollout_team.cu computes it (articulation above + this contact phase): world shapes,
+# contacts in the oracle's order (ground corners; free shape vs every other body's shapes; link shapes vs static shapes; 26 sample
+# points of one box inside the other, both directions; capacity max_contacts), Gauss-Seidel over generalised coordinates = the joints
+# and, per free body, 3 linear + 3 body-axis angular components.  Boxes only (the shipped push scenes).
+def make_contact_phase(m, p, root0, free):
+    """free: list of 13-number arrays (pos, quat xyzw, v, w), updated in place every substep.  Returns the contact_cb of rollout()."""
+    nb, ns = m.nb, m.nshapes
+    parent = [m.parent[i] for i in range(nb)]
+    anc = []
+    for i in range(nb):
+        a, j = set(), i
+        while j >= 0:
+            a.add(j); j = parent[j]
+        anc.append(a)
+    half = [np.array(m.shape_half[s][:], float) for s in range(ns)]
+    mu_s = [float(m.shape_friction[s]) for s in range(ns)]
+    kind = [m.shape_owner_kind[s] for s in range(ns)]           # 0 static, 1 link, 2 free
+    own = [m.shape_owner[s] for s in range(ns)]
+    for s in range(ns):
+        assert m.shape_type[s] == 0, "boxes only"
+
+    def ref(s):
+        if kind[s] == 2:
+            return ("f", own[s])
+        if kind[s] == 1 and own[s] >= 0:
+            return ("j", own[s])
+        return None
+
+    kp, kd = float(m.contact_kp), float(m.contact_kd)
+    mg = float(m.contact_margin)
+
+    def contact_cb(R, o, Sn, Sf, vp, piv, h):
+        gamma, beta = 1.0 / (h * (h * kp + kd)), h * kp / (h * kp + kd)
+        Rf = [q2R(f[3:7]) for f in free]
+        Rs, cs = [], []
+        for s in range(ns):
+            if kind[s] == 0:
+                rs = np.array(root0[m.shape_actor[s]], float)
+                Ro, po = q2R(rs[3:7]), rs[0:3]
+            elif kind[s] == 1:
+                Ro, po = (R[own[s]], o[own[s]]) if own[s] >= 0 else (q2R(np.array(m.base_quat[:], float)), np.array(m.base_pos[:], float))
+            else:
+                Ro, po = Rf[own[s]], free[own[s]][0:3]
+            Rs.append(Ro @ q2R(np.array(m.shape_quat[s][:], float))); cs.append(po + Ro @ np.array(m.shape_pos[s][:], float))
+        contacts = []
+
+        def add(ra, rb, pt, n, d, mu):
+            if len(contacts) < m.max_contacts:
+                contacts.append((ra, rb, np.array(pt), np.array(n), d, mu))
+
+        def points_in_box(a, b, flip):
+            cl = Rs[b].T @ (cs[a] - cs[b])
+            out = [abs(cl[k]) > half[b][k] for k in range(3)]
+            if not any(out):
+                out = [True, True, True]
+            mu = 0.5 * (mu_s[a] + mu_s[b])
+            for idx in range(27):
+                if idx == 13:
+                    continue
+                loc = np.array([idx // 9 - 1, (idx // 3) % 3 - 1, idx % 3 - 1]) * half[a]
+                pt = Rs[a] @ loc + cs[a]
+                x = Rs[b].T @ (pt - cs[b])
+                pen = half[b] - np.abs(x)
+                if not all(pen + mg > 0):
+                    continue
+                ax, best = -1, 0.0
+                for k in range(3):
+                    if out[k] and (ax < 0 or pen[k] < best):
+                        ax, best = k, pen[k]
+                n = (1.0 if x[ax] >= 0 else -1.0) * Rs[b][:, ax]
+                if not flip:
+                    add(ref(a), ref(b), pt, n, best, mu)
+                else:
+                    add(ref(b), ref(a), pt, -n, best, mu)
+
+        for a in range(ns):
+            if kind[a] != 2:
+                continue
+            if m.ground_plane:
+                mu = 0.5 * (mu_s[a] + float(m.ground_friction))
+                for ix in (-1, 1):
+                    for iy in (-1, 1):
+                        for iz in (-1, 1):
+                            pt = Rs[a] @ (np.array([ix, iy, iz]) * half[a]) + cs[a]
+                            if pt[2] < float(m.ground_margin):
+                                add(ref(a), None, pt, [0, 0, 1.0], -pt[2], mu)
+            for b in range(ns):
+                if b == a or ref(b) == ref(a) or (kind[b] == 2 and b < a):
+                    continue
+                points_in_box(a, b, False); points_in_box(b, a, True)
+        for a in range(ns):
+            if kind[a] != 1 or ref(a) is None:
+                continue
+            for b in range(ns):
+                if kind[b] == 0:
+                    points_in_box(a, b, False); points_in_box(b, a, True)
+        g = np.array(m.gravity[:], float)
+        for f in range(len(free)):
+            if m.free_gravity[f]:
+                free[f][7:10] += h * g
+        # generalised coordinates: joints, then per free body [v (world); omega (body axes)]
+        nco = nb + 6 * len(free)
+        u = np.zeros(nco); minv = np.zeros(nco)
+        u[:nb] = vp; minv[:nb] = 1.0 / np.maximum(piv, 1e-6)
+        for f in range(len(free)):
+            hf = np.array(m.free_half[f][:], float); mass = float(m.free_mass[f])
+            u[nb + 6 * f:nb + 6 * f + 3] = free[f][7:10]; u[nb + 6 * f + 3:nb + 6 * f + 6] = Rf[f].T @ free[f][10:13]
+            minv[nb + 6 * f:nb + 6 * f + 3] = 1.0 / mass
+            minv[nb + 6 * f + 3:nb + 6 * f + 6] = 1.0 / (mass / 3.0 * np.array([hf[1] ** 2 + hf[2] ** 2, hf[0] ** 2 + hf[2] ** 2, hf[0] ** 2 + hf[1] ** 2]))
+        rows, consts, lam = [], [], []
+        for ra, rb, pt, n, d, mu in contacts:
+            e = np.array([1.0, 0, 0]) if abs(n[0]) < 0.9 else np.array([0, 1.0, 0])
+            t1 = np.cross(n, e); t1 /= np.linalg.norm(t1); t2 = np.cross(n, t1)
+            J = []
+            for dr in (n, t1, t2):
+                Jr = np.zeros(nco)
+                for sg, r in ((1.0, ra), (-1.0, rb)):
+                    if r is None:
+                        continue
+                    if r[0] == "j":
+                        for j in anc[r[1]]:
+                            Jr[j] = sg * (Sf[j] @ dr + Sn[j] @ np.cross(pt, dr))
+                    else:
+                        f = r[1]
+                        Jr[nb + 6 * f:nb + 6 * f + 3] = sg * dr
+                        Jr[nb + 6 * f + 3:nb + 6 * f + 6] = sg * (Rf[f].T @ np.cross(pt - free[f][0:3], dr))
+                J.append(Jr)
+            k = [float((Jr * Jr) @ minv) for Jr in J]
+            bias = min(beta * d / h, float(m.max_depen)) if d > 0 else d / h
+            rows.append(J); lam.append(np.zeros(3))
+            consts.append((bias, mu, 1.0 / (k[0] + gamma) if k[0] > 1e-9 else 0.0, 1.0 / k[1] if k[1] > 1e-9 else 0.0, 1.0 / k[2] if k[2] > 1e-9 else 0.0))
+        for _it in range(m.contact_iters):
+            for c, J in enumerate(rows):
+                bias, mu, ikn, ikt1, ikt2 = consts[c]
+                if not ikn > 0:
+                    continue
+                vn, v1, v2 = (float(Jr @ u) for Jr in J)
+                ln, lt1, lt2 = lam[c]
+                ln_new = max(0.0, ln + (-vn + bias - gamma * ln) * ikn)
+                lim = mu * ln_new
+                lt1_new = min(max(lt1 - v1 * ikt1, -lim), lim) if ikt1 > 0 else lt1
+                lt2_new = min(max(lt2 - v2 * ikt2, -lim), lim) if ikt2 > 0 else lt2
+                u = u + minv * (J[0] * (ln_new - ln) + J[1] * (lt1_new - lt1) + J[2] * (lt2_new - lt2))
+                lam[c] = np.array([ln_new, lt1_new, lt2_new])
+        for f in range(len(free)):
+            v, w = u[nb + 6 * f:nb + 6 * f + 3], Rf[f] @ u[nb + 6 * f + 3:nb + 6 * f + 6]
+            free[f][7:10], free[f][10:13] = v, w
+            free[f][0:3] = free[f][0:3] + h * v
+            qt = free[f][3:7] + 0.5 * h * qmul(np.array([w[0], w[1], w[2], 0.0]), free[f][3:7])
+            free[f][3:7] = qt / np.linalg.norm(qt)
+        contact_cb.ncontacts.append(len(contacts))
+        return u[:nb].copy()
+
+    contact_cb.ncontacts = []
+    return contact_cb
+
+
+def check_push_scene(which="heijn", verbose=True, K=48, steps=(0, 3, 6, 9)):
+    """heijn_push with its two static obstacles (BASELINE C4 geometry) or boxer_push (C3: planar base + wheels, 2 substeps), the robot
+    really pushing the block: lock-step against the oracle (its state re-injected before every compared step), a few rollouts of
+    random commands"""
+    import ctypes
+    from oracle import oracle as orc
+    from scenes import boxer_setup, push_setup
+    T = 10
+    if which == "heijn":
+        sc, p, s0 = push_setup(K=K, T=T, noise=False, block_pos=(0.62, 1.5, 0.1))
+        a = np.random.default_rng(3).uniform(-0.6, 0.6, (T, 3, K)).astype(np.float32)
+        a[:, 0] = 0.5 + 0.1 * a[:, 0]
+    else:
+        sc, p, s0 = boxer_setup(K=K, T=T, noise=False)
+        rng = np.random.default_rng(0)
+        a = np.stack([rng.uniform(0.3, 1.2, (T, K)), rng.uniform(-1.0, 1.0, (T, K))], axis=1).astype(np.float32)
+    m = sc.model
+    nb, nd2 = m.nb, 2 * sc.ndof
+    NS = orc.lib().oracle_state_size(ctypes.byref(m))
+    state = np.zeros((NS, K), np.float32)
+    state[:nd2] = s0[:, None]
+    state[nd2:nd2 + 13] = sc.root_state0[1][:, None]
+    worst_x = worst_v = 0.0
+    most = 0
+    p1 = _one_step(p)
+    for t in range(T):
+        before = state.copy()
+        state, _ = orc.rollout(m, p, None, a, t, 1, state=state, root0=sc.root_state0, want_obs=False, use_double=True)
+        if t not in steps:
+            continue
+        for k in range(0, K, 6):
+            free = [before[nd2:nd2 + 13, k].astype(float)]
+            cb = make_contact_phase(m, p, sc.root_state0, free)
+            q, qd = rollout(m, p1, before[:nd2, k].astype(float), a[t:t + 1, :, k].astype(float), contact_cb=cb)
+            most = max(most, max(cb.ncontacts))
+            mine = np.concatenate([q, qd, free[0]])
+            refk = state[:nd2 + 13, k].astype(float)
+            pos = list(range(nb)) + list(range(nd2, nd2 + 7)); velr = list(range(nb, nd2)) + list(range(nd2 + 7, nd2 + 13))
+            worst_x = max(worst_x, np.abs(mine[pos] - refk[pos]).max()); worst_v = max(worst_v, np.abs(mine[velr] - refk[velr]).max())
+    if verbose:
+        print(f"{which}_push, lock-step on steps {steps}, {len(range(0, K, 6))} rollouts each: max |position / quaternion difference| = {worst_x:.2e}, "
+              f"max |velocity difference| = {worst_v:.2e}; up to {most} contacts per substep")
+    assert most >= 8, "the robot must have been pushing"
+    assert worst_x < 2e-6 and worst_v < 2e-5, (worst_x, worst_v)
+    return worst_x, worst_v
+
+
+def _one_step(p):
+    import copy
+    p1 = copy.copy(p)
+    p1.T = 1
+    return p1
+
+
 if __name__ == "__main__":
     check()
     check_free_box()
+    check_push_scene("heijn")
+    check_push_scene("boxer", steps=(0, 4, 7, 9))
