@@ -38,10 +38,11 @@ def test_generalised_coordinate_contact_solve_matches_the_oracle(oracle):
     assert proto_team.check_free_box(verbose=False) < 5e-6
 
 
-@pytest.mark.parametrize("scene,steps", [("heijn", (0, 3, 6, 9)), ("boxer", (0, 4, 7, 9))])
-def test_whole_contact_step_matches_the_oracle(oracle, scene, steps):
+@pytest.mark.parametrize("scene,steps,K", [("heijn", (0, 3, 6, 9), 48), ("boxer", (0, 4, 7, 9), 48), ("pick", (0, 10, 20, 29), 12)])
+def test_whole_contact_step_matches_the_oracle(oracle, scene, steps, K):
     """the team kernel's whole step restated in float64 -- tree articulation, contacts in the oracle's order up to the contact
     capacity, Gauss-Seidel over joints + free-body components -- in lock-step with the oracle on the C4 / C3 push scenes while the
-    robot pushes the block (up to 24 contacts per substep)"""
-    wx, wv = proto_team.check_push_scene(scene, verbose=False, steps=steps)
+    robot pushes the block (up to 24 contacts per substep), and on panda_pick (9-joint tree, block on the table)"""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    wx, wv = proto_team.check_push_scene(scene, verbose=False, steps=steps, K=K)
     assert wx < 2e-6 and wv < 2e-5

@@ -531,7 +531,19 @@ def check_push_scene(which="heijn", verbose=True, K=48, steps=(0, 3, 6, 9)):
     from oracle import oracle as orc
     from scenes import boxer_setup, push_setup
     T = 10
-    if which == "heijn":
+    if which == "pick":
+        from test_gpu_sizes import _pick_scene             # panda + gripper (9 joints, tree), block on the table; fingers closing
+        T = 30
+        sc, p, s0 = _pick_scene(K, T)
+        for s_ in range(sc.model.nshapes):                 # per-rollout randomisation off (the restatement has no Philox)
+            sc.model.shape_fric_pct[s_] = 0.0
+            for c_ in range(3):
+                sc.model.shape_size_sigma[s_][c_] = 0.0
+        for f_ in range(sc.model.nfree):
+            sc.model.free_mass_pct[f_] = 0.0
+        a = np.random.default_rng(5).uniform(-0.2, 0.2, (T, sc.nu, K)).astype(np.float32)
+        a[:, 7:9] = -0.15 + 0.05 * a[:, 7:9]
+    elif which == "heijn":
         sc, p, s0 = push_setup(K=K, T=T, noise=False, block_pos=(0.62, 1.5, 0.1))
         a = np.random.default_rng(3).uniform(-0.6, 0.6, (T, 3, K)).astype(np.float32)
         a[:, 0] = 0.5 + 0.1 * a[:, 0]
@@ -544,7 +556,8 @@ def check_push_scene(which="heijn", verbose=True, K=48, steps=(0, 3, 6, 9)):
     NS = orc.lib().oracle_state_size(ctypes.byref(m))
     state = np.zeros((NS, K), np.float32)
     state[:nd2] = s0[:, None]
-    state[nd2:nd2 + 13] = sc.root_state0[1][:, None]
+    free_actor = m.free_actor[0]
+    state[nd2:nd2 + 13] = sc.root_state0[free_actor][:, None]
     worst_x = worst_v = 0.0
     most = 0
     p1 = _one_step(p)
@@ -563,9 +576,9 @@ def check_push_scene(which="heijn", verbose=True, K=48, steps=(0, 3, 6, 9)):
             pos = list(range(nb)) + list(range(nd2, nd2 + 7)); velr = list(range(nb, nd2)) + list(range(nd2 + 7, nd2 + 13))
             worst_x = max(worst_x, np.abs(mine[pos] - refk[pos]).max()); worst_v = max(worst_v, np.abs(mine[velr] - refk[velr]).max())
     if verbose:
-        print(f"{which}_push, lock-step on steps {steps}, {len(range(0, K, 6))} rollouts each: max |position / quaternion difference| = {worst_x:.2e}, "
+        print(f"{'panda_pick' if which == 'pick' else which + '_push'}, lock-step on steps {steps}, {len(range(0, K, 6))} rollouts each: max |position / quaternion difference| = {worst_x:.2e}, "
               f"max |velocity difference| = {worst_v:.2e}; up to {most} contacts per substep")
-    assert most >= 8, "the robot must have been pushing"
+    assert most >= (4 if which == "pick" else 8), "the robot must have been pushing"
     assert worst_x < 2e-6 and worst_v < 2e-5, (worst_x, worst_v)
     return worst_x, worst_v
 
@@ -582,3 +595,4 @@ if __name__ == "__main__":
     check_free_box()
     check_push_scene("heijn")
     check_push_scene("boxer", steps=(0, 4, 7, 9))
+    check_push_scene("pick", K=12, steps=(0, 10, 20, 29))
