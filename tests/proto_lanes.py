@@ -2,7 +2,7 @@
 """float64 numpy restatement of the substep of csrc/rollout_lanes.cu (frames by quaternion scan, composite rigid bodies,
 joint-space LDL^T) checked against the oracle on the host -- a formulation check that needs no GPU.
 
-    python tools/proto_lanes.py
+    python tests/proto_lanes.py
 """
 import os
 import sys

@@ -7,7 +7,7 @@ angular velocity components with scalar inverse inertias, cached rows) against t
 the push scenes (articulation + contacts in the oracle's order up to the capacity + Gauss-Seidel over joints and free-body components)
 in lock-step with the oracle.  Formulation checks that need no GPU (tests/test_proto_team.py runs them):
 
-    python tools/proto_team.py
+    python tests/proto_team.py
 """
 import os
 import sys
@@ -17,7 +17,6 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 from proto_lanes import q2R, qmul, qrot, sym  # noqa: E402
 

@@ -1,6 +1,6 @@
 """CPU (no GPU): the formulation of the K2 team kernel's articulation phase (csrc/rollout_team.cu) -- frames and spatial velocities by
 pointer jumping over the ancestors, composite rigid bodies as differences of suffix sums over the depth-first body order, joint-space
-LDL^T with the leaves eliminated first -- restated in float64 numpy (tools/proto_team.py) and checked against the oracle's body-frame
+LDL^T with the leaves eliminated first -- restated in float64 numpy (tests/proto_team.py) and checked against the oracle's body-frame
 articulated-body algorithm on the tree robots of conf/actors, incl. a rollout driven far beyond the effort limits (saturation
 re-solve) and the planar differential-drive bases.  Also pinned here: the pivots of the leaves-first elimination ARE the
 articulated-body diagonals D_j, which the contact solve uses as the joints' compliance."""
@@ -10,7 +10,7 @@ import sys
 import numpy as np
 import pytest
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import proto_team  # noqa: E402
 
 
