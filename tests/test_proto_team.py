@@ -46,3 +46,9 @@ def test_whole_contact_step_matches_the_oracle(oracle, scene, steps, K):
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     wx, wv = proto_team.check_push_scene(scene, verbose=False, steps=steps, K=K)
     assert wx < 2e-6 and wv < 2e-5
+
+
+def test_lanes_formulation_matches_the_oracle(oracle):
+    """the serial-chain special case (csrc/rollout_lanes.cu: Kogge-Stone scans, distributed LDL^T from the root) -- tests/proto_lanes.py"""
+    import proto_lanes
+    proto_lanes.main()
