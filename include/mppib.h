@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MPPIB_ABI_VERSION 12
+#define MPPIB_ABI_VERSION 13
 
 #define MPPIB_MAX_BODIES 16   /* moving (1-DoF) bodies of the articulation            */
 #define MPPIB_MAX_LINKS  32   /* URDF links whose state can be observed               */
@@ -296,6 +296,10 @@ int64_t mppib_rollout_smem_bytes(const MppibModel* model_h);
 #define MPPIB_MAPPING_LANES  1
 #define MPPIB_MAPPING_TEAM   2
 int32_t mppib_rollout_mapping(MppibHandle h);
+/* The same decision for a model block before a handle exists (host-side arithmetic, no device access; honours the same environment
+ * knobs): lets host code and tests see which scenes each kernel takes -- e.g. a tree whose bodies are not numbered depth first, or one
+ * with more than 16 bodies, stays on the thread-per-rollout kernel.  Returns MPPIB_MAPPING_*, negative on a NULL model.        */
+int32_t mppib_rollout_mapping_for_model(const MppibModel* model_h);
 
 /* Optional host mirror of the action: when set, mppib_finalize also stores action_out[0..nu) to `mirror` -- a pointer into
  * PINNED host memory (device-addressable under unified addressing), so the caller of the reference's compute_action* only

@@ -23,7 +23,7 @@ SYMBOLS = [
     "mppib_abi_version", "mppib_last_error", "mppib_create", "mppib_destroy", "mppib_set_params",
     "mppib_set_model", "mppib_state_size", "mppib_obs_size", "mppib_sample", "mppib_rollout",
     "mppib_reduce", "mppib_finalize", "mppib_shift", "mppib_noise_library", "mppib_sample_library",
-    "mppib_peer_alloc", "mppib_peer_open", "mppib_peer_close", "mppib_cost_pose", "mppib_set_action_mirror", "mppib_reduce_finalize", "mppib_rollout_smem_bytes", "mppib_rollout_mapping",
+    "mppib_peer_alloc", "mppib_peer_open", "mppib_peer_close", "mppib_cost_pose", "mppib_set_action_mirror", "mppib_reduce_finalize", "mppib_rollout_smem_bytes", "mppib_rollout_mapping", "mppib_rollout_mapping_for_model",
 ]
 
 
@@ -146,11 +146,13 @@ class CudaBackend:
         self._check(self.lib.mppib_rollout(self.handle, _ptr(state0), _ptr(root0), _ptr(state), C.c_void_p(base), C.c_int32(t0), C.c_int32(nsteps),
                                            _ptr(obs), self._stream()), "mppib_rollout")
 
+    MAPPING_NAMES = {0: "thread-per-rollout (rollout.cu)", 1: "lanes-per-rollout (rollout_lanes.cu)", 2: "team-of-lanes-per-rollout (rollout_team.cu)"}
+
     def rollout_mapping(self) -> str:
         """Which K2 kernel this handle launches (include/mppib.h MPPIB_MAPPING_*)."""
         r = self.lib.mppib_rollout_mapping(self.handle)
         self._check(min(r, 0), "mppib_rollout_mapping")
-        return {0: "thread-per-rollout (rollout.cu)", 1: "lanes-per-rollout (rollout_lanes.cu)", 2: "team-of-lanes-per-rollout (rollout_team.cu)"}[r]
+        return self.MAPPING_NAMES[r]
 
     # -- multi-GPU exchange over peer memory (include/mppib.h: mppib_peer_*) ----------------------
     def peer_alloc(self, world: int, rank: int) -> bytes:

@@ -73,6 +73,14 @@ extern "C" {
 int32_t mppib_abi_version(void) { return MPPIB_ABI_VERSION; }
 const char* mppib_last_error(void) { return g_err; }
 
+// the K2 mapping knobs of the environment (A/B runs): MPPIB_K2_LANES=0, MPPIB_K2_TEAM=0|1
+static void read_mapping_knobs(MppibContext* c) {
+    c->k2_lanes = 1;
+    if (const char* e = getenv("MPPIB_K2_LANES")) c->k2_lanes = atoi(e) != 0;
+    c->k2_team = -1;
+    if (const char* e = getenv("MPPIB_K2_TEAM")) c->k2_team = atoi(e) < 0 ? -1 : (atoi(e) != 0);
+}
+
 int32_t mppib_create(const MppibModel* model_h, const MppibParams* params_h, int32_t device, MppibHandle* out) {
     MPPIB_REQUIRE(out != nullptr, "null out handle");
     if (int rc = validate(model_h, params_h)) return rc;
@@ -90,10 +98,7 @@ int32_t mppib_create(const MppibModel* model_h, const MppibParams* params_h, int
     c->model = *model_h;
     c->params = *params_h;
     c->num_sms = prop.multiProcessorCount;
-    c->k2_lanes = 1;
-    if (const char* e = getenv("MPPIB_K2_LANES")) c->k2_lanes = atoi(e) != 0;   // read once per handle, not per launch
-    c->k2_team = -1;
-    if (const char* e = getenv("MPPIB_K2_TEAM")) c->k2_team = atoi(e) < 0 ? -1 : (atoi(e) != 0);
+    read_mapping_knobs(c);                                                      // read once per handle, not per launch
     c->k2_pairs = -1;
     if (const char* e = getenv("MPPIB_K2_PAIRS")) c->k2_pairs = atoi(e) != 0;
     c->k3_variant = (getenv("MPPIB_K3_VARIANT") || getenv("MPPIB_K3_WIDE") || getenv("MPPIB_K3_GRID")) ? 1 : 0;
@@ -247,6 +252,17 @@ int32_t mppib_finalize(MppibHandle h, const float* partials, int32_t G, float* U
     }
     MPPIB_ON_DEVICE(h);
     return launch_finalize(h, partials, G, U, action_out, stats, (cudaStream_t)stream);
+}
+
+int32_t mppib_rollout_mapping_for_model(const MppibModel* model_h) {
+    if (!model_h) return -1;
+    MppibContext* c = new MppibContext();       // host arithmetic only: no device is touched
+    memset(c, 0, sizeof(*c));
+    c->model = *model_h;
+    read_mapping_knobs(c);
+    const int mapping = rollout_mapping(c);
+    delete c;
+    return mapping;
 }
 
 int32_t mppib_rollout_mapping(MppibHandle h) {

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """K-sweep of the K2 rollout kernel on the panda reach workload (T = 30, 2 substeps): the lanes-per-rollout mapping
-(csrc/rollout_lanes.cu) against the thread-per-rollout mapping (csrc/rollout.cu, MPPIB_K2_LANES=0).  Device time per launch from
+(csrc/rollout_lanes.cu) against the thread-per-rollout mapping (csrc/rollout.cu, MPPIB_K2_LANES=0 MPPIB_K2_TEAM=0).  Device time per launch from
 graph-captured back-to-back launches (bench.graph_time_us).  Run on the GPU box:
 
     python tools/k2_sweep.py [K ...] > gpurun_out/k2_sweep.md
@@ -23,6 +23,7 @@ KS = [int(a) for a in sys.argv[1:]] or [1252, 2500, 5000, 10000, 20000, 40000, 6
 
 def time_rollout(K, lanes, pairs=None):
     os.environ["MPPIB_K2_LANES"] = "1" if lanes else "0"      # read by mppib_create
+    os.environ["MPPIB_K2_TEAM"] = "0"                         # (a chain is also a tree: without this the team kernel would take it)
     if pairs is None:
         os.environ.pop("MPPIB_K2_PAIRS", None)
     else:

@@ -48,7 +48,10 @@ if world == 1:
     os.environ["MPPIB_K3_VARIANT"] = "auto"           # the block-synchronous K3 (read by mppib_create)
     pl = MPPIisaacPlanner(panda_cfg(K=4100, T=30, device=dev), PandaReachObjective(), use_cuda_graph=False)
     pl.compute_action([0.0, -0.94, 0.0, -2.8, 0.0, 1.8675, 0.0], [0.0] * 7)
-    os.environ["MPPIB_K2_LANES"] = "0"                # the thread-per-rollout chain kernel
+    os.environ["MPPIB_K2_LANES"] = "0"                # a serial chain on the contact-free TEAM kernel (a chain is a tree)
+    pl = MPPIisaacPlanner(panda_cfg(K=512, T=10, device=dev), PandaReachObjective(), use_cuda_graph=False)
+    pl.compute_action([0.0, -0.94, 0.0, -2.8, 0.0, 1.8675, 0.0], [0.0] * 7)
+    os.environ["MPPIB_K2_TEAM"] = "0"                 # ... and on the thread-per-rollout chain kernel
     pl = MPPIisaacPlanner(panda_cfg(K=512, T=10, device=dev), PandaReachObjective(), use_cuda_graph=False)
     pl.compute_action([0.0, -0.94, 0.0, -2.8, 0.0, 1.8675, 0.0], [0.0] * 7)
     os.environ["MPPIB_K2_TEAM"] = "0"                 # the thread-per-rollout contact kernels (chain and tree)
